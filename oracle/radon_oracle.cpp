@@ -1,0 +1,184 @@
+// oracle/radon_oracle.cpp -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+//
+// CPU restatement of (paths relative to /root/reference/LoopDetection/):
+//   torch-radon/src/forward.cu:12-124          radon_forward_kernel<parallel_beam=true, channels, float>
+//   torch-radon/src/texture.cu:135-140         texture: border addressing, linear filter, unnormalised coords
+//   torch-radon/torch_radon/radon.py:139-167   ParallelBeam defaults (det_spacing 1, centred volume, voxel 1)
+//   src/RING_ros/util.py:192-198               RING: angles linspace(0,2pi,120), normalise, fft2(dim=-2,"ortho")
+//   src/RING_ros/util.py:362-374               fast_corr
+// The reference samples the image with the GPU texture unit (cudaFilterModeLinear).  The CUDA
+// programming guide (appendix "Texture Fetching / Linear Filtering") defines it as
+//   tex(x,y) = (1-a)(1-b)T[i,j] + a(1-b)T[i+1,j] + (1-a)b T[i,j+1] + ab T[i+1,j+1],
+//   xB = x-0.5, i = floor(xB), a = frac(xB), with a,b held in 9-bit fixed point (8 fractional bits).
+// weight_bits = 0 evaluates exact fp32 bilinear weights; weight_bits = 8 quantises a,b to 1/256
+// (round to nearest) like the hardware.  fast_trig=1 is reserved for the GPU path's __sinf/__cosf
+// (not reproducible on a CPU); the oracle always uses sinf/cosf.
+//
+// PARITY PIN: torch-radon's own test compares against analytic line integrals with a tolerance of
+// 2e-3*(512/A)*(512/D) (tests/test_parallel_beam.py:70) -- loose; tests/ reuses the reference's
+// analytic oracle (src/symbolic.cpp, compiled unmodified into oracle/_ref) with that tolerance, and
+// on the GPU box the reference kernel itself (forward.cu + texture.cu compiled unmodified into
+// oracle/_ref) is run side by side.
+#include <algorithm>
+#include <cmath>
+#include <complex>
+#include <cstring>
+#include <vector>
+
+namespace {
+
+inline float texel(const float* img, int W, int H, int i, int j) {  // border addressing -> 0
+  return (i >= 0 && i < W && j >= 0 && j < H) ? img[(size_t)j * W + i] : 0.0f;
+}
+
+inline float tex2d(const float* img, int W, int H, float x, float y, int weight_bits) {
+  float xb = x - 0.5f, yb = y - 0.5f;
+  float fi = floorf(xb), fj = floorf(yb);
+  float a = xb - fi, b = yb - fj;
+  if (weight_bits > 0) {
+    float s = (float)(1 << weight_bits);
+    a = rintf(a * s) / s;
+    b = rintf(b * s) / s;
+  }
+  int i = (int)fi, j = (int)fj;
+  float t00 = texel(img, W, H, i, j), t10 = texel(img, W, H, i + 1, j);
+  float t01 = texel(img, W, H, i, j + 1), t11 = texel(img, W, H, i + 1, j + 1);
+  float w00 = (1.0f - a) * (1.0f - b), w10 = a * (1.0f - b), w01 = (1.0f - a) * b, w11 = a * b;
+  return fmaf(w11, t11, fmaf(w01, t01, fmaf(w10, t10, w00 * t00)));
+}
+
+}  // namespace
+
+extern "C" {
+
+// img: [batch][H][W]; angles[n_angles]; out: [batch][n_angles][det_count]
+void orc_radon_forward(const float* img, int batch, int H, int W, const float* angles, int n_angles, int det_count,
+                       float det_spacing, int weight_bits, float* out) {
+  // VolumeCfg for Volume2D(): dx = dy = 0, sx = sy = 1 (torch_radon/volumes.py)
+  const float vdx = 0.f, vdy = 0.f, vsx = 1.f, vsy = 1.f, inv_sx = 1.f, inv_sy = 1.f;
+#pragma omp parallel for collapse(2) schedule(static)
+  for (int bz = 0; bz < batch; bz++)
+    for (int angle_id = 0; angle_id < n_angles; angle_id++) {
+      const float* im = img + (size_t)bz * H * W;
+      for (int ray_id = 0; ray_id < det_count; ray_id++) {
+        float* o = out + ((size_t)bz * n_angles + angle_id) * det_count + ray_id;
+        float sx = (ray_id - det_count * 0.5f + 0.5f) * det_spacing;
+        float sy = hypotf(fabsf(vdx) + W * 0.5f, fabsf(vdy) + H * 0.5f);
+        float ex = sx, ey = -sy;
+        float angle = angles[angle_id];
+        float cs = cosf(angle), sn = sinf(angle);
+        float rsx = fmaf(sy, sn, sx * cs);          // sx*cs + sy*sn
+        float rsy = fmaf(sy, cs, -sx * sn);         // -sx*sn + sy*cs
+        float rdx = fmaf(ey, sn, ex * cs) - rsx;    // ex*cs + ey*sn - rsx
+        float rdy = fmaf(ey, cs, -ex * sn) - rsy;   // -ex*sn + ey*cs - rsy
+        float vol_orig_x = vdx - 0.5f * W * vsx;
+        float vol_orig_y = vdy - 0.5f * H * vsy;
+        rsx = (rsx - vol_orig_x) * inv_sx;
+        rsy = (rsy - vol_orig_y) * inv_sy;
+        rdx = rdx * inv_sx;
+        rdy = rdy * inv_sy;
+        // max(rdx, 1e-6): double literal -> double max -> float
+        float dx = rdx >= 0 ? (float)std::max((double)rdx, 1e-6) : (float)std::min((double)rdx, -1e-6);
+        float dy = rdy >= 0 ? (float)std::max((double)rdy, 1e-6) : (float)std::min((double)rdy, -1e-6);
+        float alpha_x_m = (-rsx) / dx, alpha_x_p = (W - rsx) / dx;
+        float alpha_y_m = (-rsy) / dy, alpha_y_p = (H - rsy) / dy;
+        float alpha_s = std::max(std::min(alpha_x_p, alpha_x_m), std::min(alpha_y_p, alpha_y_m));
+        float alpha_e = std::min(std::max(alpha_x_p, alpha_x_m), std::max(alpha_y_p, alpha_y_m));
+        if ((double)alpha_s > (double)alpha_e - 1e-6) {
+          *o = 0.f;
+          continue;
+        }
+        rsx = fmaf(rdx, alpha_s, rsx);
+        rsy = fmaf(rdy, alpha_s, rsy);
+        rdx *= (alpha_e - alpha_s);
+        rdy *= (alpha_e - alpha_s);
+        float mx = std::max(fabsf(rdx), fabsf(rdy));
+        int n_steps = (int)rintf(mx);
+        float vx = rdx / mx, vy = rdy / mx;
+        float n = hypotf(vx * vsx, vy * vsy);
+        float step;
+        if (fabsf(rdy) >= fabsf(rdx)) {
+          float y_inc = 0.5f - rsy + rintf(rsy);
+          step = y_inc / vy;
+          step += vy < 0;
+        } else {
+          float x_inc = 0.5f - rsx + rintf(rsx);
+          step = x_inc / vx;
+          step += vx < 0;
+        }
+        rsx = fmaf(step, vx, rsx);
+        rsy = fmaf(step, vy, rsy);
+        float acc = 0.f;
+        for (int j = 0; j < n_steps; j++) {
+          acc += tex2d(im, W, H, rsx, rsy, weight_bits);
+          rsx += vx;
+          rsy += vy;
+        }
+        *o = acc * n;
+      }
+    }
+}
+
+// RING tail (util.py:197-198): x = (sino - mean) / std_unbiased over the whole [C,A,D] tensor;
+// TIRING[c,k,d] = 1/sqrt(A) * sum_a x[c,a,d] exp(-2 pi i k a / A).  out: interleaved re,im float.
+void orc_ring_tiring(const float* sino, int C, int A, int D, float* out_norm, float* out_tiring) {
+  size_t n = (size_t)C * A * D;
+  double s = 0;
+  for (size_t i = 0; i < n; i++) s += sino[i];
+  double mean = s / (double)n;
+  double ss = 0;
+  for (size_t i = 0; i < n; i++) ss += ((double)sino[i] - mean) * ((double)sino[i] - mean);
+  double sd = std::sqrt(ss / (double)(n - 1));
+  float fmean = (float)mean, fsd = (float)sd;
+  std::vector<float> x(n);
+  for (size_t i = 0; i < n; i++) x[i] = (sino[i] - fmean) / fsd;
+  if (out_norm) memcpy(out_norm, x.data(), n * sizeof(float));
+  const double scale = 1.0 / std::sqrt((double)A);
+#pragma omp parallel for collapse(2) schedule(static)
+  for (int c = 0; c < C; c++)
+    for (int k = 0; k < A; k++)
+      for (int d = 0; d < D; d++) {
+        double re = 0, im = 0;
+        for (int a = 0; a < A; a++) {
+          double ph = -2.0 * M_PI * (double)((long)k * a % A) / (double)A;
+          double v = x[((size_t)c * A + a) * D + d];
+          re += v * std::cos(ph);
+          im += v * std::sin(ph);
+        }
+        size_t o = (((size_t)c * A + k) * D + d) * 2;
+        out_tiring[o] = (float)(re * scale);
+        out_tiring[o + 1] = (float)(im * scale);
+      }
+}
+
+// fast_corr (util.py:362-374): a,b complex [C,A,D] (interleaved). corr_out[A] (after fftshift), returns via pointers
+void orc_ring_fast_corr(const float* a, const float* b, int C, int A, int D, float* corr_out, float* dist, int* angle) {
+  std::vector<double> corr(A, 0.0);
+  const double scale = 1.0 / std::sqrt((double)A);
+  for (int c = 0; c < C; c++)
+    for (int d = 0; d < D; d++)
+      for (int t = 0; t < A; t++) {
+        double re = 0, im = 0;
+        for (int k = 0; k < A; k++) {
+          size_t o = (((size_t)c * A + k) * D + d) * 2;
+          double ar = a[o], ai = a[o + 1], br = b[o], bi = -b[o + 1];  // conj(b)
+          double pr = ar * br - ai * bi, pi = ar * bi + ai * br;
+          double ph = 2.0 * M_PI * (double)((long)k * t % A) / (double)A;
+          double cs = std::cos(ph), sn = std::sin(ph);
+          re += pr * cs - pi * sn;
+          im += pr * sn + pi * cs;
+        }
+        corr[t] += std::sqrt(re * re + im * im) * scale;
+      }
+  // fftshift1d: roll by A/2 (A even): out[i] = corr[(i + A - A/2) % A]  (util.py:330-337 cat(back, front) with n = ceil(A/2))
+  int nsh = (A + 1) / 2;
+  std::vector<double> sh(A);
+  for (int i = 0; i < A; i++) sh[i] = corr[(i + nsh) % A];
+  int am = 0;
+  for (int i = 1; i < A; i++)
+    if ((float)sh[i] > (float)sh[am]) am = i;
+  for (int i = 0; i < A; i++) corr_out[i] = (float)sh[i];
+  *dist = 1.0f - (float)sh[am] / (float)(0.15 * A * D);
+  *angle = -am + A / 2;
+}
+}
