@@ -1,0 +1,193 @@
+/* mrslam_b200.h -- C-ABI of the B200-native MR_SLAM hot path (libmrslam_b200.so).
+ *
+ * Plain C, opaque handles, plain pointers and sizes, int status codes (0 = OK, <0 = error; the
+ * message of the last error on the calling thread is returned by mrslam_last_error()).  No
+ * exceptions cross this boundary.  All 4x4 matrices are ROW-MAJOR float[16] / double[16]
+ * (Eigen's default is column-major: the C++ adapters in include/ transpose).
+ *
+ * Every entry point names the reference interface it replaces (paths relative to the MR_SLAM
+ * tree; FG = Mapping/src/fast_gicp, EM = Mapping/src/elevation_mapping_periodical/elevation_mapping,
+ * BEV = LoopDetection/generate_bev_cython_binary, DISCO = LoopDetection/src/disco_ros,
+ * TR = LoopDetection/torch-radon, RING = LoopDetection/src/RING_ros).
+ *
+ * There is NO CPU fallback behind this ABI: every compute entry point launches sm_100a kernels
+ * and fails with MRSLAM_ERR_CUDA when no usable device is present.
+ */
+#ifndef MRSLAM_B200_H
+#define MRSLAM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MRSLAM_OK 0
+#define MRSLAM_ERR_CUDA (-1)     /* CUDA runtime error / no device */
+#define MRSLAM_ERR_ARG (-2)      /* bad argument */
+#define MRSLAM_ERR_STATE (-3)    /* call order (e.g. align before inputs are set) */
+#define MRSLAM_ERR_NOTCONV (-4)  /* LM failed ("lm not converged!!" in the reference; result still readable) */
+
+/* ------------------------------------------------------------------------------------------ */
+/* runtime                                                                                     */
+/* ------------------------------------------------------------------------------------------ */
+int mrslam_init(int device);                 /* cudaSetDevice + stream/pool set-up; idempotent */
+const char* mrslam_last_error(void);
+const char* mrslam_version(void);
+int mrslam_device_synchronize(void);
+void* mrslam_stream(void);                   /* the cudaStream_t every kernel of this library is launched on */
+/* instrumentation: kernels launched by this library since process start (bench.py "gpu_launches") */
+unsigned long long mrslam_kernel_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------ */
+/* FastGICP  --  replaces fast_gicp::FastGICP<PointSource,PointTarget>                          */
+/*   FG/include/fast_gicp/gicp/fast_gicp.hpp:19-100, lsq_registration.hpp:15-85                 */
+/*   FG/include/fast_gicp/gicp/impl/fast_gicp_impl.hpp:9-298, impl/lsq_registration_impl.hpp    */
+/*   python: FG/src/python/main.cpp:152-190 (pygicp)                                            */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct mrslam_gicp mrslam_gicp_t;
+typedef struct mrslam_cloud mrslam_cloud_t;  /* device-resident cloud + spatial tiles + cached covariances */
+
+/* RegularizationMethod, FG/include/fast_gicp/gicp/gicp_settings.hpp:6 (same order) */
+enum { MRSLAM_REG_NONE = 0, MRSLAM_REG_MIN_EIG = 1, MRSLAM_REG_NORMALIZED_MIN_EIG = 2, MRSLAM_REG_PLANE = 3, MRSLAM_REG_FROBENIUS = 4 };
+/* LSQ_OPTIMIZER_TYPE, FG/include/fast_gicp/gicp/lsq_registration.hpp:13 */
+enum { MRSLAM_OPT_LM = 0, MRSLAM_OPT_GN = 1 };
+
+/* clouds: `xyz` points at the first float of the first point, consecutive points are
+ * `stride_floats` floats apart (3 = packed xyz, 4 = pcl::PointXYZ, 8 = pcl::PointXYZI / PointNormal). */
+mrslam_cloud_t* mrslam_cloud_create_host(const float* xyz, int n, int stride_floats);
+mrslam_cloud_t* mrslam_cloud_create_device(const float* d_xyz, int n, int stride_floats); /* device pointer (e.g. NCCL recv buffer) */
+void mrslam_cloud_destroy(mrslam_cloud_t*);
+int mrslam_cloud_size(const mrslam_cloud_t*);
+
+mrslam_gicp_t* mrslam_gicp_create(void);                              /* FastGICP() ctor: fast_gicp_impl.hpp:9-24 defaults */
+void mrslam_gicp_destroy(mrslam_gicp_t*);
+int mrslam_gicp_set_num_threads(mrslam_gicp_t*, int n);               /* setNumThreads: accepted, no effect on the GPU */
+int mrslam_gicp_set_correspondence_randomness(mrslam_gicp_t*, int k); /* setCorrespondenceRandomness (1..32) */
+int mrslam_gicp_set_regularization_method(mrslam_gicp_t*, int method);
+int mrslam_gicp_set_max_correspondence_distance(mrslam_gicp_t*, double d); /* pcl::Registration::setMaxCorrespondenceDistance */
+int mrslam_gicp_set_maximum_iterations(mrslam_gicp_t*, int n);        /* pcl::Registration::setMaximumIterations */
+int mrslam_gicp_set_transformation_epsilon(mrslam_gicp_t*, double e); /* pcl::Registration::setTransformationEpsilon */
+int mrslam_gicp_set_rotation_epsilon(mrslam_gicp_t*, double e);       /* LsqRegistration::setRotationEpsilon */
+int mrslam_gicp_set_initial_lambda_factor(mrslam_gicp_t*, double f);  /* LsqRegistration::setInitialLambdaFactor */
+int mrslam_gicp_set_lsq_optimizer(mrslam_gicp_t*, int type);
+int mrslam_gicp_set_debug_print(mrslam_gicp_t*, int on);              /* LsqRegistration::setDebugPrint */
+
+int mrslam_gicp_set_input_source(mrslam_gicp_t*, const float* xyz, int n, int stride_floats); /* setInputSource (host) */
+int mrslam_gicp_set_input_target(mrslam_gicp_t*, const float* xyz, int n, int stride_floats); /* setInputTarget (host) */
+/* share a device-resident cloud (and its cached covariances) between registrations; not owned by the handle */
+int mrslam_gicp_set_input_source_cloud(mrslam_gicp_t*, mrslam_cloud_t*);
+int mrslam_gicp_set_input_target_cloud(mrslam_gicp_t*, mrslam_cloud_t*);
+int mrslam_gicp_swap_source_and_target(mrslam_gicp_t*);               /* swapSourceAndTarget */
+int mrslam_gicp_clear_source(mrslam_gicp_t*);                         /* clearSource */
+int mrslam_gicp_clear_target(mrslam_gicp_t*);                         /* clearTarget */
+/* set/getSource/TargetCovariances: n x 16 doubles, each a ROW-MAJOR 4x4 (4th row/col zero) */
+int mrslam_gicp_set_source_covariances(mrslam_gicp_t*, const double* cov4x4, int n);
+int mrslam_gicp_set_target_covariances(mrslam_gicp_t*, const double* cov4x4, int n);
+int mrslam_gicp_get_source_covariances(mrslam_gicp_t*, double* cov4x4, int n); /* computes them if needed */
+int mrslam_gicp_get_target_covariances(mrslam_gicp_t*, double* cov4x4, int n);
+
+/* pcl::Registration::align(output, guess) -> FastGICP::computeTransformation (fast_gicp_impl.hpp:103-112).
+ * guess16 may be NULL (identity).  Returns MRSLAM_OK or MRSLAM_ERR_NOTCONV. */
+int mrslam_gicp_align(mrslam_gicp_t*, const float* guess16);
+/* n registrations advanced in lock step (one kernel launch per LM phase for the whole batch):
+ * the loop-closure-storm entry point (BASELINE configs 2 and 4).  guesses16: n x 16 or NULL. */
+int mrslam_gicp_align_batch(mrslam_gicp_t** handles, int n, const float* guesses16);
+
+int mrslam_gicp_get_final_transformation(const mrslam_gicp_t*, float* T16);   /* getFinalTransformation (x0.cast<float>()) */
+int mrslam_gicp_get_final_transformation_d(const mrslam_gicp_t*, double* T16);
+int mrslam_gicp_has_converged(const mrslam_gicp_t*);                          /* hasConverged */
+int mrslam_gicp_get_num_iterations(const mrslam_gicp_t*);                     /* nr_iterations_ */
+int mrslam_gicp_get_final_hessian(const mrslam_gicp_t*, double* H36);         /* getFinalHessian */
+int mrslam_gicp_get_eval_counts(const mrslam_gicp_t*, int* n_linearize, int* n_error);
+/* pcl::Registration::getFitnessScore(max_range): mean NN squared distance <= max_range after final_transformation_ */
+double mrslam_gicp_get_fitness_score(mrslam_gicp_t*, double max_range);
+int mrslam_gicp_get_fitness_score_batch(mrslam_gicp_t** handles, int n, double max_range, double* out);
+/* `output` cloud of align(): the source transformed by final_transformation_ (lsq_registration_impl.hpp:78) */
+int mrslam_gicp_get_aligned(mrslam_gicp_t*, float* xyz_out, int stride_floats);
+/* LsqRegistration::evaluateCost(relative_pose, H, b) -> linearize (H36/b6 may be NULL) */
+int mrslam_gicp_evaluate_cost(mrslam_gicp_t*, const float* T16, double* H36, double* b6, double* cost);
+/* test hooks: state of the last linearisation in SOURCE ORIGINAL ORDER (corr = target original index or -1) */
+int mrslam_gicp_debug_last_correspondences(mrslam_gicp_t*, int* corr, float* sq_dist, double* mahalanobis9);
+int mrslam_gicp_compute_error(mrslam_gicp_t*, const double* T16, double* cost); /* FastGICP::compute_error */
+/* kNN building block (calculate_covariances' search): indices (original order) and squared distances, n x k */
+int mrslam_cloud_knn(mrslam_cloud_t*, int k, int* idx_out, float* sqd_out);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Elevation mapping -- replaces the free functions of EM/cuda/gpu_process.cu (libgpu.so)      */
+/*   declared at EM/src/ElevationMapping.cpp:44-50, SensorProcessorBase.cpp:34,                 */
+/*   RobotMotionMapUpdater.cpp:18.  One hidden map per handle (the reference: one per process). */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct mrslam_elev mrslam_elev_t;
+mrslam_elev_t* mrslam_elev_create(void);
+void mrslam_elev_destroy(mrslam_elev_t*);
+/* Init_GPU_elevationmap(length, resolution, mahalanobisThr, obstacle_threshold)  gpu_process.cu:938 */
+int mrslam_elev_init(mrslam_elev_t*, int length, float resolution, float mahalanobis_thr, float obstacle_thr);
+/* Move(current_Position[3], resolution, length, central_coordinate_out[2], start_indice_out[2], position_shift_out[2])  :1002 */
+int mrslam_elev_move(mrslam_elev_t*, const float* current_position3, float resolution, int length, float* central_out2,
+                     int* start_out2, float* shift_out2);
+/* Process_points(map_index, x, y, z, var, x_ts, y_ts, z_ts, T, n, lower, upper, min_r, beam_a, beam_c,
+ *                sensorJacobian, rotationVariance, C_SB_transpose, P_mul_C_BM_transpose, B_r_BS_skew)   :1083
+ * Eigen arguments are passed as ROW-MAJOR float arrays (T 4x4, 1x3, 3x3, 3x3, 1x3, 3x3). All point arrays are HOST. */
+int mrslam_elev_process_points(mrslam_elev_t*, int* map_index, const float* x, const float* y, const float* z, float* var,
+                               float* x_ts, float* y_ts, float* z_ts, const float* T16, int n, double lower, double upper,
+                               float min_r, float beam_a, float beam_c, const float* sensorJacobian3,
+                               const float* rotationVariance9, const float* C_SB_transpose9,
+                               const float* P_mul_C_BM_transpose3, const float* B_r_BS_skew9);
+/* Fuse(length, n, idx, R, G, B, intensity, height, var)   :1152   (host arrays); returns #cell fuses in *n_fused (may be NULL) */
+int mrslam_elev_fuse(mrslam_elev_t*, int length, int n, const int* idx, const int* R, const int* G, const int* B,
+                     const float* intensity, const float* height, const float* var, long long* n_fused);
+/* device-resident fast path: Process_points + Fuse in one call on device arrays (x,y,z SoA device pointers;
+ * colour/intensity may be NULL = 0).  near_filter=1 keeps the reference's hard-coded sensor-frame filter (:393). */
+int mrslam_elev_process_fuse_device(mrslam_elev_t*, const float* d_x, const float* d_y, const float* d_z, int n,
+                                    const float* T16, double lower, double upper, float min_r, float beam_a, float beam_c,
+                                    const float* sensorJacobian3, const float* rotationVariance9, const float* C_SB_transpose9,
+                                    const float* P_mul_C_BM_transpose3, const float* B_r_BS_skew9, int near_filter,
+                                    long long* n_fused);
+int mrslam_elev_mapvar_update(mrslam_elev_t*, int length, float var_update);          /* Mapvar_update  :1144 */
+int mrslam_elev_map_optmove(mrslam_elev_t*, const float* opt_p, float height_update, float resolution, int length,
+                            float* opt_aligned_position2);                             /* Map_optmove    :1213 */
+int mrslam_elev_map_closeloop(mrslam_elev_t*, const float* update_position, float height_update, int length,
+                              float resolution);                                       /* Map_closeloop  :1233 */
+/* read back the hidden map (any pointer may be NULL); length*length entries each, storage (ring-buffer) order */
+int mrslam_elev_get_map(mrslam_elev_t*, float* elevation, float* variance, float* intensity, int* R, int* G, int* B,
+                        float* lowest);
+int mrslam_elev_get_state(mrslam_elev_t*, float* central2, int* start2);
+
+/* ------------------------------------------------------------------------------------------ */
+/* BEV voxelisers -- replace GPUTransformer of voxelocc (BEV/src/manager.hh, wrapper.pyx:13-39) */
+/* and gputransform (DISCO/tools/multi-layer-polar-gpu/cython/src/manager.hh).                  */
+/* point: SoA float[3*size] (x.., y.., z..) HOST; out: HOST float[num_x*num_y*num_height*enough_large*3] */
+/* ------------------------------------------------------------------------------------------ */
+int mrslam_voxelocc_transform(const float* point, int size, int max_length, int max_height, int num_x, int num_y,
+                              int num_height, int enough_large, float* out);
+int mrslam_polar_transform(const float* point, int size, int max_length, int max_height, int num_ring, int num_sector,
+                           int num_height, int enough_large, float* out);
+/* device batch variant used by the RING pipeline: points SoA per scan on the device, offsets[b]..offsets[b+1];
+ * writes only what generate_RING keeps (channel 2, the max-height image) as d_bev[batch][num_x][num_y]. */
+int mrslam_voxelocc_bev_device(const float* d_points_soa, const long long* offsets_host, int batch, int max_length,
+                               int max_height, int num_x, int num_y, float* d_bev);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Radon / RING -- replace torch_radon.ParallelBeam.forward (TR/torch_radon/radon.py:62-87,      */
+/* TR/src/forward.cu:12-178) and the RING descriptor tail + matcher (RING/util.py:192-198,362-374) */
+/* All pointers are DEVICE pointers (torch CUDA tensors' data_ptr on the python side).            */
+/* ------------------------------------------------------------------------------------------ */
+/* interp: 0 = exact fp32 bilinear, 1 = texture-unit emulation (8-bit fractional weights);
+ * fast_trig: 1 = __sinf/__cosf as the reference kernel, 0 = sinf/cosf. */
+int mrslam_radon_forward(const float* d_img, int batch, int height, int width, const float* d_angles, int n_angles,
+                         int det_count, float det_spacing, int interp, int fast_trig, float* d_sino);
+/* normalise (mean / unbiased std over each [C,A,D] item) + ortho FFT along the angle axis; out complex64 interleaved */
+int mrslam_ring_tiring(const float* d_sino, int items, int channels, int n_angles, int det_count, float* d_tiring);
+/* fast_corr of query q against `n_db` database descriptors: dist[n_db], angle[n_db] (device) */
+int mrslam_ring_fast_corr(const float* d_query, const float* d_db, int n_db, int channels, int n_angles, int det_count,
+                          float* d_dist, int* d_angle, float* d_corr_opt);
+/* fused generate_RING for a batch of BEV images: Radon -> normalise -> FFT (one kernel per image) */
+int mrslam_ring_generate(const float* d_bev, int batch, int size, const float* d_angles, int n_angles, int interp,
+                         int fast_trig, float* d_sino_opt, float* d_tiring);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MRSLAM_B200_H */

@@ -1,0 +1,146 @@
+// common.cuh -- shared host/device helpers of libmrslam_b200 (sm_100a only).
+// Build policy: every TU is compiled with -fmad=false; fused multiply-adds are written
+// explicitly (fmaf / fma) so the arithmetic is the same expression tree as the CPU oracle's.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cfloat>
+#include <climits>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/mrslam_b200.h"
+
+namespace mrslam {
+
+// ---- error plumbing (no exceptions across the C-ABI) -------------------------------------
+void set_error(const char* fmt, ...);
+extern thread_local int g_status;
+
+#define MR_CUDA(expr)                                                                          \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess) {                                                                   \
+      mrslam::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return MRSLAM_ERR_CUDA;                                                                  \
+    }                                                                                          \
+  } while (0)
+
+#define MR_CUDA_NULL(expr)                                                                     \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess) {                                                                   \
+      mrslam::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return nullptr;                                                                          \
+    }                                                                                          \
+  } while (0)
+
+#define MR_CHECK(call)            \
+  do {                            \
+    int _s = (call);              \
+    if (_s != MRSLAM_OK) return _s; \
+  } while (0)
+
+// ---- runtime singleton: device, stream, memory pool, launch counter ------------------------
+struct Runtime {
+  int device = -1;
+  cudaStream_t stream = nullptr;
+  int sm_count = 148;
+  std::atomic<unsigned long long> launches{0};
+  std::mutex mu;  // serialises host-side drivers that share the stream
+};
+Runtime& rt();
+int ensure_init();  // MRSLAM_OK or error (no device -> MRSLAM_ERR_CUDA; never a CPU fallback)
+
+inline void count_launch(int n = 1) { rt().launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+
+// stream-ordered device buffer (cudaMallocAsync pool; grow-only)
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t n) {
+    if (n <= cap) return MRSLAM_OK;
+    if (p) MR_CUDA(cudaFreeAsync(p, rt().stream));
+    p = nullptr;
+    cap = 0;
+    size_t want = n + n / 8 + 64;
+    MR_CUDA(cudaMallocAsync((void**)&p, want * sizeof(T), rt().stream));
+    cap = want;
+    return MRSLAM_OK;
+  }
+  void release() {
+    if (p) cudaFreeAsync(p, rt().stream);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+// pinned host buffer (grow-only)
+template <typename T>
+struct PinBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t n) {
+    if (n <= cap) return MRSLAM_OK;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = n + n / 8 + 64;
+    MR_CUDA(cudaMallocHost((void**)&p, want * sizeof(T)));
+    cap = want;
+    return MRSLAM_OK;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+// ---- device helpers --------------------------------------------------------------------------
+#ifdef __CUDACC__
+constexpr unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(FULL, v, o));
+  return v;
+}
+// fixed-order butterfly: bitwise deterministic
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  return v;
+}
+// squared distance, the one convention shared with the oracle: fmaf(dz,dz, fmaf(dy,dy, dx*dx))
+__device__ __forceinline__ float dist2(float qx, float qy, float qz, float px, float py, float pz) {
+  float dx = qx - px, dy = qy - py, dz = qz - pz;
+  return fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+}
+// float transform of a point: fmaf(m2,z, fmaf(m1,y, m0*x)) + m3  (row r of a row-major 3x4)
+__device__ __forceinline__ float xform_row(const float* m, float x, float y, float z) {
+  return fmaf(m[2], z, fmaf(m[1], y, m[0] * x)) + m[3];
+}
+// order-preserving float <-> uint mapping for atomicMin/Max on floats
+__device__ __forceinline__ unsigned f2ord(float f) {
+  unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(unsigned u) {
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+#endif
+
+}  // namespace mrslam

@@ -1,0 +1,757 @@
+// gicp_kernels.cuh -- sm_100a kernels of the FastGICP path.
+//
+// Data layout in HBM (per cloud):
+//   porig  float4[n]        original order (x,y,z,1)
+//   psort  float4[npad]     Morton-sorted copy, w = bit pattern of the ORIGINAL index (tie-breaks);
+//                           padded to a multiple of 32 with far-away sentinels (w = INT_MAX)
+//   tb     float[6][ntp]    per 32-point tile bounding boxes (SoA: minx,miny,minz,maxx,maxy,maxz)
+//   cov    double[npad][6]  regularised covariances in SORTED order (xx,xy,xz,yy,yz,zz)
+//
+// Search scheme ("shared-memory-tiled brute force with culling", no tree): one warp owns 32
+// spatially coherent queries (one tile).  Candidate tiles are staged through shared memory and
+// every query of the warp is compared against every point of the tile (brute force inside a
+// tile); a tile is skipped only when its bounding box is provably farther from the warp's
+// bounding box than the warp's current worst k-th distance.  The result is the exact kNN under
+// the (distance, original index) order -- identical to an exhaustive scan.
+#pragma once
+#include "common.cuh"
+
+namespace mrslam {
+
+constexpr int TILE = 32;
+constexpr int PAD_IDX = INT_MAX;
+constexpr float PAD_COORD = 3.0e18f;
+constexpr float CULL_SAFETY = 0.99999f;  // box distance is a lower bound only up to a few ulp
+constexpr int HOME_RADIUS = 2;           // tiles qt-2..qt+2 are searched first (they seed the cull radius)
+constexpr int NRED = 28;                 // 21 (H upper) + 6 (b) + 1 (cost)
+
+// ---------------------------------------------------------------------------------------------
+// cloud preparation
+// ---------------------------------------------------------------------------------------------
+__global__ void k_pack_points(const float* __restrict__ raw, int n, int stride, float4* __restrict__ porig) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* p = raw + (size_t)i * stride;
+  porig[i] = make_float4(p[0], p[1], p[2], 1.0f);
+}
+
+__global__ void k_bbox_init(unsigned* bb) {
+  if (threadIdx.x < 3) bb[threadIdx.x] = 0xffffffffu;
+  else if (threadIdx.x < 6) bb[threadIdx.x] = 0u;
+}
+
+__global__ void k_bbox(const float4* __restrict__ p, int n, unsigned* bb) {
+  float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float4 v = p[i];
+    if (isfinite(v.x) && isfinite(v.y) && isfinite(v.z)) {
+      mn[0] = fminf(mn[0], v.x); mn[1] = fminf(mn[1], v.y); mn[2] = fminf(mn[2], v.z);
+      mx[0] = fmaxf(mx[0], v.x); mx[1] = fmaxf(mx[1], v.y); mx[2] = fmaxf(mx[2], v.z);
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+    mn[a] = warp_min(mn[a]);
+    mx[a] = warp_max(mx[a]);
+  }
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      atomicMin(&bb[a], f2ord(mn[a]));
+      atomicMax(&bb[3 + a], f2ord(mx[a]));
+    }
+  }
+}
+
+__device__ __forceinline__ unsigned long long spread16(unsigned v) {  // 16 bits -> every 3rd bit
+  unsigned long long x = v & 0xffffu;
+  x = (x | x << 16) & 0x0000ff0000ffull;
+  x = (x | x << 8) & 0x00f00f00f00full;
+  x = (x | x << 4) & 0x0c30c30c30c3ull;
+  x = (x | x << 2) & 0x249249249249ull;
+  return x;
+}
+
+__global__ void k_morton(const float4* __restrict__ p, int n, const unsigned* __restrict__ bb, unsigned long long* keys, int* vals) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float mn[3] = {ord2f(bb[0]), ord2f(bb[1]), ord2f(bb[2])};
+  float mx[3] = {ord2f(bb[3]), ord2f(bb[4]), ord2f(bb[5])};
+  float ext = fmaxf(fmaxf(mx[0] - mn[0], mx[1] - mn[1]), fmaxf(mx[2] - mn[2], 1e-6f));
+  float s = 65535.0f / ext;
+  float4 v = p[i];
+  float c[3] = {v.x, v.y, v.z};
+  unsigned q[3];
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+    float f = (c[a] - mn[a]) * s;
+    f = isfinite(f) ? fminf(fmaxf(f, 0.0f), 65535.0f) : 65535.0f;
+    q[a] = (unsigned)f;
+  }
+  keys[i] = spread16(q[0]) | (spread16(q[1]) << 1) | (spread16(q[2]) << 2);
+  vals[i] = i;
+}
+
+// one warp per tile: gather the sorted points, pad, and reduce the tile's bounding box
+__global__ void k_gather_tiles(const float4* __restrict__ porig, const int* __restrict__ order, int n, int ntiles, int ntiles_pad,
+                               float4* __restrict__ psort, float* __restrict__ tb) {
+  int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (t >= ntiles_pad) return;
+  float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  if (t < ntiles) {
+    int s = t * TILE + lane;
+    float4 v;
+    if (s < n) {
+      int o = order[s];
+      v = porig[o];
+      v.w = __int_as_float(o);
+      mn[0] = mx[0] = v.x; mn[1] = mx[1] = v.y; mn[2] = mx[2] = v.z;
+    } else {
+      v = make_float4(PAD_COORD, PAD_COORD, PAD_COORD, __int_as_float(PAD_IDX));
+    }
+    psort[s] = v;
+  }
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+    mn[a] = warp_min(mn[a]);
+    mx[a] = warp_max(mx[a]);
+  }
+  if (lane == 0) {
+    bool real = t < ntiles;
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      tb[(size_t)a * ntiles_pad + t] = real ? mn[a] : PAD_COORD;
+      tb[(size_t)(3 + a) * ntiles_pad + t] = real ? mx[a] : PAD_COORD;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// shared search pieces
+// ---------------------------------------------------------------------------------------------
+struct Box {
+  float mnx, mny, mnz, mxx, mxy, mxz;
+};
+
+__device__ __forceinline__ float box_dist2(const Box& a, float mnx, float mny, float mnz, float mxx, float mxy, float mxz) {
+  float gx = fmaxf(0.0f, fmaxf(mnx - a.mxx, a.mnx - mxx));
+  float gy = fmaxf(0.0f, fmaxf(mny - a.mxy, a.mny - mxy));
+  float gz = fmaxf(0.0f, fmaxf(mnz - a.mxz, a.mnz - mxz));
+  return gx * gx + gy * gy + gz * gz;
+}
+__device__ __forceinline__ float tile_box_dist2(const Box& a, const float* __restrict__ tb, int ntp, int t) {
+  return box_dist2(a, tb[t], tb[ntp + t], tb[2 * ntp + t], tb[3 * ntp + t], tb[4 * ntp + t], tb[5 * ntp + t]);
+}
+
+template <int KC>
+struct TopK {
+  float d[KC];
+  int i[KC];
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int j = 0; j < KC; j++) {
+      d[j] = INFINITY;
+      i[j] = PAD_IDX;
+    }
+  }
+  __device__ __forceinline__ bool qualifies(float cd, int ci) const { return cd < d[KC - 1] || (cd == d[KC - 1] && ci < i[KC - 1]); }
+  // sorted insertion, ascending (distance, index)
+  __device__ __forceinline__ void insert(float cd, int ci) {
+#pragma unroll
+    for (int j = KC - 1; j > 0; --j) {
+      bool before_prev = cd < d[j - 1] || (cd == d[j - 1] && ci < i[j - 1]);
+      bool before_this = cd < d[j] || (cd == d[j] && ci < i[j]);
+      float nd = before_prev ? d[j - 1] : (before_this ? cd : d[j]);
+      int ni = before_prev ? i[j - 1] : (before_this ? ci : i[j]);
+      d[j] = nd;
+      i[j] = ni;
+    }
+    bool b0 = cd < d[0] || (cd == d[0] && ci < i[0]);
+    if (b0) {
+      d[0] = cd;
+      i[0] = ci;
+    }
+  }
+};
+
+// symmetric 3x3 eigen-decomposition, cyclic Jacobi (double); eigenvalues descending; same operation
+// order as the oracle's sym_eig3 so that covariances agree bit for bit.
+__device__ __forceinline__ void sym_eig3(const double A[9], double w[3], double V[9]) {
+  double a[9];
+#pragma unroll
+  for (int i = 0; i < 9; i++) {
+    a[i] = A[i];
+    V[i] = (i % 4 == 0) ? 1.0 : 0.0;
+  }
+  for (int sweep = 0; sweep < 32; sweep++) {
+    double off = a[1] * a[1] + a[2] * a[2] + a[5] * a[5];
+    double diag = a[0] * a[0] + a[4] * a[4] + a[8] * a[8];
+    if (off <= 1e-34 * diag || off == 0.0) break;
+#pragma unroll
+    for (int p = 0; p < 2; p++)
+#pragma unroll
+      for (int q = p + 1; q < 3; q++) {
+        double apq = a[3 * p + q];
+        if (apq == 0.0) continue;
+        double theta = (a[3 * q + q] - a[3 * p + p]) / (2.0 * apq);
+        double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+        double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          double akp = a[3 * k + p], akq = a[3 * k + q];
+          a[3 * k + p] = c * akp - s * akq;
+          a[3 * k + q] = s * akp + c * akq;
+        }
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          double apk = a[3 * p + k], aqk = a[3 * q + k];
+          a[3 * p + k] = c * apk - s * aqk;
+          a[3 * q + k] = s * apk + c * aqk;
+        }
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          double vkp = V[3 * k + p], vkq = V[3 * k + q];
+          V[3 * k + p] = c * vkp - s * vkq;
+          V[3 * k + q] = s * vkp + c * vkq;
+        }
+      }
+  }
+  double e0 = a[0], e1 = a[4], e2 = a[8];
+  // stable selection of the descending order (matches std::sort on 3 distinct values)
+  int o0 = 0, o1 = 1, o2 = 2;
+  double w0 = e0, w1 = e1, w2 = e2;
+  if (w1 > w0) { double tw = w0; w0 = w1; w1 = tw; int to = o0; o0 = o1; o1 = to; }
+  if (w2 > w1) { double tw = w1; w1 = w2; w2 = tw; int to = o1; o1 = o2; o2 = to; }
+  if (w1 > w0) { double tw = w0; w0 = w1; w1 = tw; int to = o0; o0 = o1; o1 = to; }
+  w[0] = w0; w[1] = w1; w[2] = w2;
+  double V2[9];
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    V2[3 * i + 0] = V[3 * i + o0];
+    V2[3 * i + 1] = V[3 * i + o1];
+    V2[3 * i + 2] = V[3 * i + o2];
+  }
+#pragma unroll
+  for (int i = 0; i < 9; i++) V[i] = V2[i];
+}
+
+// inverse of a 3x3 given row-major a[9]; same expression order as the oracle's inverse3
+__device__ __forceinline__ void inverse3(const double a[9], double r[9]) {
+  double c00 = a[4] * a[8] - a[5] * a[7];
+  double c01 = a[5] * a[6] - a[3] * a[8];
+  double c02 = a[3] * a[7] - a[4] * a[6];
+  double det = a[0] * c00 + a[1] * c01 + a[2] * c02;
+  double id = 1.0 / det;
+  r[0] = c00 * id;
+  r[1] = (a[2] * a[7] - a[1] * a[8]) * id;
+  r[2] = (a[1] * a[5] - a[2] * a[4]) * id;
+  r[3] = c01 * id;
+  r[4] = (a[0] * a[8] - a[2] * a[6]) * id;
+  r[5] = (a[2] * a[3] - a[0] * a[5]) * id;
+  r[6] = c02 * id;
+  r[7] = (a[1] * a[6] - a[0] * a[7]) * id;
+  r[8] = (a[0] * a[4] - a[1] * a[3]) * id;
+}
+
+// ---------------------------------------------------------------------------------------------
+// kNN (k <= KC) + covariance + regularisation.   grid.x = ceil(ntiles/4), block = 128 (4 warps).
+// fast_gicp_impl.hpp:241-298 (calculate_covariances); GPU precedent brute_force_knn.cu:16-60 +
+// covariance_estimation.cu:16-42 + covariance_regularization.cu:14-97.
+// ---------------------------------------------------------------------------------------------
+struct KnnParams {
+  const float4* psort;
+  const float4* porig;
+  const float* tb;
+  int ntiles, ntiles_pad;
+  int k, reg;
+  double* cov;      // [npad*6] sorted order (may be null when only the neighbour lists are wanted)
+  int* knn_idx;     // optional test hook, original order [n*k]
+  float* knn_sqd;   // optional
+  unsigned long long* stat_pairs;  // optional: number of (query,candidate) distance evaluations
+};
+
+template <int KC>
+__global__ void __launch_bounds__(128) k_knn_cov(const KnnParams* __restrict__ plist) {
+  const KnnParams P = plist[blockIdx.y];
+  __shared__ float4 s_tile[4][TILE];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int qt = blockIdx.x * 4 + wib;
+  if (qt >= P.ntiles) return;  // warp-uniform; no block-level barrier in this kernel
+  const float4 q = P.psort[(size_t)qt * TILE + lane];
+  const int qidx = __float_as_int(q.w);
+  const bool qvalid = qidx != PAD_IDX;
+  TopK<KC> L;
+  L.init();
+  const int ntp = P.ntiles_pad;
+  Box wb;
+  wb.mnx = P.tb[qt]; wb.mny = P.tb[ntp + qt]; wb.mnz = P.tb[2 * ntp + qt];
+  wb.mxx = P.tb[3 * ntp + qt]; wb.mxy = P.tb[4 * ntp + qt]; wb.mxz = P.tb[5 * ntp + qt];
+  unsigned long long pairs = 0;
+
+  auto process_tile = [&](int t) {
+    float4 c = P.psort[(size_t)t * TILE + lane];
+    __syncwarp();
+    s_tile[wib][lane] = c;
+    __syncwarp();
+#pragma unroll 8
+    for (int j = 0; j < TILE; j++) {
+      float4 p = s_tile[wib][j];
+      float d = dist2(q.x, q.y, q.z, p.x, p.y, p.z);
+      int pid = __float_as_int(p.w);
+      if (L.qualifies(d, pid)) L.insert(d, pid);
+    }
+    pairs += TILE;
+  };
+
+  // home tiles first: they fill the lists and make the cull radius tight
+  process_tile(qt);
+#pragma unroll 1
+  for (int o = 1; o <= HOME_RADIUS; o++) {
+    if (qt - o >= 0) process_tile(qt - o);
+    if (qt + o < P.ntiles) process_tile(qt + o);
+  }
+  float W = warp_max(qvalid ? L.d[KC - 1] : -INFINITY);
+
+#pragma unroll 1
+  for (int base = 0; base < ntp; base += 32) {
+    int t = base + lane;
+    float bd = tile_box_dist2(wb, P.tb, ntp, t);
+    int dt = t - qt;
+    bool pass = (t < P.ntiles) && (dt > HOME_RADIUS || dt < -HOME_RADIUS) && (bd * CULL_SAFETY <= W);
+    unsigned m = __ballot_sync(FULL, pass);
+    while (m) {
+      int j = __ffs(m) - 1;
+      m &= m - 1;
+      float bdj = __shfl_sync(FULL, bd, j);
+      if (bdj * CULL_SAFETY > W) continue;
+      process_tile(base + j);
+      W = warp_max(qvalid ? L.d[KC - 1] : -INFINITY);
+    }
+  }
+  if (P.stat_pairs && lane == 0) atomicAdd(P.stat_pairs, pairs * 32ull);
+  if (!qvalid) return;
+
+  const int k = P.k;
+  if (P.knn_idx) {
+#pragma unroll
+    for (int j = 0; j < KC; j++)
+      if (j < k) {
+        bool real = L.i[j] != PAD_IDX;
+        P.knn_idx[(size_t)qidx * k + j] = real ? L.i[j] : -1;
+        if (P.knn_sqd) P.knn_sqd[(size_t)qidx * k + j] = real ? L.d[j] : INFINITY;
+      }
+  }
+  if (!P.cov) return;
+
+  // --- covariance of the k neighbours (double), fast_gicp_impl.hpp:256-261 ---
+  double mean[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+  for (int j = 0; j < KC; j++)
+    if (j < k && L.i[j] != PAD_IDX) {
+      float4 p = P.porig[L.i[j]];
+      mean[0] += (double)p.x;
+      mean[1] += (double)p.y;
+      mean[2] += (double)p.z;
+    }
+  const double dk = (double)k;
+  mean[0] /= dk; mean[1] /= dk; mean[2] /= dk;
+  double C[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+  for (int j = 0; j < KC; j++)
+    if (j < k) {
+      double dd[3];
+      if (L.i[j] != PAD_IDX) {
+        float4 p = P.porig[L.i[j]];
+        dd[0] = (double)p.x - mean[0]; dd[1] = (double)p.y - mean[1]; dd[2] = (double)p.z - mean[2];
+      } else {
+        dd[0] = 0.0 - mean[0]; dd[1] = 0.0 - mean[1]; dd[2] = 0.0 - mean[2];
+      }
+#pragma unroll
+      for (int a = 0; a < 3; a++)
+#pragma unroll
+        for (int b = 0; b < 3; b++) C[3 * a + b] += dd[a] * dd[b];
+    }
+#pragma unroll
+  for (int a = 0; a < 9; a++) C[a] /= dk;
+
+  double out[9];
+  if (P.reg == MRSLAM_REG_NONE) {
+#pragma unroll
+    for (int a = 0; a < 9; a++) out[a] = C[a];
+  } else if (P.reg == MRSLAM_REG_FROBENIUS) {
+    double Cl[9], Ci[9], Cn[9];
+#pragma unroll
+    for (int a = 0; a < 9; a++) Cl[a] = C[a];
+    Cl[0] += 1e-3; Cl[4] += 1e-3; Cl[8] += 1e-3;
+    inverse3(Cl, Ci);
+    double nrm = 0.0;
+#pragma unroll
+    for (int a = 0; a < 9; a++) nrm += Ci[a] * Ci[a];
+    nrm = sqrt(nrm);
+#pragma unroll
+    for (int a = 0; a < 9; a++) Cn[a] = Ci[a] / nrm;
+    inverse3(Cn, out);
+  } else {
+    double w[3], V[9], vals[3];
+    sym_eig3(C, w, V);
+    if (P.reg == MRSLAM_REG_PLANE) {
+      vals[0] = 1.0; vals[1] = 1.0; vals[2] = 1e-3;
+    } else if (P.reg == MRSLAM_REG_MIN_EIG) {
+      vals[0] = fmax(w[0], 1e-3); vals[1] = fmax(w[1], 1e-3); vals[2] = fmax(w[2], 1e-3);
+    } else {
+      vals[0] = fmax(w[0] / w[0], 1e-3); vals[1] = fmax(w[1] / w[0], 1e-3); vals[2] = fmax(w[2] / w[0], 1e-3);
+    }
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+#pragma unroll
+      for (int b = a; b < 3; b++)
+        out[3 * a + b] = V[3 * a] * vals[0] * V[3 * b] + V[3 * a + 1] * vals[1] * V[3 * b + 1] + V[3 * a + 2] * vals[2] * V[3 * b + 2];
+  }
+  double* co = P.cov + ((size_t)qt * TILE + lane) * 6;
+  co[0] = out[0]; co[1] = out[1]; co[2] = out[2]; co[3] = out[4]; co[4] = out[5]; co[5] = out[8];
+}
+
+// ---------------------------------------------------------------------------------------------
+// NN-1 correspondence + Mahalanobis + J^T M J / J^T M e / cost, fused.
+// fast_gicp_impl.hpp:115-152 (update_correspondences) + :155-211 (linearize); GPU precedent
+// find_voxel_correspondences.cu + compute_mahalanobis.cu + compute_derivatives.cu.
+// grid = (ceil(src_ntiles/4), n_active), block = 128.
+// ---------------------------------------------------------------------------------------------
+struct PairParams {
+  const float4* src_sort;
+  const double* src_cov;
+  int src_ntiles;
+  const float4* tgt_sort;
+  const float* tgt_tb;
+  const double* tgt_cov;
+  int tgt_ntiles, tgt_ntiles_pad;
+  int* corr;       // [src_npad] target SORTED position, -1 = none
+  int* nnpos;      // [src_npad] last nearest neighbour (sorted position) -- seed of the next search
+  float* sqd;      // [src_npad]
+  double* mahal;   // [src_npad*6]
+  double* partials;  // [nblocks * NRED]
+  double thr2;     // max correspondence distance, squared
+  int use_seed;
+};
+
+enum { MODE_LINEARIZE = 0, MODE_FITNESS = 1 };
+
+template <int MODE>
+__global__ void __launch_bounds__(128) k_nn1(const PairParams* __restrict__ plist, const int* __restrict__ active,
+                                             const double* __restrict__ Tbuf, double max_range,
+                                             unsigned long long* stat_pairs) {
+  const int pid = active[blockIdx.y];
+  const PairParams P = plist[pid];
+  __shared__ float4 s_tile[4][TILE];
+  __shared__ double s_red[4][NRED];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int qt = blockIdx.x * 4 + wib;
+  if (blockIdx.x * 4 >= P.src_ntiles) return;  // block-uniform
+  const bool wvalid = qt < P.src_ntiles;
+
+  const double* Td = Tbuf + (size_t)pid * 12;
+  float Tf[12];
+#pragma unroll
+  for (int i = 0; i < 12; i++) Tf[i] = (float)Td[i];
+
+  double acc[MODE == MODE_LINEARIZE ? NRED : 2];
+#pragma unroll
+  for (int i = 0; i < (MODE == MODE_LINEARIZE ? NRED : 2); i++) acc[i] = 0.0;
+
+  if (wvalid) {
+    const size_t s = (size_t)qt * TILE + lane;
+    const float4 p = P.src_sort[s];
+    const bool qvalid = __float_as_int(p.w) != PAD_IDX;
+    const float qx = xform_row(Tf + 0, p.x, p.y, p.z);
+    const float qy = xform_row(Tf + 4, p.x, p.y, p.z);
+    const float qz = xform_row(Tf + 8, p.x, p.y, p.z);
+    Box wb;
+    wb.mnx = warp_min(qvalid ? qx : FLT_MAX); wb.mny = warp_min(qvalid ? qy : FLT_MAX); wb.mnz = warp_min(qvalid ? qz : FLT_MAX);
+    wb.mxx = warp_max(qvalid ? qx : -FLT_MAX); wb.mxy = warp_max(qvalid ? qy : -FLT_MAX); wb.mxz = warp_max(qvalid ? qz : -FLT_MAX);
+
+    float best = INFINITY;
+    int bidx = PAD_IDX, bpos = -1;
+    const int ntp = P.tgt_ntiles_pad;
+    unsigned long long pairs = 0;
+    const float cap = (MODE == MODE_LINEARIZE) ? (float)fmin(P.thr2, (double)FLT_MAX) : (float)fmin(max_range, (double)FLT_MAX);
+
+    auto process_tile = [&](int t) {
+      float4 c = P.tgt_sort[(size_t)t * TILE + lane];
+      __syncwarp();
+      s_tile[wib][lane] = c;
+      __syncwarp();
+#pragma unroll 8
+      for (int j = 0; j < TILE; j++) {
+        float4 c4 = s_tile[wib][j];
+        float d = dist2(qx, qy, qz, c4.x, c4.y, c4.z);
+        int cid = __float_as_int(c4.w);
+        if (d < best || (d == best && cid < bidx)) {
+          best = d;
+          bidx = cid;
+          bpos = t * TILE + j;
+        }
+      }
+      pairs += TILE;
+    };
+
+    int home = -1;
+    if (P.use_seed) {
+      int sp = P.nnpos[s];
+      if (qvalid && sp >= 0) {
+        float4 c4 = P.tgt_sort[sp];
+        best = dist2(qx, qy, qz, c4.x, c4.y, c4.z);
+        bidx = __float_as_int(c4.w);
+        bpos = sp;
+      }
+    } else if (P.tgt_ntiles > 0) {
+      // no seed yet: start with the target tile whose box is closest to this warp's box
+      float mb = INFINITY;
+      int mt = 0;
+      for (int t = lane; t < P.tgt_ntiles; t += 32) {
+        float bd = tile_box_dist2(wb, P.tgt_tb, ntp, t);
+        if (bd < mb) {
+          mb = bd;
+          mt = t;
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        float ob = __shfl_xor_sync(FULL, mb, o);
+        int ot = __shfl_xor_sync(FULL, mt, o);
+        if (ob < mb || (ob == mb && ot < mt)) {
+          mb = ob;
+          mt = ot;
+        }
+      }
+      home = mt;
+      process_tile(home);
+    }
+    float W = fminf(warp_max(qvalid ? best : -INFINITY), cap);
+
+#pragma unroll 1
+    for (int base = 0; base < ntp; base += 32) {
+      int t = base + lane;
+      float bd = tile_box_dist2(wb, P.tgt_tb, ntp, t);
+      bool pass = (t < P.tgt_ntiles) && (t != home) && (bd * CULL_SAFETY <= W);
+      unsigned m = __ballot_sync(FULL, pass);
+      while (m) {
+        int j = __ffs(m) - 1;
+        m &= m - 1;
+        float bdj = __shfl_sync(FULL, bd, j);
+        if (bdj * CULL_SAFETY > W) continue;
+        process_tile(base + j);
+        W = fminf(warp_max(qvalid ? best : -INFINITY), cap);
+      }
+    }
+    if (stat_pairs && lane == 0) atomicAdd(stat_pairs, pairs * 32ull);
+
+    if (MODE == MODE_FITNESS) {
+      if (qvalid && bpos >= 0 && (double)best <= max_range) {
+        acc[0] = (double)best;
+        acc[1] = 1.0;
+      }
+    } else {
+      int corr = -1;
+      if (qvalid) {
+        corr = (bpos >= 0 && (double)best < P.thr2) ? bpos : -1;
+        P.corr[s] = corr;
+        P.nnpos[s] = bpos;
+        P.sqd[s] = best;
+      }
+      if (corr >= 0) {
+        double R[9], tt[3];
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+          R[3 * r] = Td[4 * r]; R[3 * r + 1] = Td[4 * r + 1]; R[3 * r + 2] = Td[4 * r + 2];
+          tt[r] = Td[4 * r + 3];
+        }
+        const double* ca = P.src_cov + s * 6;
+        const double* cb = P.tgt_cov + (size_t)corr * 6;
+        const double CA[9] = {ca[0], ca[1], ca[2], ca[1], ca[3], ca[4], ca[2], ca[4], ca[5]};
+        const double CB[9] = {cb[0], cb[1], cb[2], cb[1], cb[3], cb[4], cb[2], cb[4], cb[5]};
+        double RCA[9];
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+          for (int j = 0; j < 3; j++) RCA[3 * i + j] = R[3 * i] * CA[j] + R[3 * i + 1] * CA[3 + j] + R[3 * i + 2] * CA[6 + j];
+        double RCR[9];
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+          for (int j = i; j < 3; j++) {
+            double sij = RCA[3 * i] * R[3 * j] + RCA[3 * i + 1] * R[3 * j + 1] + RCA[3 * i + 2] * R[3 * j + 2];
+            RCR[3 * i + j] = sij + CB[3 * i + j];
+          }
+        RCR[3] = RCR[1]; RCR[6] = RCR[2]; RCR[7] = RCR[5];
+        double M[9];
+        inverse3(RCR, M);
+        double* mo = P.mahal + s * 6;
+        mo[0] = M[0]; mo[1] = M[1]; mo[2] = M[2]; mo[3] = M[4]; mo[4] = M[5]; mo[5] = M[8];
+
+        const float4 pb = P.tgt_sort[corr];
+        const double a0 = (double)p.x, a1 = (double)p.y, a2 = (double)p.z;
+        double ta[3];
+#pragma unroll
+        for (int r = 0; r < 3; r++) ta[r] = R[3 * r] * a0 + R[3 * r + 1] * a1 + R[3 * r + 2] * a2 + tt[r];
+        const double e[3] = {(double)pb.x - ta[0], (double)pb.y - ta[1], (double)pb.z - ta[2]};
+        double Me[3];
+#pragma unroll
+        for (int r = 0; r < 3; r++) Me[r] = M[3 * r] * e[0] + M[3 * r + 1] * e[1] + M[3 * r + 2] * e[2];
+        acc[27] = e[0] * Me[0] + e[1] * Me[1] + e[2] * Me[2];
+        const double J[3][6] = {{0, -ta[2], ta[1], -1, 0, 0}, {ta[2], 0, -ta[0], 0, -1, 0}, {-ta[1], ta[0], 0, 0, 0, -1}};
+        double MJ[3][6];
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+#pragma unroll
+          for (int c = 0; c < 6; c++) MJ[r][c] = M[3 * r] * J[0][c] + M[3 * r + 1] * J[1][c] + M[3 * r + 2] * J[2][c];
+        int o = 0;
+#pragma unroll
+        for (int r = 0; r < 6; r++) {
+#pragma unroll
+          for (int c = r; c < 6; c++) acc[o++] = J[0][r] * MJ[0][c] + J[1][r] * MJ[1][c] + J[2][r] * MJ[2][c];
+        }
+#pragma unroll
+        for (int r = 0; r < 6; r++) acc[21 + r] = J[0][r] * Me[0] + J[1][r] * Me[1] + J[2][r] * Me[2];
+      }
+    }
+  }
+  // deterministic reduction: lanes -> warp (butterfly) -> block (fixed order) -> one partial row per block
+  constexpr int NV = (MODE == MODE_LINEARIZE) ? NRED : 2;
+#pragma unroll
+  for (int i = 0; i < NV; i++) {
+    double v = warp_sum(acc[i]);
+    if (lane == 0) s_red[wib][i] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < NV) {
+    double v = ((s_red[0][threadIdx.x] + s_red[1][threadIdx.x]) + s_red[2][threadIdx.x]) + s_red[3][threadIdx.x];
+    P.partials[(size_t)blockIdx.x * NRED + threadIdx.x] = v;
+  }
+}
+
+// compute_error: fast_gicp_impl.hpp:214-236.  Streams src point, corr, target point, M. grid = (nblk, n_active)
+__global__ void __launch_bounds__(128) k_error(const PairParams* __restrict__ plist, const int* __restrict__ active,
+                                               const double* __restrict__ Tbuf) {
+  const int pid = active[blockIdx.y];
+  const PairParams P = plist[pid];
+  __shared__ double s_red[4];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  if (blockIdx.x * 4 >= P.src_ntiles) return;
+  const int qt = blockIdx.x * 4 + wib;
+  const double* Td = Tbuf + (size_t)pid * 12;
+  double err = 0.0;
+  if (qt < P.src_ntiles) {
+    const size_t s = (size_t)qt * TILE + lane;
+    const float4 p = P.src_sort[s];
+    const int corr = (__float_as_int(p.w) != PAD_IDX) ? P.corr[s] : -1;
+    if (corr >= 0) {
+      const float4 pb = P.tgt_sort[corr];
+      const double* mo = P.mahal + s * 6;
+      const double M[9] = {mo[0], mo[1], mo[2], mo[1], mo[3], mo[4], mo[2], mo[4], mo[5]};
+      const double a0 = (double)p.x, a1 = (double)p.y, a2 = (double)p.z;
+      double e[3];
+#pragma unroll
+      for (int r = 0; r < 3; r++) {
+        double ta = Td[4 * r] * a0 + Td[4 * r + 1] * a1 + Td[4 * r + 2] * a2 + Td[4 * r + 3];
+        e[r] = (double)(r == 0 ? pb.x : (r == 1 ? pb.y : pb.z)) - ta;
+      }
+      double Me[3];
+#pragma unroll
+      for (int r = 0; r < 3; r++) Me[r] = M[3 * r] * e[0] + M[3 * r + 1] * e[1] + M[3 * r + 2] * e[2];
+      err = e[0] * Me[0] + e[1] * Me[1] + e[2] * Me[2];
+    }
+  }
+  err = warp_sum(err);
+  if (lane == 0) s_red[wib] = err;
+  __syncthreads();
+  if (threadIdx.x == 0) P.partials[(size_t)blockIdx.x * NRED + 27] = ((s_red[0] + s_red[1]) + s_red[2]) + s_red[3];
+}
+
+// sums partial rows in a fixed order: grid = n_active blocks, block = 32*ncols threads (warp c owns column col0+c)
+__global__ void k_reduce_partials(const PairParams* __restrict__ plist, const int* __restrict__ active, int col0, int ncols,
+                                  double* __restrict__ out /* [n_problems][NRED], pinned host or device */) {
+  const int pid = active[blockIdx.x];
+  const PairParams P = plist[pid];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (w >= ncols) return;
+  const int nblk = (P.src_ntiles + 3) / 4;
+  double v = 0.0;
+  for (int r = lane; r < nblk; r += 32) v += P.partials[(size_t)r * NRED + col0 + w];
+  v = warp_sum(v);
+  if (lane == 0) out[(size_t)pid * NRED + col0 + w] = v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// small utility kernels
+// ---------------------------------------------------------------------------------------------
+__global__ void k_fill_int(int* p, size_t n, int v) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+// pcl::transformPointCloud(*input_, output, final_transformation_) -- lsq_registration_impl.hpp:78
+__global__ void k_transform_out(const float4* __restrict__ porig, int n, const float* __restrict__ Tf12, float* __restrict__ out,
+                                int stride) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 p = porig[i];
+  float T[12];
+#pragma unroll
+  for (int k = 0; k < 12; k++) T[k] = Tf12[k];
+  float* o = out + (size_t)i * stride;
+  o[0] = xform_row(T + 0, p.x, p.y, p.z);
+  o[1] = xform_row(T + 4, p.x, p.y, p.z);
+  o[2] = xform_row(T + 8, p.x, p.y, p.z);
+}
+
+// user covariances (original order, row-major 4x4 doubles) <-> sorted 6-double storage
+__global__ void k_cov_from_user(const double* __restrict__ user16, const float4* __restrict__ psort, int npad, double* __restrict__ cov) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= npad) return;
+  int o = __float_as_int(psort[s].w);
+  double* c = cov + (size_t)s * 6;
+  if (o == PAD_IDX) {
+    c[0] = c[3] = c[5] = 1.0;
+    c[1] = c[2] = c[4] = 0.0;
+    return;
+  }
+  const double* u = user16 + (size_t)o * 16;
+  c[0] = u[0]; c[1] = u[1]; c[2] = u[2]; c[3] = u[5]; c[4] = u[6]; c[5] = u[10];
+}
+__global__ void k_cov_to_user(const double* __restrict__ cov, const float4* __restrict__ psort, int npad, double* __restrict__ user16) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= npad) return;
+  int o = __float_as_int(psort[s].w);
+  if (o == PAD_IDX) return;
+  const double* c = cov + (size_t)s * 6;
+  double* u = user16 + (size_t)o * 16;
+  u[0] = c[0]; u[1] = c[1]; u[2] = c[2]; u[3] = 0;
+  u[4] = c[1]; u[5] = c[3]; u[6] = c[4]; u[7] = 0;
+  u[8] = c[2]; u[9] = c[4]; u[10] = c[5]; u[11] = 0;
+  u[12] = u[13] = u[14] = u[15] = 0;
+}
+
+// debug: last linearisation state in source ORIGINAL order, corr as target ORIGINAL index
+__global__ void k_debug_corr(const float4* __restrict__ src_sort, const float4* __restrict__ tgt_sort, int src_npad,
+                             const int* __restrict__ corr, const float* __restrict__ sqd, const double* __restrict__ mahal,
+                             int* __restrict__ corr_out, float* __restrict__ sqd_out, double* __restrict__ mahal9_out) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= src_npad) return;
+  int o = __float_as_int(src_sort[s].w);
+  if (o == PAD_IDX) return;
+  int c = corr[s];
+  if (corr_out) corr_out[o] = c >= 0 ? __float_as_int(tgt_sort[c].w) : -1;
+  if (sqd_out) sqd_out[o] = sqd[s];
+  if (mahal9_out) {
+    double* m = mahal9_out + (size_t)o * 9;
+    if (c >= 0) {
+      const double* mi = mahal + (size_t)s * 6;
+      m[0] = mi[0]; m[1] = mi[1]; m[2] = mi[2]; m[3] = mi[1]; m[4] = mi[3]; m[5] = mi[4]; m[6] = mi[2]; m[7] = mi[4]; m[8] = mi[5];
+    } else {
+      for (int k = 0; k < 9; k++) m[k] = 0.0;
+    }
+  }
+}
+
+}  // namespace mrslam

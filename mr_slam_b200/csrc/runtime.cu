@@ -1,0 +1,85 @@
+// runtime.cu -- process-global runtime of libmrslam_b200: device selection, the library stream,
+// the stream-ordered memory pool, error strings, launch counter.
+#include "common.cuh"
+
+namespace mrslam {
+
+thread_local int g_status = 0;
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+Runtime& rt() {
+  static Runtime r;
+  return r;
+}
+
+static int init_device(int device) {
+  Runtime& R = rt();
+  std::lock_guard<std::mutex> lk(R.mu);
+  if (R.device >= 0 && (device < 0 || device == R.device)) return MRSLAM_OK;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    set_error("no CUDA device available (%s); libmrslam_b200 has no CPU fallback", e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    return MRSLAM_ERR_CUDA;
+  }
+  if (device < 0) {
+    if (cudaGetDevice(&device) != cudaSuccess) device = 0;
+  }
+  if (device >= count) {
+    set_error("device %d out of range (%d devices)", device, count);
+    return MRSLAM_ERR_ARG;
+  }
+  MR_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  MR_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) {
+    set_error("device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+    return MRSLAM_ERR_CUDA;
+  }
+  if (R.stream) {
+    cudaStreamDestroy(R.stream);
+    R.stream = nullptr;
+  }
+  MR_CUDA(cudaStreamCreateWithFlags(&R.stream, cudaStreamNonBlocking));
+  cudaMemPool_t pool;
+  MR_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+  unsigned long long thresh = ~0ull;  // keep freed blocks cached: handles are created per loop-closure check
+  MR_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
+  R.sm_count = prop.multiProcessorCount;
+  R.device = device;
+  return MRSLAM_OK;
+}
+
+int ensure_init() {
+  if (rt().device >= 0) {
+    // the calling thread may not have the device current yet
+    int cur = -1;
+    if (cudaGetDevice(&cur) == cudaSuccess && cur != rt().device) cudaSetDevice(rt().device);
+    return MRSLAM_OK;
+  }
+  return init_device(-1);
+}
+
+}  // namespace mrslam
+
+using namespace mrslam;
+
+extern "C" {
+int mrslam_init(int device) { return init_device(device); }
+const char* mrslam_last_error(void) { return g_err; }
+const char* mrslam_version(void) { return "mrslam_b200 0.1 (sm_100a)"; }
+int mrslam_device_synchronize(void) {
+  MR_CHECK(ensure_init());
+  MR_CUDA(cudaStreamSynchronize(rt().stream));
+  return MRSLAM_OK;
+}
+void* mrslam_stream(void) { return ensure_init() == MRSLAM_OK ? (void*)rt().stream : nullptr; }
+unsigned long long mrslam_kernel_launch_count(void) { return rt().launches.load(); }
+}

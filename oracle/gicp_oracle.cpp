@@ -29,6 +29,8 @@
 //   * squared distance in float: d = fmaf(dz,dz, fmaf(dy,dy, dx*dx)), dx = q.x - p.x ...
 //   * kNN / NN ties: lexicographic (distance, point index) -> lowest index wins.
 //   * float transform of a point: fmaf(m02,z, fmaf(m01,y, m00*x)) + m03.
+//   * covariances / RCR / Mahalanobis matrices are kept exactly symmetric (upper triangle mirrored);
+//     the reference's are symmetric only up to rounding (1e-17 relative).
 //   * kNN with fewer than k points in the cloud: all points are neighbours; the divisor
 //     stays k_correspondences (as fast_gicp_impl.hpp:261 divides by k_correspondences_).
 #include <algorithm>
@@ -477,6 +479,10 @@ struct Gicp {
         for (int a = 0; a < 3; a++)
           for (int b = 0; b < 3; b++)
             out(a, b) = V(a, 0) * vals[0] * V(b, 0) + V(a, 1) * vals[1] * V(b, 1) + V(a, 2) * vals[2] * V(b, 2);
+        // exactly symmetric (upper triangle mirrored): the CUDA path stores 6 unique entries
+        out(1, 0) = out(0, 1);
+        out(2, 0) = out(0, 2);
+        out(2, 1) = out(1, 2);
       }
       memcpy(&covs[(size_t)i * 9], out.m, sizeof(out.m));
     }
@@ -509,6 +515,9 @@ struct Gicp {
       memcpy(CB.m, &tgt_cov[(size_t)corr[i] * 9], sizeof(CB.m));
       M3 RCR = mul(mul(trans.R, CA), transpose(trans.R));
       for (int a = 0; a < 9; a++) RCR.m[a] += CB.m[a];
+      RCR(1, 0) = RCR(0, 1);  // exactly symmetric, see calculate_covariances
+      RCR(2, 0) = RCR(0, 2);
+      RCR(2, 1) = RCR(1, 2);
       M3 Mi;
       inverse3(RCR, Mi);
       memcpy(&mahal[(size_t)i * 9], Mi.m, sizeof(Mi.m));

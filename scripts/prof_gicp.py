@@ -1,0 +1,24 @@
+"""Small GICP workload for ncu: B fresh aligns of one synthetic 120k-pt pair (covariances recomputed)."""
+import os, sys, time
+sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(__file__), "..")))
+import numpy as np
+from mr_slam_b200 import synth, pygicp, _lib
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 4
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+_lib.init(0)
+src, tgt, Tgt, Tg, Pa, Pb = synth.make_pair(0, "hdl64")
+Tg = Tg.astype(np.float32)
+L = _lib.lib()
+for rep in range(reps):
+    regs = []
+    for i in range(B):
+        g = pygicp.FastGICP(); g.set_correspondence_randomness(15); g.set_max_correspondence_distance(100.0)
+        g.set_maximum_iterations(50); g.set_transformation_epsilon(1e-3)
+        g.set_input_source(src); g.set_input_target(tgt)
+        regs.append(g)
+    L.mrslam_device_synchronize()
+    L.mrslam_gicp_stats_enable(1)
+    t = time.time(); Ts = pygicp.align_batch(regs, np.stack([Tg] * B)); dt = time.time() - t
+    pairs = L.mrslam_gicp_stats_pairs()
+    print(f"rep {rep}: batch {B}: {dt*1e3:.2f} ms, {B/dt:.1f} aligns/s, pair evals {pairs:.3e} ({pairs/B/ (2*120000):.0f} per query-pass avg over passes), err {synth.pose_error(Ts[0], Tgt)}")
+    L.mrslam_gicp_stats_enable(0)
