@@ -21,10 +21,11 @@ namespace mrslam {
 // device-resident cloud
 // ---------------------------------------------------------------------------------------------
 struct Cloud {
-  int n = 0, npad = 0, ntiles = 0, ntiles_pad = 0;
+  int n = 0, npad = 0, ntiles = 0, ntiles_pad = 0, nsuper = 0, nsuper_pad = 0;
   DevBuf<float4> porig, psort;
-  DevBuf<float> tb;
+  DevBuf<float> tb, sb;
   DevBuf<double> cov;
+  DevBuf<int> knn_ids;  // [npad*k] neighbour lists (scratch between k_knn_search and k_cov)
   bool cov_valid = false;
   // scratch for the build
   DevBuf<float> raw;
@@ -41,10 +42,14 @@ struct Cloud {
     ntiles = npad / TILE;
     ntiles_pad = ((ntiles + 31) / 32) * 32;
     if (ntiles_pad == 0) ntiles_pad = 32;
+    nsuper = (ntiles + 31) / 32;
+    nsuper_pad = ((nsuper + 31) / 32) * 32;
+    if (nsuper_pad == 0) nsuper_pad = 32;
     cov_valid = false;
     MR_CHECK(porig.reserve(std::max(n, 1)));
     MR_CHECK(psort.reserve(std::max(npad, 1)));
     MR_CHECK(tb.reserve((size_t)6 * ntiles_pad));
+    MR_CHECK(sb.reserve((size_t)6 * nsuper_pad));
     MR_CHECK(keys.reserve(std::max(n, 1)));
     MR_CHECK(keys_alt.reserve(std::max(n, 1)));
     MR_CHECK(vals.reserve(std::max(n, 1)));
@@ -71,6 +76,8 @@ struct Cloud {
       k_gather_tiles<<<(ntiles_pad * 32 + 127) / 128, 128, 0, st>>>(porig.p, nullptr, 0, 0, ntiles_pad, psort.p, tb.p);
       count_launch(1);
     }
+    k_super_boxes<<<(nsuper_pad * 32 + 127) / 128, 128, 0, st>>>(tb.p, ntiles, ntiles_pad, nsuper_pad, sb.p);
+    count_launch(1);
     MR_CUDA(cudaGetLastError());
     return MRSLAM_OK;
   }
@@ -90,28 +97,24 @@ struct Cloud {
   }
 
   void release() {
-    porig.release(); psort.release(); tb.release(); cov.release(); raw.release();
+    porig.release(); psort.release(); tb.release(); sb.release(); cov.release(); knn_ids.release(); raw.release();
     keys.release(); keys_alt.release(); vals.release(); vals_alt.release(); cubtmp.release(); bbox.release();
   }
 };
 
-template <int KC>
-static void launch_knn(const KnnParams* d_params, int nproblems, int max_tiles) {
-  dim3 grid((max_tiles + 3) / 4, nproblems);
-  k_knn_cov<KC><<<grid, 128, 0, rt().stream>>>(d_params);
-  count_launch(1);
-}
-static int dispatch_knn(int k, const KnnParams* d_params, int nproblems, int max_tiles) {
+static int dispatch_knn(int k, const KnnParams* d_params, int nproblems, int max_tiles, bool with_cov) {
   if (k < 1 || k > 32) {
     set_error("k_correspondences must be in 1..32 (got %d)", k);
     return MRSLAM_ERR_ARG;
   }
   if (max_tiles <= 0 || nproblems <= 0) return MRSLAM_OK;
-  if (k <= 8) launch_knn<8>(d_params, nproblems, max_tiles);
-  else if (k <= 16) launch_knn<16>(d_params, nproblems, max_tiles);
-  else if (k <= 20) launch_knn<20>(d_params, nproblems, max_tiles);
-  else if (k <= 24) launch_knn<24>(d_params, nproblems, max_tiles);
-  else launch_knn<32>(d_params, nproblems, max_tiles);
+  dim3 grid((max_tiles + 3) / 4, nproblems);
+  k_knn_search<<<grid, 128, 0, rt().stream>>>(d_params);
+  count_launch(1);
+  if (with_cov) {
+    k_cov<<<dim3((max_tiles * TILE + 127) / 128, nproblems), 128, 0, rt().stream>>>(d_params);
+    count_launch(1);
+  }
   MR_CUDA(cudaGetLastError());
   return MRSLAM_OK;
 }
@@ -260,7 +263,8 @@ struct BatchScratch {
   PinBuf<PairParams> h_pairs;
   PinBuf<KnnParams> h_knn;
   PinBuf<int> h_active;
-  PinBuf<double> h_T;    // [n][12]  read by kernels straight from pinned host memory
+  PinBuf<double> h_T;    // [n][12]  staging of the transforms of the next launch
+  DevBuf<double> d_T;    // [n][12]
   PinBuf<double> h_out;  // [n][NRED] written by k_reduce_partials straight into pinned host memory
   DevBuf<unsigned long long> d_stat;
   bool stats = false;
@@ -287,9 +291,12 @@ static PairParams make_pair_params(Gicp* g) {
   p.src_ntiles = g->src->ntiles;
   p.tgt_sort = g->tgt->psort.p;
   p.tgt_tb = g->tgt->tb.p;
+  p.tgt_sb = g->tgt->sb.p;
   p.tgt_cov = g->tgt->cov.p;
   p.tgt_ntiles = g->tgt->ntiles;
   p.tgt_ntiles_pad = g->tgt->ntiles_pad;
+  p.tgt_nsuper = g->tgt->nsuper;
+  p.tgt_nsuper_pad = g->tgt->nsuper_pad;
   p.corr = g->corr.p;
   p.nnpos = g->nnpos.p;
   p.sqd = g->sqd.p;
@@ -333,9 +340,11 @@ static int compute_covariances(Gicp** hs, int n) {
   for (size_t i = 0; i < order.size(); i++) {
     Cloud* c = todo[order[i]];
     MR_CHECK(c->cov.reserve((size_t)std::max(c->npad, 1) * 6));
+    MR_CHECK(c->knn_ids.reserve((size_t)std::max(c->npad, 1) * ks[order[i]]));
     KnnParams p;
-    p.psort = c->psort.p; p.porig = c->porig.p; p.tb = c->tb.p;
-    p.ntiles = c->ntiles; p.ntiles_pad = c->ntiles_pad;
+    p.n = c->n; p.ids = c->knn_ids.p;
+    p.psort = c->psort.p; p.porig = c->porig.p; p.tb = c->tb.p; p.sb = c->sb.p;
+    p.ntiles = c->ntiles; p.ntiles_pad = c->ntiles_pad; p.nsuper = c->nsuper; p.nsuper_pad = c->nsuper_pad;
     p.k = ks[order[i]]; p.reg = regs[order[i]];
     p.cov = c->cov.p; p.knn_idx = nullptr; p.knn_sqd = nullptr;
     p.stat_pairs = S.stats ? S.d_stat.p : nullptr;
@@ -350,7 +359,7 @@ static int compute_covariances(Gicp** hs, int n) {
       maxt = std::max(maxt, todo[order[i1]]->ntiles);
       i1++;
     }
-    MR_CHECK(dispatch_knn(k, S.d_knn.p + i0, (int)(i1 - i0), maxt));
+    MR_CHECK(dispatch_knn(k, S.d_knn.p + i0, (int)(i1 - i0), maxt, true));
     i0 = i1;
   }
   for (Cloud* c : todo) c->cov_valid = true;
@@ -401,11 +410,13 @@ static int run_linearize(Gicp** hs, const std::vector<int>& ids) {
   int nmax = *std::max_element(ids.begin(), ids.end()) + 1;
   MR_CUDA(cudaMemcpyAsync(S.d_pairs.p, S.h_pairs.p, sizeof(PairParams) * nmax, cudaMemcpyHostToDevice, st));
   MR_CUDA(cudaMemcpyAsync(S.d_active.p, S.h_active.p, sizeof(int) * na, cudaMemcpyHostToDevice, st));
+  MR_CUDA(cudaMemcpyAsync(S.d_T.p, S.h_T.p, sizeof(double) * 12 * nmax, cudaMemcpyHostToDevice, st));
   if (maxt > 0) {
     dim3 grid((maxt + 3) / 4, na);
-    k_nn1<MODE_LINEARIZE><<<grid, 128, 0, st>>>(S.d_pairs.p, S.d_active.p, S.h_T.p, 0.0, S.stats ? S.d_stat.p : nullptr);
+    k_nn1_search<MODE_LINEARIZE><<<grid, 128, 0, st>>>(S.d_pairs.p, S.d_active.p, S.d_T.p, 0.0, S.stats ? S.d_stat.p : nullptr);
+    k_linearize<<<grid, 128, 0, st>>>(S.d_pairs.p, S.d_active.p, S.d_T.p);
     k_reduce_partials<<<na, 32 * NRED, 0, st>>>(S.d_pairs.p, S.d_active.p, 0, NRED, S.h_out.p);
-    count_launch(2);
+    count_launch(3);
   }
   MR_CUDA(cudaGetLastError());
   MR_CUDA(cudaStreamSynchronize(st));
@@ -431,9 +442,13 @@ static int run_error(Gicp** hs, const std::vector<int>& ids) {
     hs[ids[a]]->n_error++;
   }
   MR_CUDA(cudaMemcpyAsync(S.d_active.p, S.h_active.p, sizeof(int) * na, cudaMemcpyHostToDevice, st));
+  {
+    int nmax = *std::max_element(ids.begin(), ids.end()) + 1;
+    MR_CUDA(cudaMemcpyAsync(S.d_T.p, S.h_T.p, sizeof(double) * 12 * nmax, cudaMemcpyHostToDevice, st));
+  }
   if (maxt > 0) {
     dim3 grid((maxt + 3) / 4, na);
-    k_error<<<grid, 128, 0, st>>>(S.d_pairs.p, S.d_active.p, S.h_T.p);
+    k_error<<<grid, 128, 0, st>>>(S.d_pairs.p, S.d_active.p, S.d_T.p);
     k_reduce_partials<<<na, 32, 0, st>>>(S.d_pairs.p, S.d_active.p, 27, 1, S.h_out.p);
     count_launch(2);
   }
@@ -449,6 +464,7 @@ static int reserve_scratch(int n) {
   MR_CHECK(S.h_pairs.reserve(n));
   MR_CHECK(S.h_active.reserve(n));
   MR_CHECK(S.h_T.reserve((size_t)n * 12));
+  MR_CHECK(S.d_T.reserve((size_t)n * 12));
   MR_CHECK(S.h_out.reserve((size_t)n * NRED));
   MR_CHECK(S.d_stat.reserve(4));
   return MRSLAM_OK;
@@ -617,9 +633,10 @@ static int fitness_batch(Gicp** hs, int n, double max_range, double* out) {
   }
   MR_CUDA(cudaMemcpyAsync(S.d_pairs.p, S.h_pairs.p, sizeof(PairParams) * n, cudaMemcpyHostToDevice, st));
   MR_CUDA(cudaMemcpyAsync(S.d_active.p, S.h_active.p, sizeof(int) * n, cudaMemcpyHostToDevice, st));
+  MR_CUDA(cudaMemcpyAsync(S.d_T.p, S.h_T.p, sizeof(double) * 12 * n, cudaMemcpyHostToDevice, st));
   if (maxt > 0) {
     dim3 grid((maxt + 3) / 4, n);
-    k_nn1<MODE_FITNESS><<<grid, 128, 0, st>>>(S.d_pairs.p, S.d_active.p, S.h_T.p, max_range, S.stats ? S.d_stat.p : nullptr);
+    k_nn1_search<MODE_FITNESS><<<grid, 128, 0, st>>>(S.d_pairs.p, S.d_active.p, S.d_T.p, max_range, S.stats ? S.d_stat.p : nullptr);
     k_reduce_partials<<<n, 64, 0, st>>>(S.d_pairs.p, S.d_active.p, 0, 2, S.h_out.p);
     count_launch(2);
   }
@@ -696,13 +713,19 @@ int mrslam_cloud_knn(mrslam_cloud_t* h, int k, int* idx_out, float* sqd_out) {
   size_t tot = (size_t)std::max(c->n, 1) * k;
   MR_CHECK(di.reserve(tot));
   MR_CHECK(dd.reserve(tot));
+  if (k < 1 || k > 32) {
+    set_error("k must be in 1..32");
+    return MRSLAM_ERR_ARG;
+  }
+  MR_CHECK(c->knn_ids.reserve((size_t)std::max(c->npad, 1) * k));
   KnnParams p;
-  p.psort = c->psort.p; p.porig = c->porig.p; p.tb = c->tb.p;
-  p.ntiles = c->ntiles; p.ntiles_pad = c->ntiles_pad; p.k = k; p.reg = 0;
+  p.n = c->n; p.ids = c->knn_ids.p;
+  p.psort = c->psort.p; p.porig = c->porig.p; p.tb = c->tb.p; p.sb = c->sb.p;
+  p.ntiles = c->ntiles; p.ntiles_pad = c->ntiles_pad; p.nsuper = c->nsuper; p.nsuper_pad = c->nsuper_pad; p.k = k; p.reg = 0;
   p.cov = nullptr; p.knn_idx = di.p; p.knn_sqd = dd.p; p.stat_pairs = nullptr;
   S.h_knn.p[0] = p;
   MR_CUDA(cudaMemcpyAsync(S.d_knn.p, S.h_knn.p, sizeof(KnnParams), cudaMemcpyHostToDevice, rt().stream));
-  MR_CHECK(dispatch_knn(k, S.d_knn.p, 1, c->ntiles));
+  MR_CHECK(dispatch_knn(k, S.d_knn.p, 1, c->ntiles, false));
   if (c->n > 0) {
     MR_CUDA(cudaMemcpyAsync(idx_out, di.p, sizeof(int) * (size_t)c->n * k, cudaMemcpyDeviceToHost, rt().stream));
     if (sqd_out) MR_CUDA(cudaMemcpyAsync(sqd_out, dd.p, sizeof(float) * (size_t)c->n * k, cudaMemcpyDeviceToHost, rt().stream));

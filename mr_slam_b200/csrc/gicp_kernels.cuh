@@ -7,12 +7,16 @@
 //   tb     float[6][ntp]    per 32-point tile bounding boxes (SoA: minx,miny,minz,maxx,maxy,maxz)
 //   cov    double[npad][6]  regularised covariances in SORTED order (xx,xy,xz,yy,yz,zz)
 //
-// Search scheme ("shared-memory-tiled brute force with culling", no tree): one warp owns 32
-// spatially coherent queries (one tile).  Candidate tiles are staged through shared memory and
-// every query of the warp is compared against every point of the tile (brute force inside a
-// tile); a tile is skipped only when its bounding box is provably farther from the warp's
-// bounding box than the warp's current worst k-th distance.  The result is the exact kNN under
-// the (distance, original index) order -- identical to an exhaustive scan.
+//   sb     float[6][nsp]    bounding boxes of "super tiles" (32 consecutive tiles = 1024 points)
+//
+// Search scheme (tiled brute force with box culling and a warp-shuffle k-min; no tree): one warp
+// owns the 32 spatially coherent queries of one tile and serves them one after the other.  For a
+// query the 32 lanes evaluate the 32 points of a candidate tile in parallel (coalesced 512 B load,
+// brute force inside the tile); the running k-best list lives one entry per lane, kept sorted by
+// (distance, original index), and a qualifying candidate is merged with one shuffle-up step.
+// A tile (or a whole super tile) is skipped only when its bounding box is provably farther from the
+// query than the current k-th distance, so the result is the exact kNN under the (distance, index)
+// order -- identical to an exhaustive scan.
 #pragma once
 #include "common.cuh"
 
@@ -130,50 +134,41 @@ __global__ void k_gather_tiles(const float4* __restrict__ porig, const int* __re
 // ---------------------------------------------------------------------------------------------
 // shared search pieces
 // ---------------------------------------------------------------------------------------------
-struct Box {
-  float mnx, mny, mnz, mxx, mxy, mxz;
-};
+// one warp per super tile: box of its (real) tiles
+__global__ void k_super_boxes(const float* __restrict__ tb, int ntiles, int ntiles_pad, int nsuper_pad, float* __restrict__ sb) {
+  int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (s >= nsuper_pad) return;
+  int t = s * 32 + lane;
+  bool real = t < ntiles;
+  float mn[3], mx[3];
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+    mn[a] = warp_min(real ? tb[(size_t)a * ntiles_pad + t] : FLT_MAX);
+    mx[a] = warp_max(real ? tb[(size_t)(3 + a) * ntiles_pad + t] : -FLT_MAX);
+  }
+  bool any = __any_sync(FULL, real);
+  if (lane == 0) {
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      sb[(size_t)a * nsuper_pad + s] = any ? mn[a] : PAD_COORD;
+      sb[(size_t)(3 + a) * nsuper_pad + s] = any ? mx[a] : PAD_COORD;
+    }
+  }
+}
 
-__device__ __forceinline__ float box_dist2(const Box& a, float mnx, float mny, float mnz, float mxx, float mxy, float mxz) {
-  float gx = fmaxf(0.0f, fmaxf(mnx - a.mxx, a.mnx - mxx));
-  float gy = fmaxf(0.0f, fmaxf(mny - a.mxy, a.mny - mxy));
-  float gz = fmaxf(0.0f, fmaxf(mnz - a.mxz, a.mnz - mxz));
+// ---------------------------------------------------------------------------------------------
+// shared search pieces
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool lex_lt(float ad, int ai, float bd, int bi) { return ad < bd || (ad == bd && ai < bi); }
+
+// squared distance from a point to box t of an SoA box table (stride = padded count)
+__device__ __forceinline__ float pt_box_dist2(float x, float y, float z, const float* __restrict__ b, int stride, int t) {
+  float gx = fmaxf(0.0f, fmaxf(b[t] - x, x - b[3 * stride + t]));
+  float gy = fmaxf(0.0f, fmaxf(b[stride + t] - y, y - b[4 * stride + t]));
+  float gz = fmaxf(0.0f, fmaxf(b[2 * stride + t] - z, z - b[5 * stride + t]));
   return gx * gx + gy * gy + gz * gz;
 }
-__device__ __forceinline__ float tile_box_dist2(const Box& a, const float* __restrict__ tb, int ntp, int t) {
-  return box_dist2(a, tb[t], tb[ntp + t], tb[2 * ntp + t], tb[3 * ntp + t], tb[4 * ntp + t], tb[5 * ntp + t]);
-}
-
-template <int KC>
-struct TopK {
-  float d[KC];
-  int i[KC];
-  __device__ __forceinline__ void init() {
-#pragma unroll
-    for (int j = 0; j < KC; j++) {
-      d[j] = INFINITY;
-      i[j] = PAD_IDX;
-    }
-  }
-  __device__ __forceinline__ bool qualifies(float cd, int ci) const { return cd < d[KC - 1] || (cd == d[KC - 1] && ci < i[KC - 1]); }
-  // sorted insertion, ascending (distance, index)
-  __device__ __forceinline__ void insert(float cd, int ci) {
-#pragma unroll
-    for (int j = KC - 1; j > 0; --j) {
-      bool before_prev = cd < d[j - 1] || (cd == d[j - 1] && ci < i[j - 1]);
-      bool before_this = cd < d[j] || (cd == d[j] && ci < i[j]);
-      float nd = before_prev ? d[j - 1] : (before_this ? cd : d[j]);
-      int ni = before_prev ? i[j - 1] : (before_this ? ci : i[j]);
-      d[j] = nd;
-      i[j] = ni;
-    }
-    bool b0 = cd < d[0] || (cd == d[0] && ci < i[0]);
-    if (b0) {
-      d[0] = cd;
-      i[0] = ci;
-    }
-  }
-};
 
 // symmetric 3x3 eigen-decomposition, cyclic Jacobi (double); eigenvalues descending; same operation
 // order as the oracle's sym_eig3 so that covariances agree bit for bit.
@@ -255,7 +250,7 @@ __device__ __forceinline__ void inverse3(const double a[9], double r[9]) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// kNN (k <= KC) + covariance + regularisation.   grid.x = ceil(ntiles/4), block = 128 (4 warps).
+// kNN search (k <= 32), then covariance + regularisation as a separate lane-per-point kernel.
 // fast_gicp_impl.hpp:241-298 (calculate_covariances); GPU precedent brute_force_knn.cu:16-60 +
 // covariance_estimation.cu:16-42 + covariance_regularization.cu:14-97.
 // ---------------------------------------------------------------------------------------------
@@ -263,115 +258,151 @@ struct KnnParams {
   const float4* psort;
   const float4* porig;
   const float* tb;
-  int ntiles, ntiles_pad;
+  const float* sb;
+  int n, ntiles, ntiles_pad, nsuper, nsuper_pad;
   int k, reg;
+  int* ids;         // [npad*k] neighbour ORIGINAL indices per SORTED position (PAD_IDX = absent)
   double* cov;      // [npad*6] sorted order (may be null when only the neighbour lists are wanted)
   int* knn_idx;     // optional test hook, original order [n*k]
   float* knn_sqd;   // optional
   unsigned long long* stat_pairs;  // optional: number of (query,candidate) distance evaluations
 };
 
-template <int KC>
-__global__ void __launch_bounds__(128) k_knn_cov(const KnnParams* __restrict__ plist) {
+constexpr int SGROUP = 4;  // super-tile box tests kept in flight together (4 x 32 boxes)
+
+// grid = (ceil(ntiles/4), n_clouds), block = 128; one warp per query tile, queries served one by one
+__global__ void __launch_bounds__(128) k_knn_search(const KnnParams* __restrict__ plist) {
   const KnnParams P = plist[blockIdx.y];
-  __shared__ float4 s_tile[4][TILE];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int qt = blockIdx.x * 4 + wib;
   if (qt >= P.ntiles) return;  // warp-uniform; no block-level barrier in this kernel
-  const float4 q = P.psort[(size_t)qt * TILE + lane];
-  const int qidx = __float_as_int(q.w);
-  const bool qvalid = qidx != PAD_IDX;
-  TopK<KC> L;
-  L.init();
-  const int ntp = P.ntiles_pad;
-  Box wb;
-  wb.mnx = P.tb[qt]; wb.mny = P.tb[ntp + qt]; wb.mnz = P.tb[2 * ntp + qt];
-  wb.mxx = P.tb[3 * ntp + qt]; wb.mxy = P.tb[4 * ntp + qt]; wb.mxz = P.tb[5 * ntp + qt];
-  unsigned long long pairs = 0;
-
-  auto process_tile = [&](int t) {
-    float4 c = P.psort[(size_t)t * TILE + lane];
-    __syncwarp();
-    s_tile[wib][lane] = c;
-    __syncwarp();
-#pragma unroll 8
-    for (int j = 0; j < TILE; j++) {
-      float4 p = s_tile[wib][j];
-      float d = dist2(q.x, q.y, q.z, p.x, p.y, p.z);
-      int pid = __float_as_int(p.w);
-      if (L.qualifies(d, pid)) L.insert(d, pid);
-    }
-    pairs += TILE;
-  };
-
-  // home tiles first: they fill the lists and make the cull radius tight
-  process_tile(qt);
-#pragma unroll 1
-  for (int o = 1; o <= HOME_RADIUS; o++) {
-    if (qt - o >= 0) process_tile(qt - o);
-    if (qt + o < P.ntiles) process_tile(qt + o);
-  }
-  float W = warp_max(qvalid ? L.d[KC - 1] : -INFINITY);
-
-#pragma unroll 1
-  for (int base = 0; base < ntp; base += 32) {
-    int t = base + lane;
-    float bd = tile_box_dist2(wb, P.tb, ntp, t);
-    int dt = t - qt;
-    bool pass = (t < P.ntiles) && (dt > HOME_RADIUS || dt < -HOME_RADIUS) && (bd * CULL_SAFETY <= W);
-    unsigned m = __ballot_sync(FULL, pass);
-    while (m) {
-      int j = __ffs(m) - 1;
-      m &= m - 1;
-      float bdj = __shfl_sync(FULL, bd, j);
-      if (bdj * CULL_SAFETY > W) continue;
-      process_tile(base + j);
-      W = warp_max(qvalid ? L.d[KC - 1] : -INFINITY);
-    }
-  }
-  if (P.stat_pairs && lane == 0) atomicAdd(P.stat_pairs, pairs * 32ull);
-  if (!qvalid) return;
-
+  const float4 qmine = P.psort[(size_t)qt * TILE + lane];
   const int k = P.k;
-  if (P.knn_idx) {
-#pragma unroll
-    for (int j = 0; j < KC; j++)
-      if (j < k) {
-        bool real = L.i[j] != PAD_IDX;
-        P.knn_idx[(size_t)qidx * k + j] = real ? L.i[j] : -1;
-        if (P.knn_sqd) P.knn_sqd[(size_t)qidx * k + j] = real ? L.d[j] : INFINITY;
-      }
-  }
-  if (!P.cov) return;
+  const int ntp = P.ntiles_pad, nsp = P.nsuper_pad;
+  unsigned long long tiles_done = 0;
 
-  // --- covariance of the k neighbours (double), fast_gicp_impl.hpp:256-261 ---
-  double mean[3] = {0.0, 0.0, 0.0};
+#pragma unroll 1
+  for (int qi = 0; qi < TILE; qi++) {
+    const float qx = __shfl_sync(FULL, qmine.x, qi), qy = __shfl_sync(FULL, qmine.y, qi), qz = __shfl_sync(FULL, qmine.z, qi);
+    const int qidx = __shfl_sync(FULL, __float_as_int(qmine.w), qi);
+    if (qidx == PAD_IDX) continue;
+    // k-best list, one entry per lane, ascending (distance, index); (wd, wi) = current k-th entry
+    float my_d = INFINITY;
+    int my_i = PAD_IDX;
+    float wd = INFINITY;
+    int wi = PAD_IDX;
+
+    auto process_tile = [&](int t) {
+      const float4 c = P.psort[(size_t)t * TILE + lane];
+      const float d = dist2(qx, qy, qz, c.x, c.y, c.z);
+      const int cid = __float_as_int(c.w);
+      unsigned m = __ballot_sync(FULL, lex_lt(d, cid, wd, wi));
+      while (m) {
+        const int j = __ffs(m) - 1;
+        m &= m - 1;
+        const float cd = __shfl_sync(FULL, d, j);
+        const int ci = __shfl_sync(FULL, cid, j);
+        if (!lex_lt(cd, ci, wd, wi)) continue;
+        const float ud = __shfl_up_sync(FULL, my_d, 1);
+        const int ui = __shfl_up_sync(FULL, my_i, 1);
+        const bool before = lex_lt(cd, ci, my_d, my_i);
+        const bool before_prev = lane > 0 && lex_lt(cd, ci, ud, ui);
+        if (before) {
+          my_d = before_prev ? ud : cd;
+          my_i = before_prev ? ui : ci;
+        }
+        wd = __shfl_sync(FULL, my_d, k - 1);
+        wi = __shfl_sync(FULL, my_i, k - 1);
+      }
+      tiles_done++;
+    };
+
+    // home tiles first: they fill the list and make the cull radius tight
+    process_tile(qt);
+#pragma unroll 1
+    for (int o = 1; o <= HOME_RADIUS; o++) {
+      if (qt - o >= 0) process_tile(qt - o);
+      if (qt + o < P.ntiles) process_tile(qt + o);
+    }
+#pragma unroll 1
+    for (int g0 = 0; g0 < nsp; g0 += 32 * SGROUP) {
+      float b1[SGROUP];
 #pragma unroll
-  for (int j = 0; j < KC; j++)
-    if (j < k && L.i[j] != PAD_IDX) {
-      float4 p = P.porig[L.i[j]];
+      for (int u = 0; u < SGROUP; u++) {
+        const int s1 = g0 + u * 32 + lane;
+        b1[u] = (s1 < P.nsuper) ? pt_box_dist2(qx, qy, qz, P.sb, nsp, s1) : INFINITY;
+      }
+#pragma unroll
+      for (int u = 0; u < SGROUP; u++) {
+        unsigned ms = __ballot_sync(FULL, b1[u] * CULL_SAFETY <= wd);
+        while (ms) {
+          const int js = __ffs(ms) - 1;
+          ms &= ms - 1;
+          if (__shfl_sync(FULL, b1[u], js) * CULL_SAFETY > wd) continue;
+          const int sidx = g0 + u * 32 + js;
+          const int t = sidx * 32 + lane;
+          const float bt = pt_box_dist2(qx, qy, qz, P.tb, ntp, t);
+          const int dt = t - qt;
+          unsigned mt = __ballot_sync(FULL, t < P.ntiles && (dt > HOME_RADIUS || dt < -HOME_RADIUS) && bt * CULL_SAFETY <= wd);
+          while (mt) {
+            const int jt = __ffs(mt) - 1;
+            mt &= mt - 1;
+            if (__shfl_sync(FULL, bt, jt) * CULL_SAFETY > wd) continue;
+            process_tile(sidx * 32 + jt);
+          }
+        }
+      }
+    }
+    if (lane < k) {
+      P.ids[((size_t)qt * TILE + qi) * k + lane] = my_i;
+      if (P.knn_idx) {
+        const bool real = my_i != PAD_IDX;
+        P.knn_idx[(size_t)qidx * k + lane] = real ? my_i : -1;
+        if (P.knn_sqd) P.knn_sqd[(size_t)qidx * k + lane] = real ? my_d : INFINITY;
+      }
+    }
+  }
+  if (P.stat_pairs && lane == 0) atomicAdd(P.stat_pairs, tiles_done * 32ull);
+}
+
+// covariance of the k neighbours (double), one thread per SORTED point; grid = (ceil(npad/128), n_clouds)
+__global__ void __launch_bounds__(128) k_cov(const KnnParams* __restrict__ plist) {
+  const KnnParams P = plist[blockIdx.y];
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= P.ntiles * TILE) return;
+  if (__float_as_int(P.psort[s].w) == PAD_IDX) return;
+  const int k = P.k;
+  const int* ids = P.ids + (size_t)s * k;
+  // fast_gicp_impl.hpp:256-261
+  double mean[3] = {0.0, 0.0, 0.0};
+#pragma unroll 1
+  for (int j = 0; j < k; j++) {
+    const int id = ids[j];
+    if (id != PAD_IDX) {
+      const float4 p = P.porig[id];
       mean[0] += (double)p.x;
       mean[1] += (double)p.y;
       mean[2] += (double)p.z;
     }
+  }
   const double dk = (double)k;
   mean[0] /= dk; mean[1] /= dk; mean[2] /= dk;
   double C[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-#pragma unroll
-  for (int j = 0; j < KC; j++)
-    if (j < k) {
-      double dd[3];
-      if (L.i[j] != PAD_IDX) {
-        float4 p = P.porig[L.i[j]];
-        dd[0] = (double)p.x - mean[0]; dd[1] = (double)p.y - mean[1]; dd[2] = (double)p.z - mean[2];
-      } else {
-        dd[0] = 0.0 - mean[0]; dd[1] = 0.0 - mean[1]; dd[2] = 0.0 - mean[2];
-      }
-#pragma unroll
-      for (int a = 0; a < 3; a++)
-#pragma unroll
-        for (int b = 0; b < 3; b++) C[3 * a + b] += dd[a] * dd[b];
+#pragma unroll 1
+  for (int j = 0; j < k; j++) {
+    const int id = ids[j];
+    double dd[3];
+    if (id != PAD_IDX) {
+      const float4 p = P.porig[id];
+      dd[0] = (double)p.x - mean[0]; dd[1] = (double)p.y - mean[1]; dd[2] = (double)p.z - mean[2];
+    } else {
+      dd[0] = 0.0 - mean[0]; dd[1] = 0.0 - mean[1]; dd[2] = 0.0 - mean[2];
     }
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+#pragma unroll
+      for (int b = 0; b < 3; b++) C[3 * a + b] += dd[a] * dd[b];
+  }
 #pragma unroll
   for (int a = 0; a < 9; a++) C[a] /= dk;
 
@@ -408,15 +439,14 @@ __global__ void __launch_bounds__(128) k_knn_cov(const KnnParams* __restrict__ p
       for (int b = a; b < 3; b++)
         out[3 * a + b] = V[3 * a] * vals[0] * V[3 * b] + V[3 * a + 1] * vals[1] * V[3 * b + 1] + V[3 * a + 2] * vals[2] * V[3 * b + 2];
   }
-  double* co = P.cov + ((size_t)qt * TILE + lane) * 6;
+  double* co = P.cov + (size_t)s * 6;
   co[0] = out[0]; co[1] = out[1]; co[2] = out[2]; co[3] = out[4]; co[4] = out[5]; co[5] = out[8];
 }
 
 // ---------------------------------------------------------------------------------------------
-// NN-1 correspondence + Mahalanobis + J^T M J / J^T M e / cost, fused.
-// fast_gicp_impl.hpp:115-152 (update_correspondences) + :155-211 (linearize); GPU precedent
-// find_voxel_correspondences.cu + compute_mahalanobis.cu + compute_derivatives.cu.
-// grid = (ceil(src_ntiles/4), n_active), block = 128.
+// NN-1 correspondence search (warp per query tile), then Mahalanobis + J^T M J / J^T M e / cost as a
+// lane-per-point kernel.  fast_gicp_impl.hpp:115-152 (update_correspondences) + :155-211 (linearize);
+// GPU precedent find_voxel_correspondences.cu + compute_mahalanobis.cu + compute_derivatives.cu.
 // ---------------------------------------------------------------------------------------------
 struct PairParams {
   const float4* src_sort;
@@ -424,8 +454,9 @@ struct PairParams {
   int src_ntiles;
   const float4* tgt_sort;
   const float* tgt_tb;
+  const float* tgt_sb;
   const double* tgt_cov;
-  int tgt_ntiles, tgt_ntiles_pad;
+  int tgt_ntiles, tgt_ntiles_pad, tgt_nsuper, tgt_nsuper_pad;
   int* corr;       // [src_npad] target SORTED position, -1 = none
   int* nnpos;      // [src_npad] last nearest neighbour (sorted position) -- seed of the next search
   float* sqd;      // [src_npad]
@@ -437,128 +468,192 @@ struct PairParams {
 
 enum { MODE_LINEARIZE = 0, MODE_FITNESS = 1 };
 
+// grid = (ceil(src_ntiles/4), n_active), block = 128.  MODE_LINEARIZE: writes nnpos/sqd.
+// MODE_FITNESS: per-block partial (sum of d <= max_range, count) into partials[.. + 0/1].
 template <int MODE>
-__global__ void __launch_bounds__(128) k_nn1(const PairParams* __restrict__ plist, const int* __restrict__ active,
-                                             const double* __restrict__ Tbuf, double max_range,
-                                             unsigned long long* stat_pairs) {
+__global__ void __launch_bounds__(128) k_nn1_search(const PairParams* __restrict__ plist, const int* __restrict__ active,
+                                                    const double* __restrict__ Tbuf, double max_range,
+                                                    unsigned long long* stat_pairs) {
   const int pid = active[blockIdx.y];
   const PairParams P = plist[pid];
-  __shared__ float4 s_tile[4][TILE];
-  __shared__ double s_red[4][NRED];
+  __shared__ double s_red[4][2];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int qt = blockIdx.x * 4 + wib;
   if (blockIdx.x * 4 >= P.src_ntiles) return;  // block-uniform
   const bool wvalid = qt < P.src_ntiles;
-
   const double* Td = Tbuf + (size_t)pid * 12;
-  float Tf[12];
-#pragma unroll
-  for (int i = 0; i < 12; i++) Tf[i] = (float)Td[i];
-
-  double acc[MODE == MODE_LINEARIZE ? NRED : 2];
-#pragma unroll
-  for (int i = 0; i < (MODE == MODE_LINEARIZE ? NRED : 2); i++) acc[i] = 0.0;
-
+  float res_d = INFINITY;  // result of this lane's own query
+  int res_pos = -1;
+  bool qvalid = false;
   if (wvalid) {
+    float Tf[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) Tf[i] = (float)Td[i];
     const size_t s = (size_t)qt * TILE + lane;
     const float4 p = P.src_sort[s];
-    const bool qvalid = __float_as_int(p.w) != PAD_IDX;
-    const float qx = xform_row(Tf + 0, p.x, p.y, p.z);
-    const float qy = xform_row(Tf + 4, p.x, p.y, p.z);
-    const float qz = xform_row(Tf + 8, p.x, p.y, p.z);
-    Box wb;
-    wb.mnx = warp_min(qvalid ? qx : FLT_MAX); wb.mny = warp_min(qvalid ? qy : FLT_MAX); wb.mnz = warp_min(qvalid ? qz : FLT_MAX);
-    wb.mxx = warp_max(qvalid ? qx : -FLT_MAX); wb.mxy = warp_max(qvalid ? qy : -FLT_MAX); wb.mxz = warp_max(qvalid ? qz : -FLT_MAX);
-
-    float best = INFINITY;
-    int bidx = PAD_IDX, bpos = -1;
-    const int ntp = P.tgt_ntiles_pad;
-    unsigned long long pairs = 0;
+    qvalid = __float_as_int(p.w) != PAD_IDX;
+    const float qxm = xform_row(Tf + 0, p.x, p.y, p.z);
+    const float qym = xform_row(Tf + 4, p.x, p.y, p.z);
+    const float qzm = xform_row(Tf + 8, p.x, p.y, p.z);
+    const int seed_mine = P.use_seed ? P.nnpos[s] : -1;
+    const int ntp = P.tgt_ntiles_pad, nsp = P.tgt_nsuper_pad;
     const float cap = (MODE == MODE_LINEARIZE) ? (float)fmin(P.thr2, (double)FLT_MAX) : (float)fmin(max_range, (double)FLT_MAX);
-
-    auto process_tile = [&](int t) {
-      float4 c = P.tgt_sort[(size_t)t * TILE + lane];
-      __syncwarp();
-      s_tile[wib][lane] = c;
-      __syncwarp();
-#pragma unroll 8
-      for (int j = 0; j < TILE; j++) {
-        float4 c4 = s_tile[wib][j];
-        float d = dist2(qx, qy, qz, c4.x, c4.y, c4.z);
-        int cid = __float_as_int(c4.w);
-        if (d < best || (d == best && cid < bidx)) {
-          best = d;
-          bidx = cid;
-          bpos = t * TILE + j;
-        }
-      }
-      pairs += TILE;
-    };
-
-    int home = -1;
-    if (P.use_seed) {
-      int sp = P.nnpos[s];
-      if (qvalid && sp >= 0) {
-        float4 c4 = P.tgt_sort[sp];
-        best = dist2(qx, qy, qz, c4.x, c4.y, c4.z);
-        bidx = __float_as_int(c4.w);
-        bpos = sp;
-      }
-    } else if (P.tgt_ntiles > 0) {
-      // no seed yet: start with the target tile whose box is closest to this warp's box
-      float mb = INFINITY;
-      int mt = 0;
-      for (int t = lane; t < P.tgt_ntiles; t += 32) {
-        float bd = tile_box_dist2(wb, P.tgt_tb, ntp, t);
-        if (bd < mb) {
-          mb = bd;
-          mt = t;
-        }
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        float ob = __shfl_xor_sync(FULL, mb, o);
-        int ot = __shfl_xor_sync(FULL, mt, o);
-        if (ob < mb || (ob == mb && ot < mt)) {
-          mb = ob;
-          mt = ot;
-        }
-      }
-      home = mt;
-      process_tile(home);
-    }
-    float W = fminf(warp_max(qvalid ? best : -INFINITY), cap);
+    unsigned long long tiles_done = 0;
+    int prev_pos = -1;  // NN of the previous query of this tile: the seed when no stored seed exists
 
 #pragma unroll 1
-    for (int base = 0; base < ntp; base += 32) {
-      int t = base + lane;
-      float bd = tile_box_dist2(wb, P.tgt_tb, ntp, t);
-      bool pass = (t < P.tgt_ntiles) && (t != home) && (bd * CULL_SAFETY <= W);
-      unsigned m = __ballot_sync(FULL, pass);
-      while (m) {
-        int j = __ffs(m) - 1;
-        m &= m - 1;
-        float bdj = __shfl_sync(FULL, bd, j);
-        if (bdj * CULL_SAFETY > W) continue;
-        process_tile(base + j);
-        W = fminf(warp_max(qvalid ? best : -INFINITY), cap);
+    for (int qi = 0; qi < TILE; qi++) {
+      if (!__shfl_sync(FULL, (int)qvalid, qi)) continue;
+      const float qx = __shfl_sync(FULL, qxm, qi), qy = __shfl_sync(FULL, qym, qi), qz = __shfl_sync(FULL, qzm, qi);
+      // per-lane best over the candidates this lane evaluated; rad = warp-uniform best distance so far
+      float bd = INFINITY;
+      int bi = PAD_IDX, bp = -1;
+      float rad = INFINITY;
+
+      auto process_tile = [&](int t) {
+        const float4 c = P.tgt_sort[(size_t)t * TILE + lane];
+        const float d = dist2(qx, qy, qz, c.x, c.y, c.z);
+        const int cid = __float_as_int(c.w);
+        if (lex_lt(d, cid, bd, bi)) {
+          bd = d;
+          bi = cid;
+          bp = t * TILE + lane;
+        }
+        rad = fminf(rad, warp_min(d));
+        tiles_done++;
+      };
+
+      if (P.tgt_ntiles > 0) {
+        int sp = __shfl_sync(FULL, seed_mine, qi);
+        if (sp < 0) sp = prev_pos;
+        if (sp >= 0) {
+          process_tile(sp >> 5);  // the whole tile of the seed: 32 candidates for one coalesced load
+        } else {
+          // no seed at all (first query of a tile in the first iteration): start with the closest box
+          float mb = INFINITY;
+          int ms = 0;
+          for (int s0 = lane; s0 < P.tgt_nsuper; s0 += 32) {
+            const float b = pt_box_dist2(qx, qy, qz, P.tgt_sb, nsp, s0);
+            if (b < mb) {
+              mb = b;
+              ms = s0;
+            }
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(FULL, mb, o);
+            const int os = __shfl_xor_sync(FULL, ms, o);
+            if (ob < mb || (ob == mb && os < ms)) {
+              mb = ob;
+              ms = os;
+            }
+          }
+          int mt = ms * 32 + lane;
+          float tbd = (mt < P.tgt_ntiles) ? pt_box_dist2(qx, qy, qz, P.tgt_tb, ntp, mt) : INFINITY;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(FULL, tbd, o);
+            const int ot = __shfl_xor_sync(FULL, mt, o);
+            if (ob < tbd || (ob == tbd && ot < mt)) {
+              tbd = ob;
+              mt = ot;
+            }
+          }
+          process_tile(mt);
+        }
+        rad = fminf(rad, cap);
+#pragma unroll 1
+        for (int g0 = 0; g0 < nsp; g0 += 32 * SGROUP) {
+          float b1[SGROUP];
+#pragma unroll
+          for (int u = 0; u < SGROUP; u++) {
+            const int s1 = g0 + u * 32 + lane;
+            b1[u] = (s1 < P.tgt_nsuper) ? pt_box_dist2(qx, qy, qz, P.tgt_sb, nsp, s1) : INFINITY;
+          }
+#pragma unroll
+          for (int u = 0; u < SGROUP; u++) {
+            unsigned ms = __ballot_sync(FULL, b1[u] * CULL_SAFETY <= rad);
+            while (ms) {
+              const int js = __ffs(ms) - 1;
+              ms &= ms - 1;
+              if (__shfl_sync(FULL, b1[u], js) * CULL_SAFETY > rad) continue;
+              const int sidx = g0 + u * 32 + js;
+              const int t = sidx * 32 + lane;
+              const float bt = pt_box_dist2(qx, qy, qz, P.tgt_tb, ntp, t);
+              unsigned mt = __ballot_sync(FULL, t < P.tgt_ntiles && bt * CULL_SAFETY <= rad);
+              while (mt) {
+                const int jt = __ffs(mt) - 1;
+                mt &= mt - 1;
+                if (__shfl_sync(FULL, bt, jt) * CULL_SAFETY > rad) continue;
+                process_tile(sidx * 32 + jt);
+              }
+            }
+          }
+        }
+      }
+      // warp arg-min of the per-lane bests under (distance, index)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float od = __shfl_xor_sync(FULL, bd, o);
+        const int oi = __shfl_xor_sync(FULL, bi, o);
+        const int op = __shfl_xor_sync(FULL, bp, o);
+        if (lex_lt(od, oi, bd, bi)) {
+          bd = od;
+          bi = oi;
+          bp = op;
+        }
+      }
+      prev_pos = bp;
+      if (lane == qi) {
+        res_d = bd;
+        res_pos = bp;
       }
     }
-    if (stat_pairs && lane == 0) atomicAdd(stat_pairs, pairs * 32ull);
+    if (stat_pairs && lane == 0) atomicAdd(stat_pairs, tiles_done * 32ull);
+    if (MODE == MODE_LINEARIZE && qvalid) {
+      P.nnpos[s] = res_pos;
+      P.sqd[s] = res_d;
+    }
+  }
+  if (MODE == MODE_FITNESS) {
+    double a0 = 0.0, a1 = 0.0;
+    if (wvalid && qvalid && res_pos >= 0 && (double)res_d <= max_range) {
+      a0 = (double)res_d;
+      a1 = 1.0;
+    }
+    a0 = warp_sum(a0);
+    a1 = warp_sum(a1);
+    if (lane == 0) {
+      s_red[wib][0] = a0;
+      s_red[wib][1] = a1;
+    }
+    __syncthreads();
+    if (threadIdx.x < 2)
+      P.partials[(size_t)blockIdx.x * NRED + threadIdx.x] =
+          ((s_red[0][threadIdx.x] + s_red[1][threadIdx.x]) + s_red[2][threadIdx.x]) + s_red[3][threadIdx.x];
+  }
+}
 
-    if (MODE == MODE_FITNESS) {
-      if (qvalid && bpos >= 0 && (double)best <= max_range) {
-        acc[0] = (double)best;
-        acc[1] = 1.0;
-      }
-    } else {
-      int corr = -1;
-      if (qvalid) {
-        corr = (bpos >= 0 && (double)best < P.thr2) ? bpos : -1;
-        P.corr[s] = corr;
-        P.nnpos[s] = bpos;
-        P.sqd[s] = best;
-      }
+// Mahalanobis + linearisation terms, one thread per SORTED source point.  grid = (ceil(src_ntiles/4), n_active)
+__global__ void __launch_bounds__(128) k_linearize(const PairParams* __restrict__ plist, const int* __restrict__ active,
+                                                   const double* __restrict__ Tbuf) {
+  const int pid = active[blockIdx.y];
+  const PairParams P = plist[pid];
+  __shared__ double s_red[4][NRED];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  if (blockIdx.x * 4 >= P.src_ntiles) return;  // block-uniform
+  const int qt = blockIdx.x * 4 + wib;
+  const double* Td = Tbuf + (size_t)pid * 12;
+  double acc[NRED];
+#pragma unroll
+  for (int i = 0; i < NRED; i++) acc[i] = 0.0;
+  if (qt < P.src_ntiles) {
+    const size_t s = (size_t)qt * TILE + lane;
+    const float4 p = P.src_sort[s];
+    if (__float_as_int(p.w) != PAD_IDX) {
+      const int bpos = P.nnpos[s];
+      const int corr = (bpos >= 0 && (double)P.sqd[s] < P.thr2) ? bpos : -1;
+      P.corr[s] = corr;
       if (corr >= 0) {
         double R[9], tt[3];
 #pragma unroll
@@ -617,14 +712,13 @@ __global__ void __launch_bounds__(128) k_nn1(const PairParams* __restrict__ plis
     }
   }
   // deterministic reduction: lanes -> warp (butterfly) -> block (fixed order) -> one partial row per block
-  constexpr int NV = (MODE == MODE_LINEARIZE) ? NRED : 2;
 #pragma unroll
-  for (int i = 0; i < NV; i++) {
+  for (int i = 0; i < NRED; i++) {
     double v = warp_sum(acc[i]);
     if (lane == 0) s_red[wib][i] = v;
   }
   __syncthreads();
-  if (threadIdx.x < NV) {
+  if (threadIdx.x < NRED) {
     double v = ((s_red[0][threadIdx.x] + s_red[1][threadIdx.x]) + s_red[2][threadIdx.x]) + s_red[3][threadIdx.x];
     P.partials[(size_t)blockIdx.x * NRED + threadIdx.x] = v;
   }
