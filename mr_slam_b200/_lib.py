@@ -90,6 +90,8 @@ def _declare(L):
     L.mrslam_gicp_compute_error.argtypes = [vp, dp, C.POINTER(d)]
     L.mrslam_gicp_stats_enable.argtypes = [i]
     L.mrslam_gicp_stats_pairs.restype = C.c_ulonglong
+    L.mrslam_gicp_stats_get.argtypes = [i]
+    L.mrslam_gicp_stats_get.restype = C.c_ulonglong
 
     if hasattr(L, "mrslam_elev_create"):
         L.mrslam_elev_create.restype = vp

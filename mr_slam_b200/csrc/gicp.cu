@@ -1084,13 +1084,15 @@ int mrslam_gicp_stats_enable(int on) {
   S.stats = on != 0;
   return MRSLAM_OK;
 }
-unsigned long long mrslam_gicp_stats_pairs(void) {
+// which: 0 = kNN distance evaluations, 1 = NN-1 distance evaluations, 2 = k-min insertion rounds
+unsigned long long mrslam_gicp_stats_get(int which) {
   LOCK();
   BatchScratch& S = scratch();
-  unsigned long long v = 0;
-  if (!S.d_stat.p) return 0;
-  cudaMemcpyAsync(&v, S.d_stat.p, sizeof(v), cudaMemcpyDeviceToHost, rt().stream);
+  unsigned long long v[4] = {0, 0, 0, 0};
+  if (!S.d_stat.p || which < 0 || which > 3) return 0;
+  cudaMemcpyAsync(v, S.d_stat.p, sizeof(v), cudaMemcpyDeviceToHost, rt().stream);
   cudaStreamSynchronize(rt().stream);
-  return v;
+  return v[which];
 }
+unsigned long long mrslam_gicp_stats_pairs(void) { return mrslam_gicp_stats_get(0) + mrslam_gicp_stats_get(1); }
 }

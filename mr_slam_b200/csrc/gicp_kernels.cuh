@@ -270,6 +270,30 @@ struct KnnParams {
 
 constexpr int SGROUP = 4;  // super-tile box tests kept in flight together (4 x 32 boxes)
 
+// (distance, index) packed into one 64-bit key: distances are >= +0, so their bit patterns order like
+// unsigned integers and key order == lexicographic (distance, index) order.
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 make_key(float d, int idx) { return ((u64)__float_as_uint(d) << 32) | (unsigned)idx; }
+__device__ __forceinline__ float key_dist(u64 k) { return __uint_as_float((unsigned)(k >> 32)); }
+__device__ __forceinline__ int key_idx(u64 k) { return (int)(unsigned)(k & 0xffffffffull); }
+constexpr u64 KEY_NONE = ((u64)0x7f800000u << 32) | 0x7fffffffu;  // (+inf, PAD_IDX)
+constexpr int PF = 4;  // candidate tiles fetched ahead of their (serial) processing
+
+// ascending bitonic sort of one key per lane
+__device__ __forceinline__ u64 warp_sort_keys(u64 key, int lane) {
+#pragma unroll
+  for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      const u64 other = __shfl_xor_sync(FULL, key, stride);
+      const bool take_min = ((lane & size) == 0) == ((lane & stride) == 0);
+      const u64 lo = key < other ? key : other, hi = key < other ? other : key;
+      key = take_min ? lo : hi;
+    }
+  }
+  return key;
+}
+
 // grid = (ceil(ntiles/4), n_clouds), block = 128; one warp per query tile, queries served one by one
 __global__ void __launch_bounds__(128) k_knn_search(const KnnParams* __restrict__ plist) {
   const KnnParams P = plist[blockIdx.y];
@@ -279,90 +303,116 @@ __global__ void __launch_bounds__(128) k_knn_search(const KnnParams* __restrict_
   const float4 qmine = P.psort[(size_t)qt * TILE + lane];
   const int k = P.k;
   const int ntp = P.ntiles_pad, nsp = P.nsuper_pad;
-  unsigned long long tiles_done = 0;
+  unsigned long long tiles_done = 0, inserts = 0;
+  // the home tiles are the same for every query of this warp: keep them in registers
+  float4 home[2 * HOME_RADIUS + 1];
+#pragma unroll
+  for (int o = 0; o < 2 * HOME_RADIUS + 1; o++) {
+    const int t = qt + o - HOME_RADIUS;
+    home[o] = (t >= 0 && t < P.ntiles) ? P.psort[(size_t)t * TILE + lane]
+                                       : make_float4(PAD_COORD, PAD_COORD, PAD_COORD, __int_as_float(PAD_IDX));
+  }
 
 #pragma unroll 1
   for (int qi = 0; qi < TILE; qi++) {
     const float qx = __shfl_sync(FULL, qmine.x, qi), qy = __shfl_sync(FULL, qmine.y, qi), qz = __shfl_sync(FULL, qmine.z, qi);
     const int qidx = __shfl_sync(FULL, __float_as_int(qmine.w), qi);
     if (qidx == PAD_IDX) continue;
-    // k-best list, one entry per lane, ascending (distance, index); (wd, wi) = current k-th entry
-    float my_d = INFINITY;
-    int my_i = PAD_IDX;
-    float wd = INFINITY;
-    int wi = PAD_IDX;
-
-    auto process_tile = [&](int t) {
-      const float4 c = P.psort[(size_t)t * TILE + lane];
-      const float d = dist2(qx, qy, qz, c.x, c.y, c.z);
-      const int cid = __float_as_int(c.w);
-      unsigned m = __ballot_sync(FULL, lex_lt(d, cid, wd, wi));
-      while (m) {
-        const int j = __ffs(m) - 1;
-        m &= m - 1;
-        const float cd = __shfl_sync(FULL, d, j);
-        const int ci = __shfl_sync(FULL, cid, j);
-        if (!lex_lt(cd, ci, wd, wi)) continue;
-        const float ud = __shfl_up_sync(FULL, my_d, 1);
-        const int ui = __shfl_up_sync(FULL, my_i, 1);
-        const bool before = lex_lt(cd, ci, my_d, my_i);
-        const bool before_prev = lane > 0 && lex_lt(cd, ci, ud, ui);
-        if (before) {
-          my_d = before_prev ? ud : cd;
-          my_i = before_prev ? ui : ci;
+    // super-tile box tests do not depend on the list: issue their loads first
+    float b1[SGROUP];
+#pragma unroll
+    for (int u = 0; u < SGROUP; u++) {
+      const int s1 = u * 32 + lane;
+      b1[u] = (s1 < P.nsuper) ? pt_box_dist2(qx, qy, qz, P.sb, nsp, s1) : INFINITY;
+    }
+    // k-best list, one key per lane, ascending; wkey = current k-th entry
+    u64 my_key;
+    u64 wkey;
+    {  // own tile: all 32 candidates enter the (empty) list -> one bitonic sort instead of 32 insertions
+      const float4 c = home[HOME_RADIUS];
+      my_key = warp_sort_keys(make_key(dist2(qx, qy, qz, c.x, c.y, c.z), __float_as_int(c.w)), lane);
+      wkey = __shfl_sync(FULL, my_key, k - 1);
+      tiles_done++;
+    }
+    auto merge_tile = [&](const float4 c) {
+      const u64 ckey = make_key(dist2(qx, qy, qz, c.x, c.y, c.z), __float_as_int(c.w));
+      unsigned m = __ballot_sync(FULL, ckey < wkey);
+      if (m) {
+        // A candidate that no longer beats the (tightened) k-th entry only touches lanes >= k, which are
+        // never read -- so no re-check and no refresh of wkey inside the loop.
+        while (m) {
+          const int j = __ffs(m) - 1;
+          m &= m - 1;
+          const u64 ck = __shfl_sync(FULL, ckey, j);
+          const u64 up = __shfl_up_sync(FULL, my_key, 1);
+          if (ck < my_key) my_key = (lane > 0 && ck < up) ? up : ck;
+          inserts++;
         }
-        wd = __shfl_sync(FULL, my_d, k - 1);
-        wi = __shfl_sync(FULL, my_i, k - 1);
+        wkey = __shfl_sync(FULL, my_key, k - 1);
       }
       tiles_done++;
     };
-
-    // home tiles first: they fill the list and make the cull radius tight
-    process_tile(qt);
-#pragma unroll 1
+#pragma unroll
     for (int o = 1; o <= HOME_RADIUS; o++) {
-      if (qt - o >= 0) process_tile(qt - o);
-      if (qt + o < P.ntiles) process_tile(qt + o);
+      if (qt - o >= 0) merge_tile(home[HOME_RADIUS - o]);
+      if (qt + o < P.ntiles) merge_tile(home[HOME_RADIUS + o]);
     }
+
 #pragma unroll 1
     for (int g0 = 0; g0 < nsp; g0 += 32 * SGROUP) {
-      float b1[SGROUP];
+      if (g0 > 0) {
 #pragma unroll
-      for (int u = 0; u < SGROUP; u++) {
-        const int s1 = g0 + u * 32 + lane;
-        b1[u] = (s1 < P.nsuper) ? pt_box_dist2(qx, qy, qz, P.sb, nsp, s1) : INFINITY;
+        for (int u = 0; u < SGROUP; u++) {
+          const int s1 = g0 + u * 32 + lane;
+          b1[u] = (s1 < P.nsuper) ? pt_box_dist2(qx, qy, qz, P.sb, nsp, s1) : INFINITY;
+        }
       }
 #pragma unroll
       for (int u = 0; u < SGROUP; u++) {
-        unsigned ms = __ballot_sync(FULL, b1[u] * CULL_SAFETY <= wd);
+        unsigned ms = __ballot_sync(FULL, b1[u] * CULL_SAFETY <= key_dist(wkey));
         while (ms) {
           const int js = __ffs(ms) - 1;
           ms &= ms - 1;
-          if (__shfl_sync(FULL, b1[u], js) * CULL_SAFETY > wd) continue;
+          if (__shfl_sync(FULL, b1[u], js) * CULL_SAFETY > key_dist(wkey)) continue;
           const int sidx = g0 + u * 32 + js;
           const int t = sidx * 32 + lane;
           const float bt = pt_box_dist2(qx, qy, qz, P.tb, ntp, t);
           const int dt = t - qt;
-          unsigned mt = __ballot_sync(FULL, t < P.ntiles && (dt > HOME_RADIUS || dt < -HOME_RADIUS) && bt * CULL_SAFETY <= wd);
+          unsigned mt = __ballot_sync(FULL, t < P.ntiles && (dt > HOME_RADIUS || dt < -HOME_RADIUS) && bt * CULL_SAFETY <= key_dist(wkey));
           while (mt) {
-            const int jt = __ffs(mt) - 1;
-            mt &= mt - 1;
-            if (__shfl_sync(FULL, bt, jt) * CULL_SAFETY > wd) continue;
-            process_tile(sidx * 32 + jt);
+            float4 cc[PF];
+            float bb[PF];
+#pragma unroll
+            for (int f = 0; f < PF; f++) {  // fetch up to PF passing tiles before touching the list
+              bb[f] = INFINITY;
+              if (mt) {
+                const int jt = __ffs(mt) - 1;
+                mt &= mt - 1;
+                bb[f] = __shfl_sync(FULL, bt, jt);
+                cc[f] = P.psort[(size_t)(sidx * 32 + jt) * TILE + lane];
+              }
+            }
+#pragma unroll
+            for (int f = 0; f < PF; f++)
+              if (bb[f] * CULL_SAFETY <= key_dist(wkey)) merge_tile(cc[f]);
           }
         }
       }
     }
     if (lane < k) {
+      const int my_i = key_idx(my_key);
       P.ids[((size_t)qt * TILE + qi) * k + lane] = my_i;
       if (P.knn_idx) {
         const bool real = my_i != PAD_IDX;
         P.knn_idx[(size_t)qidx * k + lane] = real ? my_i : -1;
-        if (P.knn_sqd) P.knn_sqd[(size_t)qidx * k + lane] = real ? my_d : INFINITY;
+        if (P.knn_sqd) P.knn_sqd[(size_t)qidx * k + lane] = real ? key_dist(my_key) : INFINITY;
       }
     }
   }
-  if (P.stat_pairs && lane == 0) atomicAdd(P.stat_pairs, tiles_done * 32ull);
+  if (P.stat_pairs && lane == 0) {
+    atomicAdd(P.stat_pairs, tiles_done * 32ull);
+    atomicAdd(P.stat_pairs + 2, inserts);
+  }
 }
 
 // covariance of the k neighbours (double), one thread per SORTED point; grid = (ceil(npad/128), n_clouds)
@@ -506,28 +556,37 @@ __global__ void __launch_bounds__(128) k_nn1_search(const PairParams* __restrict
       if (!__shfl_sync(FULL, (int)qvalid, qi)) continue;
       const float qx = __shfl_sync(FULL, qxm, qi), qy = __shfl_sync(FULL, qym, qi), qz = __shfl_sync(FULL, qzm, qi);
       // per-lane best over the candidates this lane evaluated; rad = warp-uniform best distance so far
-      float bd = INFINITY;
-      int bi = PAD_IDX, bp = -1;
+      u64 bkey = KEY_NONE;
+      int bp = -1;
       float rad = INFINITY;
 
-      auto process_tile = [&](int t) {
-        const float4 c = P.tgt_sort[(size_t)t * TILE + lane];
+      auto eval_tile = [&](const float4 c, int t) {
         const float d = dist2(qx, qy, qz, c.x, c.y, c.z);
-        const int cid = __float_as_int(c.w);
-        if (lex_lt(d, cid, bd, bi)) {
-          bd = d;
-          bi = cid;
+        const u64 ckey = make_key(d, __float_as_int(c.w));
+        if (ckey < bkey) {
+          bkey = ckey;
           bp = t * TILE + lane;
         }
-        rad = fminf(rad, warp_min(d));
+        rad = fminf(rad, __uint_as_float(__reduce_min_sync(FULL, __float_as_uint(d))));
         tiles_done++;
       };
 
       if (P.tgt_ntiles > 0) {
         int sp = __shfl_sync(FULL, seed_mine, qi);
         if (sp < 0) sp = prev_pos;
+        // loads that do not depend on each other go out together: seed tile + super-tile boxes
+        float4 cseed = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (sp >= 0) cseed = P.tgt_sort[(size_t)(sp >> 5) * TILE + lane];
+        float b1[SGROUP];
+#pragma unroll
+        for (int u = 0; u < SGROUP; u++) {
+          const int s1 = u * 32 + lane;
+          b1[u] = (s1 < P.tgt_nsuper) ? pt_box_dist2(qx, qy, qz, P.tgt_sb, nsp, s1) : INFINITY;
+        }
+        int seed_tile = -1;
         if (sp >= 0) {
-          process_tile(sp >> 5);  // the whole tile of the seed: 32 candidates for one coalesced load
+          seed_tile = sp >> 5;
+          eval_tile(cseed, seed_tile);  // the whole tile of the seed: 32 candidates for one coalesced load
         } else {
           // no seed at all (first query of a tile in the first iteration): start with the closest box
           float mb = INFINITY;
@@ -559,16 +618,18 @@ __global__ void __launch_bounds__(128) k_nn1_search(const PairParams* __restrict
               mt = ot;
             }
           }
-          process_tile(mt);
+          seed_tile = mt;
+          eval_tile(P.tgt_sort[(size_t)mt * TILE + lane], mt);
         }
         rad = fminf(rad, cap);
 #pragma unroll 1
         for (int g0 = 0; g0 < nsp; g0 += 32 * SGROUP) {
-          float b1[SGROUP];
+          if (g0 > 0) {
 #pragma unroll
-          for (int u = 0; u < SGROUP; u++) {
-            const int s1 = g0 + u * 32 + lane;
-            b1[u] = (s1 < P.tgt_nsuper) ? pt_box_dist2(qx, qy, qz, P.tgt_sb, nsp, s1) : INFINITY;
+            for (int u = 0; u < SGROUP; u++) {
+              const int s1 = g0 + u * 32 + lane;
+              b1[u] = (s1 < P.tgt_nsuper) ? pt_box_dist2(qx, qy, qz, P.tgt_sb, nsp, s1) : INFINITY;
+            }
           }
 #pragma unroll
           for (int u = 0; u < SGROUP; u++) {
@@ -580,36 +641,44 @@ __global__ void __launch_bounds__(128) k_nn1_search(const PairParams* __restrict
               const int sidx = g0 + u * 32 + js;
               const int t = sidx * 32 + lane;
               const float bt = pt_box_dist2(qx, qy, qz, P.tgt_tb, ntp, t);
-              unsigned mt = __ballot_sync(FULL, t < P.tgt_ntiles && bt * CULL_SAFETY <= rad);
+              unsigned mt = __ballot_sync(FULL, t < P.tgt_ntiles && t != seed_tile && bt * CULL_SAFETY <= rad);
               while (mt) {
-                const int jt = __ffs(mt) - 1;
-                mt &= mt - 1;
-                if (__shfl_sync(FULL, bt, jt) * CULL_SAFETY > rad) continue;
-                process_tile(sidx * 32 + jt);
+                float4 cc[PF];
+                float bb[PF];
+                int tt[PF];
+#pragma unroll
+                for (int f = 0; f < PF; f++) {  // fetch up to PF passing tiles, then evaluate them in order
+                  bb[f] = INFINITY;
+                  tt[f] = 0;
+                  if (mt) {
+                    const int jt = __ffs(mt) - 1;
+                    mt &= mt - 1;
+                    bb[f] = __shfl_sync(FULL, bt, jt);
+                    tt[f] = sidx * 32 + jt;
+                    cc[f] = P.tgt_sort[(size_t)tt[f] * TILE + lane];
+                  }
+                }
+#pragma unroll
+                for (int f = 0; f < PF; f++)
+                  if (bb[f] * CULL_SAFETY <= rad) eval_tile(cc[f], tt[f]);
               }
             }
           }
         }
       }
-      // warp arg-min of the per-lane bests under (distance, index)
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float od = __shfl_xor_sync(FULL, bd, o);
-        const int oi = __shfl_xor_sync(FULL, bi, o);
-        const int op = __shfl_xor_sync(FULL, bp, o);
-        if (lex_lt(od, oi, bd, bi)) {
-          bd = od;
-          bi = oi;
-          bp = op;
-        }
-      }
-      prev_pos = bp;
+      // warp arg-min of the per-lane bests (key order == (distance, index) order)
+      const unsigned hi = (unsigned)(bkey >> 32), lo = (unsigned)(bkey & 0xffffffffull);
+      const unsigned mhi = __reduce_min_sync(FULL, hi);
+      const unsigned mlo = __reduce_min_sync(FULL, hi == mhi ? lo : 0xffffffffu);
+      const int win = __ffs(__ballot_sync(FULL, hi == mhi && lo == mlo)) - 1;
+      const int wpos = __shfl_sync(FULL, bp, win);
+      prev_pos = wpos;
       if (lane == qi) {
-        res_d = bd;
-        res_pos = bp;
+        res_d = __uint_as_float(mhi);
+        res_pos = wpos;
       }
     }
-    if (stat_pairs && lane == 0) atomicAdd(stat_pairs, tiles_done * 32ull);
+    if (stat_pairs && lane == 0) atomicAdd(stat_pairs + 1, tiles_done * 32ull);
     if (MODE == MODE_LINEARIZE && qvalid) {
       P.nnpos[s] = res_pos;
       P.sqd[s] = res_d;
