@@ -1,0 +1,630 @@
+// elevation.cu -- elevation-mapping point process + order-preserving fuse for sm_100a, and the C-ABI
+// that replaces the free functions of the reference's libgpu.so.
+//
+// Reference (paths relative to Mapping/src/elevation_mapping_periodical/elevation_mapping/):
+//   cuda/gpu_process.cu:384-455   G_pointsprocess      -> k_elev_process
+//   cuda/gpu_process.cu:477-535   G_fuse (O(cells x points), per cell in ascending point index)
+//                                 -> stable radix sort by cell + k_elev_fuse_segments (O(points))
+//   cuda/gpu_process.cu:198-276   init / clear kernels -> k_elev_fill, k_elev_clear_*
+//   cuda/gpu_process.cu:538-545   G_Mapvar_update      -> k_elev_mapvar
+//   cuda/gpu_process.cu:938-1252  host wrappers (Init_GPU_elevationmap, Move, Process_points, Fuse,
+//                                 Mapvar_update, Map_optmove, Map_closeloop)
+//
+// HBM layout: the map is SoA like the reference's (elevation, variance, intensity, lowest, traver :
+// float[L*L]; colour R,G,B : int[L*L]) in ring-buffer storage order.  Per-frame point arrays are SoA
+// device buffers that persist between calls (no cudaMalloc/cudaFree per frame as in the reference).
+//
+// Arithmetic: built with -fmad=false; every fused multiply-add below is explicit and is the
+// contraction nvcc applies to the reference kernels (t=a*b; t=fma(c,d,t) ... left to right), so the
+// cell indices are bit-identical to the reference's and to the CPU oracle's.
+#include <cub/device/device_radix_sort.cuh>
+
+#include <algorithm>
+#include <cmath>
+
+#include "common.cuh"
+
+namespace mrslam {
+
+struct ElevGeom {
+  int L;
+  float res;
+  float cx, cy;    // central_coordinate
+  int sx, sy;      // start_indice
+};
+
+struct ProcParams {
+  float T[16];
+  double lower, upper;
+  float min_r, beam_a, beam_c;
+  float sJ[3], rotVar[9], CSBT[9], PCBM[3], BrBS[9];
+  int near_filter;
+};
+
+__device__ __forceinline__ bool cell_of(const ElevGeom& g, float px, float py, int& ix, int& iy) {
+  // gpu_process.cu:309-358
+  const float sx = px - g.cx, sy = py - g.cy;
+  if (g.L % 2 == 0) {
+    ix = (int)((float)(g.L / 2) - sx / g.res);
+    iy = (int)((float)(g.L / 2) - sy / g.res);
+  } else {
+    ix = g.L / 2 - (int)((double)(sx / g.res) + 0.5 * (sx > 0 ? 1 : -1));
+    iy = g.L / 2 - (int)((double)(sy / g.res) + 0.5 * (sy > 0 ? 1 : -1));
+  }
+  return ix >= 0 && ix < g.L && iy >= 0 && iy < g.L;
+}
+
+__device__ __forceinline__ float atomic_min_float(float* addr, float val) {
+  int* ai = (int*)addr;
+  int old = *ai, assumed;
+  do {
+    assumed = old;
+    old = atomicCAS(ai, assumed, __float_as_int(fminf(val, __int_as_float(assumed))));
+  } while (assumed != old);
+  return __int_as_float(old);
+}
+
+__global__ void k_elev_fill(float* elevation, float* variance, float* intensity, float* lowest, float* traver, int* R, int* G, int* B,
+                            int n, int mode) {
+  // mode 0: G_Init_map, 1: G_Clear_allmap
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  intensity[i] = 0;
+  elevation[i] = -10;
+  variance[i] = -10;
+  if (mode == 0) lowest[i] = 100;
+  traver[i] = -10;
+  R[i] = 0;
+  G[i] = 0;
+  B[i] = 0;
+}
+
+// G_Clear_map(start, shift, row_flag): gpu_process.cu:254-276
+__global__ void k_elev_clear_region(float* elevation, float* variance, float* intensity, int* R, int* G, int* B, int L, int start,
+                                    int shift, int row_flag) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= L * shift) return;
+  size_t c = row_flag ? (size_t)start * L + i : (size_t)(i / shift) * L + i % shift + start;
+  intensity[c] = 0;
+  elevation[c] = -10;
+  variance[c] = -10;
+  R[c] = 0;
+  G[c] = 0;
+  B[c] = 0;
+}
+
+// G_pointsprocess.  Outputs -1 everywhere for dropped points.  keys[i] = map_index or `cells` (sorts last).
+__global__ void k_elev_process(const float* __restrict__ px, const float* __restrict__ py, const float* __restrict__ pz, int n,
+                               ProcParams P, ElevGeom g, float* __restrict__ lowest, int* __restrict__ map_index,
+                               float* __restrict__ var, float* __restrict__ x_ts, float* __restrict__ y_ts, float* __restrict__ z_ts,
+                               int* __restrict__ keys, int* __restrict__ vals) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float x = px[i], y = py[i], z = pz[i];
+  const float* T = P.T;
+  const float height = fmaf(T[10], z, fmaf(T[9], y, T[8] * x)) + T[11];
+  int flag = 0;
+  if (P.near_filter && ((x > -1.5f && x < 1.5f && y > -1.5f && y < 1.5f) || (y > -1.0f && y < 1.0f) || y > 0.0f)) flag = 1;
+  int mi = -1;
+  float hv = -1.f, xt = -1.f, yt = -1.f, zt = -1.f;
+  if (((double)height > P.lower && (double)height < P.upper) && flag == 0) {
+    xt = fmaf(T[2], z, fmaf(T[1], y, T[0] * x)) + T[3];
+    yt = fmaf(T[6], z, fmaf(T[5], y, T[4] * x)) + T[7];
+    zt = height;
+    const float dist = sqrtf(fmaf(z, z, fmaf(y, y, x * x)));
+    const float varN = P.min_r * P.min_r;
+    const float lat = fmaf(P.beam_a, dist, P.beam_c);
+    const float varL = lat * lat;
+    float v[3];
+#pragma unroll
+    for (int r = 0; r < 3; r++) v[r] = fmaf(P.CSBT[3 * r + 2], z, fmaf(P.CSBT[3 * r + 1], y, P.CSBT[3 * r] * x));
+    float S[9] = {0.f, -v[2], v[1], v[2], 0.f, -v[0], -v[1], v[0], 0.f};
+#pragma unroll
+    for (int a = 0; a < 9; a++) S[a] = S[a] + P.BrBS[a];
+    float rJ[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) rJ[c] = fmaf(P.PCBM[2], S[6 + c], fmaf(P.PCBM[1], S[3 + c], P.PCBM[0] * S[c]));
+    float a1[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) a1[c] = fmaf(rJ[2], P.rotVar[6 + c], fmaf(rJ[1], P.rotVar[3 + c], rJ[0] * P.rotVar[c]));
+    hv = fmaf(a1[2], rJ[2], fmaf(a1[1], rJ[1], a1[0] * rJ[0]));
+    const float sv[3] = {varL, varL, varN};
+    float b1[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) b1[c] = P.sJ[c] * sv[c];
+    hv += fmaf(b1[2], P.sJ[2], fmaf(b1[1], P.sJ[1], b1[0] * P.sJ[0]));
+    int ix, iy;
+    if (cell_of(g, xt, yt, ix, iy)) {
+      mi = ((ix + g.sx) % g.L) * g.L + (iy + g.sy) % g.L;
+      const int gi = ix * g.L + iy;
+      // racy in the reference as well (gpu_process.cu:434-438); map_lowest only feeds the ray-tracing clean-up
+      atomic_min_float(&lowest[gi], height);
+      if (height == lowest[gi]) lowest[gi] = lowest[gi] + 3 * hv;
+    }
+  }
+  if (map_index) map_index[i] = mi;
+  if (var) var[i] = hv;
+  if (x_ts) {
+    x_ts[i] = xt;
+    y_ts[i] = yt;
+  }
+  if (z_ts) z_ts[i] = zt;
+  if (keys) {
+    keys[i] = (mi >= 0 && zt != -1.f) ? mi : g.L * g.L;
+    vals[i] = i;
+  }
+}
+
+// keys for Fuse() called with caller-provided indices
+__global__ void k_elev_keys(const int* __restrict__ idx, const float* __restrict__ h, int n, int cells, int* keys, int* vals) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int c = idx[i];
+  keys[i] = (c >= 0 && c < cells && h[i] != -1.f) ? c : cells;
+  vals[i] = i;
+}
+
+// One thread per run of equal cell keys (points inside a run are in ascending point index because the
+// radix sort is stable): the sequential recurrence of G_fuse, gpu_process.cu:477-535.
+__global__ void k_elev_fuse_segments(const int* __restrict__ keys, const int* __restrict__ order, int n, int cells,
+                                     const float* __restrict__ ph, const float* __restrict__ pv, const int* __restrict__ cR,
+                                     const int* __restrict__ cG, const int* __restrict__ cB, const float* __restrict__ inten,
+                                     float* __restrict__ elevation, float* __restrict__ variance, float* __restrict__ intensity,
+                                     int* __restrict__ R, int* __restrict__ G, int* __restrict__ B, unsigned long long* n_fused) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int c = keys[i];
+  if (c >= cells) return;
+  if (i > 0 && keys[i - 1] == c) return;  // not the head of a run
+  float e = elevation[c], v = variance[c];
+  float ci = 0.f;
+  int cr = 0, cg = 0, cb = 0;
+  bool colour_written = false;
+  int cnt = 0;
+  for (int j = i; j < n && keys[j] == c; j++) {
+    const int pi = order[j];
+    const float h = ph[pi], hv = pv[pi];
+    cnt++;
+    bool colour = false;
+    if (cR) colour = cR[pi] != 0 && cG[pi] != 0 && cB[pi] != 0 && inten[pi] != 0.f;
+    bool wc = false;
+    if (e == -10.f) {
+      e = h;
+      v = hv;
+      wc = colour;
+    } else {
+      const float md = fabsf(h - e) / sqrtf(v);
+      if (md > 5.f) {
+        if (e < h) {
+          e = h;
+          v = hv;
+          wc = colour;
+        }
+      } else {
+        const float ne = fmaf(v, h, hv * e) / (v + hv);
+        const float nv = (hv * v) / (hv + v);
+        e = ne;
+        v = nv;
+        wc = colour;
+      }
+    }
+    if (wc) {
+      ci = inten[pi];
+      cr = cR[pi];
+      cg = cG[pi];
+      cb = cB[pi];
+      colour_written = true;
+    }
+  }
+  elevation[c] = e;
+  variance[c] = v;
+  if (colour_written) {
+    intensity[c] = ci;
+    R[c] = cr;
+    G[c] = cg;
+    B[c] = cb;
+  }
+  if (n_fused) atomicAdd(n_fused, (unsigned long long)cnt);
+}
+
+// tail of G_fuse (gpu_process.cu:531-532): every cell, including empty ones
+__global__ void k_elev_clamp_var(float* __restrict__ variance, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int i4 = i * 4;
+  if (i4 + 3 < n) {
+    float4 v = reinterpret_cast<float4*>(variance)[i];
+    bool ch = v.x < 0.0001f || v.y < 0.0001f || v.z < 0.0001f || v.w < 0.0001f;
+    if (ch) {
+      v.x = v.x < 0.0001f ? 0.0001f : v.x;
+      v.y = v.y < 0.0001f ? 0.0001f : v.y;
+      v.z = v.z < 0.0001f ? 0.0001f : v.z;
+      v.w = v.w < 0.0001f ? 0.0001f : v.w;
+      reinterpret_cast<float4*>(variance)[i] = v;
+    }
+  } else {
+    for (int j = i4; j < n; j++)
+      if (variance[j] < 0.0001f) variance[j] = 0.0001f;
+  }
+}
+
+__global__ void k_elev_mapvar(float* __restrict__ variance, int n, float upd) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && variance[i] != -10.f) variance[i] += upd;
+}
+__global__ void k_elev_height(float* __restrict__ elevation, int n, float upd) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && elevation[i] != -10.f) elevation[i] += upd;
+}
+
+struct Elev {
+  ElevGeom g{0, 0.f, 0.f, 0.f, 0, 0};
+  float mahal_thr = 0, obstacle_thr = 0, sensor_z = 0;
+  DevBuf<float> elevation, variance, intensity, lowest, traver;
+  DevBuf<int> R, G, B;
+  // per-frame buffers
+  DevBuf<float> px, py, pz, pvar, pxt, pyt, pzt, pint, ph;
+  DevBuf<int> pidx, pR, pG, pB, keys, keys_alt, vals, vals_alt;
+  DevBuf<unsigned char> cubtmp;
+  DevBuf<unsigned long long> counter;
+  std::mutex mu;  // Fuse and Mapvar_update may be called from two threads (ElevationMapping.cpp:393-394)
+
+  int cells() const { return g.L * g.L; }
+  int reserve_points(int n) {
+    size_t m = std::max(n, 1);
+    MR_CHECK(px.reserve(m)); MR_CHECK(py.reserve(m)); MR_CHECK(pz.reserve(m));
+    MR_CHECK(pvar.reserve(m)); MR_CHECK(pxt.reserve(m)); MR_CHECK(pyt.reserve(m)); MR_CHECK(pzt.reserve(m));
+    MR_CHECK(pint.reserve(m)); MR_CHECK(ph.reserve(m));
+    MR_CHECK(pidx.reserve(m)); MR_CHECK(pR.reserve(m)); MR_CHECK(pG.reserve(m)); MR_CHECK(pB.reserve(m));
+    MR_CHECK(keys.reserve(m)); MR_CHECK(keys_alt.reserve(m)); MR_CHECK(vals.reserve(m)); MR_CHECK(vals_alt.reserve(m));
+    MR_CHECK(counter.reserve(2));
+    return MRSLAM_OK;
+  }
+  void release() {
+    for (DevBuf<float>* b : {&elevation, &variance, &intensity, &lowest, &traver, &px, &py, &pz, &pvar, &pxt, &pyt, &pzt, &pint, &ph}) b->release();
+    for (DevBuf<int>* b : {&R, &G, &B, &pidx, &pR, &pG, &pB, &keys, &keys_alt, &vals, &vals_alt}) b->release();
+    cubtmp.release();
+    counter.release();
+  }
+};
+
+// sort (keys = cell, vals = point index), fuse runs, clamp.  Arrays are device pointers.
+static int fuse_sorted(Elev* m, int n, const float* d_h, const float* d_v, const int* d_R, const int* d_G, const int* d_B,
+                       const float* d_I, long long* n_fused) {
+  cudaStream_t st = rt().stream;
+  const int cells = m->cells();
+  if (n > 0) {
+    int bits = 1;
+    while ((1ll << bits) <= cells) bits++;
+    cub::DoubleBuffer<int> dk(m->keys.p, m->keys_alt.p), dv(m->vals.p, m->vals_alt.p);
+    size_t tmp = 0;
+    MR_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp, dk, dv, n, 0, bits, st));
+    MR_CHECK(m->cubtmp.reserve(tmp));
+    MR_CUDA(cub::DeviceRadixSort::SortPairs(m->cubtmp.p, tmp, dk, dv, n, 0, bits, st));
+    MR_CUDA(cudaMemsetAsync(m->counter.p, 0, sizeof(unsigned long long), st));
+    k_elev_fuse_segments<<<(n + 127) / 128, 128, 0, st>>>(dk.Current(), dv.Current(), n, cells, d_h, d_v, d_R, d_G, d_B, d_I,
+                                                         m->elevation.p, m->variance.p, m->intensity.p, m->R.p, m->G.p, m->B.p,
+                                                         m->counter.p);
+    count_launch(1);
+  }
+  k_elev_clamp_var<<<((cells + 3) / 4 + 255) / 256, 256, 0, st>>>(m->variance.p, cells);
+  count_launch(1);
+  MR_CUDA(cudaGetLastError());
+  if (n_fused) {
+    unsigned long long c = 0;
+    if (n > 0) MR_CUDA(cudaMemcpyAsync(&c, m->counter.p, sizeof(c), cudaMemcpyDeviceToHost, st));
+    MR_CUDA(cudaStreamSynchronize(st));
+    *n_fused = (long long)c;
+  }
+  return MRSLAM_OK;
+}
+
+static void fill_proc(ProcParams& P, const float* T16, double lower, double upper, float min_r, float beam_a, float beam_c,
+                      const float* sJ, const float* rotVar, const float* CSBT, const float* PCBM, const float* BrBS, int near_filter) {
+  memcpy(P.T, T16, sizeof(float) * 16);
+  P.lower = lower; P.upper = upper;
+  P.min_r = min_r; P.beam_a = beam_a; P.beam_c = beam_c;
+  memcpy(P.sJ, sJ, 12); memcpy(P.rotVar, rotVar, 36); memcpy(P.CSBT, CSBT, 36); memcpy(P.PCBM, PCBM, 12); memcpy(P.BrBS, BrBS, 36);
+  P.near_filter = near_filter;
+}
+
+// host helpers of gpu_process.cu:890-918, 994-1000
+static int index_to_range(int index, int L) {
+  if (index < 0) index += ((-index / L) + 1) * L;
+  return index % L;
+}
+static float position_to_range(float p, float shift, float res) {
+  int p_index = (int)std::round(p / res);
+  int shift_index = (int)std::round(shift / res);
+  return (p_index + shift_index) * res;
+}
+static void index_shift(int* ishift, const float* pshift, float res) {
+  for (int i = 0; i < 2; i++) ishift[i] = static_cast<int>(pshift[i] / res + 0.5 * (pshift[i] > 0 ? 1 : -1));
+}
+
+}  // namespace mrslam
+
+using namespace mrslam;
+#define E(h) (reinterpret_cast<Elev*>(h))
+#define REQ(h)                                   \
+  do {                                           \
+    if (!(h)) {                                  \
+      set_error("%s: null handle", __func__);    \
+      return MRSLAM_ERR_ARG;                     \
+    }                                            \
+  } while (0)
+#define REQ_INIT(m)                                             \
+  do {                                                          \
+    if ((m)->g.L <= 0) {                                        \
+      set_error("%s: Init_GPU_elevationmap not called", __func__); \
+      return MRSLAM_ERR_STATE;                                  \
+    }                                                           \
+  } while (0)
+
+extern "C" {
+
+mrslam_elev_t* mrslam_elev_create(void) {
+  if (ensure_init() != MRSLAM_OK) return nullptr;
+  return reinterpret_cast<mrslam_elev_t*>(new Elev());
+}
+void mrslam_elev_destroy(mrslam_elev_t* h) {
+  if (!h) return;
+  std::lock_guard<std::mutex> lk(rt().mu);
+  E(h)->release();
+  delete E(h);
+}
+
+int mrslam_elev_init(mrslam_elev_t* h, int length, float resolution, float mahal, float obst) {
+  REQ(h);
+  MR_CHECK(ensure_init());
+  if (length <= 0 || !(resolution > 0.f)) {
+    set_error("Init_GPU_elevationmap: bad length/resolution");
+    return MRSLAM_ERR_ARG;
+  }
+  Elev* m = E(h);
+  std::lock_guard<std::mutex> lk2(m->mu);
+  std::lock_guard<std::mutex> lk(rt().mu);
+  m->g = ElevGeom{length, resolution, 0.f, 0.f, 0, 0};
+  m->mahal_thr = mahal;
+  m->obstacle_thr = obst;
+  size_t n = (size_t)length * length;
+  for (DevBuf<float>* b : {&m->elevation, &m->variance, &m->intensity, &m->lowest, &m->traver}) MR_CHECK(b->reserve(n + 4));
+  for (DevBuf<int>* b : {&m->R, &m->G, &m->B}) MR_CHECK(b->reserve(n));
+  k_elev_fill<<<((int)n + 255) / 256, 256, 0, rt().stream>>>(m->elevation.p, m->variance.p, m->intensity.p, m->lowest.p, m->traver.p,
+                                                               m->R.p, m->G.p, m->B.p, (int)n, 0);
+  count_launch(1);
+  MR_CUDA(cudaGetLastError());
+  return MRSLAM_OK;
+}
+
+int mrslam_elev_move(mrslam_elev_t* h, const float* pos, float resolution, int length, float* central_out, int* start_out,
+                     float* shift_out) {
+  REQ(h);
+  Elev* m = E(h);
+  REQ_INIT(m);
+  std::lock_guard<std::mutex> lk2(m->mu);
+  std::lock_guard<std::mutex> lk(rt().mu);
+  cudaStream_t st = rt().stream;
+  int ishift[2];
+  float pshift[2];
+  m->sensor_z = pos[2];
+  float hc[2] = {m->g.cx, m->g.cy};
+  int hs[2] = {m->g.sx, m->g.sy};
+  pshift[0] = pos[0] - hc[0];
+  pshift[1] = pos[1] - hc[1];
+  index_shift(ishift, pshift, resolution);
+  float ashift[2];
+  for (int i = 0; i < 2; i++) ashift[i] = (float)ishift[i] * resolution;
+  auto clear = [&](int start, int ncell, int row) {
+    int cnt = ncell * length;
+    if (cnt <= 0) return;
+    k_elev_clear_region<<<(cnt + 255) / 256, 256, 0, st>>>(m->elevation.p, m->variance.p, m->intensity.p, m->R.p, m->G.p, m->B.p, length,
+                                                          start, ncell, row);
+    count_launch(1);
+  };
+  for (int i = 0; i < 2; i++) {
+    if (ishift[i] != 0) {
+      if (ishift[i] >= length) {
+        int n = length * length;
+        k_elev_fill<<<(n + 127) / 128, 128, 0, st>>>(m->elevation.p, m->variance.p, m->intensity.p, m->lowest.p, m->traver.p, m->R.p,
+                                                    m->G.p, m->B.p, n, 1);
+        count_launch(1);
+      } else {
+        int sign = ishift[i] > 0 ? 1 : -1;
+        int startIndex = hs[i] - (sign > 0 ? 1 : 0);
+        int endIndex = startIndex + sign - ishift[i];
+        int nCells = std::abs(ishift[i]);
+        int index = sign < 0 ? startIndex : endIndex;
+        index = index_to_range(index, length);
+        if (index + nCells <= length) {
+          clear(index, nCells, i == 0);
+        } else {
+          int firstn = length - index;
+          clear(index, firstn, i == 0);
+          clear(0, nCells - firstn, i == 0);
+        }
+      }
+    }
+    hs[i] -= ishift[i];
+    hs[i] = index_to_range(hs[i], length);
+    hc[i] = position_to_range(hc[i], ashift[i], resolution);
+  }
+  MR_CUDA(cudaGetLastError());
+  m->g.cx = hc[0]; m->g.cy = hc[1];
+  m->g.sx = hs[0]; m->g.sy = hs[1];
+  if (central_out) { central_out[0] = hc[0]; central_out[1] = hc[1]; }
+  if (start_out) { start_out[0] = hs[0]; start_out[1] = hs[1]; }
+  if (shift_out) { shift_out[0] = ashift[0]; shift_out[1] = ashift[1]; }
+  return MRSLAM_OK;
+}
+
+int mrslam_elev_process_points(mrslam_elev_t* h, int* map_index, const float* x, const float* y, const float* z, float* var,
+                               float* x_ts, float* y_ts, float* z_ts, const float* T16, int n, double lower, double upper, float min_r,
+                               float beam_a, float beam_c, const float* sJ, const float* rotVar, const float* CSBT, const float* PCBM,
+                               const float* BrBS) {
+  REQ(h);
+  Elev* m = E(h);
+  REQ_INIT(m);
+  if (n < 0) {
+    set_error("Process_points: n < 0");
+    return MRSLAM_ERR_ARG;
+  }
+  std::lock_guard<std::mutex> lk2(m->mu);
+  std::lock_guard<std::mutex> lk(rt().mu);
+  cudaStream_t st = rt().stream;
+  MR_CHECK(m->reserve_points(n));
+  if (n == 0) return MRSLAM_OK;
+  size_t b = sizeof(float) * (size_t)n;
+  MR_CUDA(cudaMemcpyAsync(m->px.p, x, b, cudaMemcpyHostToDevice, st));
+  MR_CUDA(cudaMemcpyAsync(m->py.p, y, b, cudaMemcpyHostToDevice, st));
+  MR_CUDA(cudaMemcpyAsync(m->pz.p, z, b, cudaMemcpyHostToDevice, st));
+  ProcParams P;
+  fill_proc(P, T16, lower, upper, min_r, beam_a, beam_c, sJ, rotVar, CSBT, PCBM, BrBS, 1);
+  k_elev_process<<<(n + 255) / 256, 256, 0, st>>>(m->px.p, m->py.p, m->pz.p, n, P, m->g, m->lowest.p, m->pidx.p, m->pvar.p, m->pxt.p,
+                                                 m->pyt.p, m->pzt.p, nullptr, nullptr);
+  count_launch(1);
+  MR_CUDA(cudaGetLastError());
+  MR_CUDA(cudaMemcpyAsync(var, m->pvar.p, b, cudaMemcpyDeviceToHost, st));
+  MR_CUDA(cudaMemcpyAsync(z_ts, m->pzt.p, b, cudaMemcpyDeviceToHost, st));
+  MR_CUDA(cudaMemcpyAsync(map_index, m->pidx.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, st));
+  MR_CUDA(cudaMemcpyAsync(x_ts, m->pxt.p, b, cudaMemcpyDeviceToHost, st));
+  MR_CUDA(cudaMemcpyAsync(y_ts, m->pyt.p, b, cudaMemcpyDeviceToHost, st));
+  MR_CUDA(cudaStreamSynchronize(st));
+  return MRSLAM_OK;
+}
+
+int mrslam_elev_fuse(mrslam_elev_t* h, int length, int n, const int* idx, const int* R, const int* G, const int* B,
+                     const float* intensity, const float* height, const float* var, long long* n_fused) {
+  REQ(h);
+  Elev* m = E(h);
+  REQ_INIT(m);
+  if (length != m->g.L || n < 0) {
+    set_error("Fuse: length %d does not match the initialised map (%d)", length, m->g.L);
+    return MRSLAM_ERR_ARG;
+  }
+  std::lock_guard<std::mutex> lk2(m->mu);
+  std::lock_guard<std::mutex> lk(rt().mu);
+  cudaStream_t st = rt().stream;
+  MR_CHECK(m->reserve_points(n));
+  if (n > 0) {
+    size_t bi = sizeof(int) * (size_t)n, bf = sizeof(float) * (size_t)n;
+    MR_CUDA(cudaMemcpyAsync(m->pidx.p, idx, bi, cudaMemcpyHostToDevice, st));
+    MR_CUDA(cudaMemcpyAsync(m->pR.p, R, bi, cudaMemcpyHostToDevice, st));
+    MR_CUDA(cudaMemcpyAsync(m->pG.p, G, bi, cudaMemcpyHostToDevice, st));
+    MR_CUDA(cudaMemcpyAsync(m->pB.p, B, bi, cudaMemcpyHostToDevice, st));
+    MR_CUDA(cudaMemcpyAsync(m->pint.p, intensity, bf, cudaMemcpyHostToDevice, st));
+    MR_CUDA(cudaMemcpyAsync(m->ph.p, height, bf, cudaMemcpyHostToDevice, st));
+    MR_CUDA(cudaMemcpyAsync(m->pvar.p, var, bf, cudaMemcpyHostToDevice, st));
+    k_elev_keys<<<(n + 255) / 256, 256, 0, st>>>(m->pidx.p, m->ph.p, n, m->cells(), m->keys.p, m->vals.p);
+    count_launch(1);
+  }
+  int s = fuse_sorted(m, n, m->ph.p, m->pvar.p, m->pR.p, m->pG.p, m->pB.p, m->pint.p, n_fused);
+  if (s == MRSLAM_OK && !n_fused) MR_CUDA(cudaStreamSynchronize(st));  // Fuse is synchronous for the caller
+  return s;
+}
+
+int mrslam_elev_process_fuse_device(mrslam_elev_t* h, const float* d_x, const float* d_y, const float* d_z, int n, const float* T16,
+                                    double lower, double upper, float min_r, float beam_a, float beam_c, const float* sJ,
+                                    const float* rotVar, const float* CSBT, const float* PCBM, const float* BrBS, int near_filter,
+                                    long long* n_fused) {
+  REQ(h);
+  Elev* m = E(h);
+  REQ_INIT(m);
+  if (n < 0) {
+    set_error("process_fuse_device: n < 0");
+    return MRSLAM_ERR_ARG;
+  }
+  std::lock_guard<std::mutex> lk2(m->mu);
+  std::lock_guard<std::mutex> lk(rt().mu);
+  cudaStream_t st = rt().stream;
+  MR_CHECK(m->reserve_points(n));
+  if (n > 0) {
+    ProcParams P;
+    fill_proc(P, T16, lower, upper, min_r, beam_a, beam_c, sJ, rotVar, CSBT, PCBM, BrBS, near_filter);
+    k_elev_process<<<(n + 255) / 256, 256, 0, st>>>(d_x, d_y, d_z, n, P, m->g, m->lowest.p, nullptr, m->pvar.p, nullptr, nullptr,
+                                                   m->pzt.p, m->keys.p, m->vals.p);
+    count_launch(1);
+  }
+  return fuse_sorted(m, n, m->pzt.p, m->pvar.p, nullptr, nullptr, nullptr, nullptr, n_fused);
+}
+
+int mrslam_elev_mapvar_update(mrslam_elev_t* h, int length, float upd) {
+  REQ(h);
+  Elev* m = E(h);
+  REQ_INIT(m);
+  std::lock_guard<std::mutex> lk2(m->mu);
+  std::lock_guard<std::mutex> lk(rt().mu);
+  int n = length * length;
+  k_elev_mapvar<<<(n + 255) / 256, 256, 0, rt().stream>>>(m->variance.p, std::min(n, m->cells()), upd);
+  count_launch(1);
+  MR_CUDA(cudaGetLastError());
+  return MRSLAM_OK;
+}
+
+int mrslam_elev_map_optmove(mrslam_elev_t* h, const float* opt_p, float height_update, float resolution, int length, float* out2) {
+  REQ(h);
+  Elev* m = E(h);
+  REQ_INIT(m);
+  std::lock_guard<std::mutex> lk2(m->mu);
+  std::lock_guard<std::mutex> lk(rt().mu);
+  float last[2] = {m->g.cx, m->g.cy};
+  for (int i = 0; i < 2; i++) {
+    float ps = opt_p[i] - last[i];
+    int is = static_cast<int>(ps / resolution + 0.5 * (ps > 0 ? 1 : -1));
+    out2[i] = last[i] + resolution * is;
+  }
+  m->g.cx = out2[0];
+  m->g.cy = out2[1];
+  int n = std::min(length * length, m->cells());
+  k_elev_height<<<(n + 255) / 256, 256, 0, rt().stream>>>(m->elevation.p, n, height_update);
+  count_launch(1);
+  MR_CUDA(cudaGetLastError());
+  return MRSLAM_OK;
+}
+
+int mrslam_elev_map_closeloop(mrslam_elev_t* h, const float* upos, float height_update, int length, float resolution) {
+  REQ(h);
+  Elev* m = E(h);
+  REQ_INIT(m);
+  std::lock_guard<std::mutex> lk2(m->mu);
+  std::lock_guard<std::mutex> lk(rt().mu);
+  int ishift[2];
+  float pshift[2] = {upos[0] - m->g.cx, upos[1] - m->g.cy}, ashift[2];
+  index_shift(ishift, pshift, resolution);
+  for (int i = 0; i < 2; i++) ashift[i] = (float)ishift[i] * resolution;
+  m->g.cx = position_to_range(m->g.cx, ashift[0], resolution);
+  m->g.cy = position_to_range(m->g.cy, ashift[1], resolution);
+  int n = std::min(length * length, m->cells());
+  k_elev_height<<<(n + 255) / 256, 256, 0, rt().stream>>>(m->elevation.p, n, height_update);
+  count_launch(1);
+  MR_CUDA(cudaGetLastError());
+  return MRSLAM_OK;
+}
+
+int mrslam_elev_get_map(mrslam_elev_t* h, float* elevation, float* variance, float* intensity, int* R, int* G, int* B, float* lowest) {
+  REQ(h);
+  Elev* m = E(h);
+  REQ_INIT(m);
+  std::lock_guard<std::mutex> lk2(m->mu);
+  std::lock_guard<std::mutex> lk(rt().mu);
+  cudaStream_t st = rt().stream;
+  size_t n = (size_t)m->cells();
+  if (elevation) MR_CUDA(cudaMemcpyAsync(elevation, m->elevation.p, n * 4, cudaMemcpyDeviceToHost, st));
+  if (variance) MR_CUDA(cudaMemcpyAsync(variance, m->variance.p, n * 4, cudaMemcpyDeviceToHost, st));
+  if (intensity) MR_CUDA(cudaMemcpyAsync(intensity, m->intensity.p, n * 4, cudaMemcpyDeviceToHost, st));
+  if (R) MR_CUDA(cudaMemcpyAsync(R, m->R.p, n * 4, cudaMemcpyDeviceToHost, st));
+  if (G) MR_CUDA(cudaMemcpyAsync(G, m->G.p, n * 4, cudaMemcpyDeviceToHost, st));
+  if (B) MR_CUDA(cudaMemcpyAsync(B, m->B.p, n * 4, cudaMemcpyDeviceToHost, st));
+  if (lowest) MR_CUDA(cudaMemcpyAsync(lowest, m->lowest.p, n * 4, cudaMemcpyDeviceToHost, st));
+  MR_CUDA(cudaStreamSynchronize(st));
+  return MRSLAM_OK;
+}
+int mrslam_elev_get_state(mrslam_elev_t* h, float* central2, int* start2) {
+  REQ(h);
+  Elev* m = E(h);
+  central2[0] = m->g.cx;
+  central2[1] = m->g.cy;
+  start2[0] = m->g.sx;
+  start2[1] = m->g.sy;
+  return MRSLAM_OK;
+}
+}

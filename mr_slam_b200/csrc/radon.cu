@@ -1,0 +1,352 @@
+// radon.cu -- parallel-beam Radon forward projection and the RING descriptor tail / matcher for sm_100a.
+//
+// Reference (paths relative to LoopDetection/):
+//   torch-radon/src/forward.cu:12-124     radon_forward_kernel<parallel_beam=true>  -> k_radon_forward
+//   torch-radon/src/texture.cu:114-189    texture upload, border addressing, linear filter (replaced by a shared-
+//                                         memory resident image and a software bilinear fetch)
+//   src/RING_ros/util.py:197-198          normalise + fft2(dim=-2, "ortho")          -> k_ring_stats + k_ring_tiring
+//   src/RING_ros/util.py:362-374          fast_corr                                  -> k_ring_fast_corr
+//
+// Radon kernel: one block per (image, group of ANGLES_PER_BLOCK angles); the image (H*W*4 B, 57.6 KB for RING)
+// is staged once in shared memory with coalesced float4 loads and every ray of the group marches through it
+// there -- no texture objects, no cudaArray upload, deterministic fp32.  interp = 1 emulates the texture unit's
+// 8-bit fractional weights so results track the reference's hardware-filtered numbers, interp = 0 is exact bilinear.
+// On-chip bound (shared-memory gathers); HBM floor per image = read H*W*4 + write A*D*4.
+#include <algorithm>
+#include <cmath>
+
+#include "common.cuh"
+
+namespace mrslam {
+
+constexpr int ANGLES_PER_BLOCK = 8;
+constexpr int RADON_THREADS = 128;
+
+template <bool SMEM>
+__device__ __forceinline__ float texel(const float* __restrict__ img, int W, int H, int i, int j) {
+  return (i >= 0 && i < W && j >= 0 && j < H) ? img[j * W + i] : 0.0f;  // cudaAddressModeBorder
+}
+
+template <bool SMEM>
+__device__ __forceinline__ float tex2d(const float* __restrict__ img, int W, int H, float x, float y, int interp) {
+  const float xb = x - 0.5f, yb = y - 0.5f;
+  const float fi = floorf(xb), fj = floorf(yb);
+  float a = xb - fi, b = yb - fj;
+  if (interp) {
+    a = rintf(a * 256.0f) / 256.0f;
+    b = rintf(b * 256.0f) / 256.0f;
+  }
+  const int i = (int)fi, j = (int)fj;
+  const float t00 = texel<SMEM>(img, W, H, i, j), t10 = texel<SMEM>(img, W, H, i + 1, j);
+  const float t01 = texel<SMEM>(img, W, H, i, j + 1), t11 = texel<SMEM>(img, W, H, i + 1, j + 1);
+  const float w00 = (1.0f - a) * (1.0f - b), w10 = a * (1.0f - b), w01 = (1.0f - a) * b, w11 = a * b;
+  return fmaf(w11, t11, fmaf(w01, t01, fmaf(w10, t10, w00 * t00)));
+}
+
+template <bool SMEM>
+__global__ void __launch_bounds__(RADON_THREADS) k_radon_forward(const float* __restrict__ img, int H, int W,
+                                                                 const float* __restrict__ angles, int n_angles, int det_count,
+                                                                 float det_spacing, int interp, int fast_trig,
+                                                                 float* __restrict__ out) {
+  extern __shared__ float s_img[];
+  const int b = blockIdx.y;
+  const float* im = img + (size_t)b * H * W;
+  if (SMEM) {
+    const int n = H * W;
+    if ((n & 3) == 0 && ((size_t)im & 15) == 0) {
+      const float4* src = reinterpret_cast<const float4*>(im);
+      float4* dst = reinterpret_cast<float4*>(s_img);
+      for (int i = threadIdx.x; i < n / 4; i += blockDim.x) dst[i] = src[i];
+    } else {
+      for (int i = threadIdx.x; i < n; i += blockDim.x) s_img[i] = im[i];
+    }
+    __syncthreads();
+    im = s_img;
+  }
+  const int a0 = blockIdx.x * ANGLES_PER_BLOCK;
+  const int a1 = min(a0 + ANGLES_PER_BLOCK, n_angles);
+  const float fW = (float)W, fH = (float)H;
+  for (int angle_id = a0; angle_id < a1; angle_id++) {
+    const float angle = angles[angle_id];
+    // accurate mode: double-precision value rounded to float (same bits as the CPU oracle); fast mode: the
+    // reference kernel's intrinsics (forward.cu:46-47)
+    const float cs = fast_trig ? __cosf(angle) : (float)cos((double)angle);
+    const float sn = fast_trig ? __sinf(angle) : (float)sin((double)angle);
+    for (int ray_id = threadIdx.x; ray_id < det_count; ray_id += blockDim.x) {
+      float* o = out + ((size_t)b * n_angles + angle_id) * det_count + ray_id;
+      // forward.cu:33-37 (parallel beam; Volume2D(): dx = dy = 0, sx = sy = 1)
+      const float sx = ((float)ray_id - (float)det_count * 0.5f + 0.5f) * det_spacing;
+      const float sy = hypotf(fW * 0.5f, fH * 0.5f);
+      const float ex = sx, ey = -sy;
+      float rsx = fmaf(sy, sn, sx * cs);
+      float rsy = fmaf(sy, cs, -sx * sn);
+      float rdx = fmaf(ey, sn, ex * cs) - rsx;
+      float rdy = fmaf(ey, cs, -ex * sn) - rsy;
+      const float vol_orig_x = 0.0f - 0.5f * fW * 1.0f;
+      const float vol_orig_y = 0.0f - 0.5f * fH * 1.0f;
+      rsx = (rsx - vol_orig_x) * 1.0f;
+      rsy = (rsy - vol_orig_y) * 1.0f;
+      // clip to the volume, forward.cu:63-80
+      const float dx = rdx >= 0 ? (float)fmax((double)rdx, 1e-6) : (float)fmin((double)rdx, -1e-6);
+      const float dy = rdy >= 0 ? (float)fmax((double)rdy, 1e-6) : (float)fmin((double)rdy, -1e-6);
+      const float alpha_x_m = (-rsx) / dx, alpha_x_p = (fW - rsx) / dx;
+      const float alpha_y_m = (-rsy) / dy, alpha_y_p = (fH - rsy) / dy;
+      const float alpha_s = fmaxf(fminf(alpha_x_p, alpha_x_m), fminf(alpha_y_p, alpha_y_m));
+      const float alpha_e = fminf(fmaxf(alpha_x_p, alpha_x_m), fmaxf(alpha_y_p, alpha_y_m));
+      if ((double)alpha_s > (double)alpha_e - 1e-6) {
+        *o = 0.0f;
+        continue;
+      }
+      rsx = fmaf(rdx, alpha_s, rsx);
+      rsy = fmaf(rdy, alpha_s, rsy);
+      rdx *= (alpha_e - alpha_s);
+      rdy *= (alpha_e - alpha_s);
+      const float mx = fmaxf(fabsf(rdx), fabsf(rdy));
+      const int n_steps = __float2int_rn(mx);
+      const float vx = rdx / mx, vy = rdy / mx;
+      const float nrm = hypotf(vx, vy);
+      float step;
+      if (fabsf(rdy) >= fabsf(rdx)) {
+        const float y_inc = 0.5f - rsy + (float)__float2int_rn(rsy);
+        step = y_inc / vy;
+        step += (vy < 0) ? 1.0f : 0.0f;
+      } else {
+        const float x_inc = 0.5f - rsx + (float)__float2int_rn(rsx);
+        step = x_inc / vx;
+        step += (vx < 0) ? 1.0f : 0.0f;
+      }
+      rsx = fmaf(step, vx, rsx);
+      rsy = fmaf(step, vy, rsy);
+      float acc = 0.0f;
+      for (int j = 0; j < n_steps; j++) {
+        acc += tex2d<SMEM>(im, W, H, rsx, rsy, interp);
+        rsx += vx;
+        rsy += vy;
+      }
+      *o = acc * nrm;
+    }
+  }
+}
+
+// mean and unbiased std over each item of n elements (double accumulation); stats[item] = {mean, std}
+__global__ void __launch_bounds__(256) k_ring_stats(const float* __restrict__ x, int n, float* __restrict__ stats) {
+  __shared__ double s_a[8], s_b[8];
+  const float* p = x + (size_t)blockIdx.x * n;
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += (double)p[i];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) s_a[threadIdx.x >> 5] = s;
+  __syncthreads();
+  double tot = 0.0;
+  for (int w = 0; w < 8; w++) tot += s_a[w];
+  const double mean = tot / (double)n;
+  double q = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double d = (double)p[i] - mean;
+    q += d * d;
+  }
+  q = warp_sum(q);
+  if ((threadIdx.x & 31) == 0) s_b[threadIdx.x >> 5] = q;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tq = 0.0;
+    for (int w = 0; w < 8; w++) tq += s_b[w];
+    stats[2 * blockIdx.x] = (float)mean;
+    stats[2 * blockIdx.x + 1] = (float)sqrt(tq / (double)(n - 1));
+  }
+}
+
+// TIRING[c,k,d] = 1/sqrt(A) sum_a ((x[c,a,d]-mean)/std) exp(-2 pi i k a / A); grid = (channels, items), block 256.
+// The normalised sinogram of one channel (A*D floats) and the twiddle table live in shared memory.
+__global__ void __launch_bounds__(256) k_ring_tiring(const float* __restrict__ sino, const float* __restrict__ stats, int C, int A, int D,
+                                                    float* __restrict__ out) {
+  extern __shared__ float sm[];
+  float* xs = sm;              // A*D
+  float* tw_c = sm + A * D;    // A
+  float* tw_s = tw_c + A;      // A
+  const int item = blockIdx.y, c = blockIdx.x;
+  const float mean = stats[2 * item], sd = stats[2 * item + 1];
+  const float* p = sino + ((size_t)item * C + c) * A * D;
+  for (int i = threadIdx.x; i < A * D; i += blockDim.x) xs[i] = (p[i] - mean) / sd;
+  for (int i = threadIdx.x; i < A; i += blockDim.x) {
+    double sv, cv;
+    sincospi(-2.0 * (double)i / (double)A, &sv, &cv);
+    tw_c[i] = (float)cv;
+    tw_s[i] = (float)sv;
+  }
+  __syncthreads();
+  const float scale = (float)(1.0 / sqrt((double)A));
+  float* o = out + ((size_t)item * C + c) * A * D * 2;
+  for (int idx = threadIdx.x; idx < A * D; idx += blockDim.x) {
+    const int k = idx / D, d = idx - k * D;
+    float re = 0.f, im = 0.f;
+    int ph = 0;
+    for (int a = 0; a < A; a++) {
+      const float v = xs[a * D + d];
+      re = fmaf(v, tw_c[ph], re);
+      im = fmaf(v, tw_s[ph], im);
+      ph += k;
+      if (ph >= A) ph -= A;
+    }
+    o[2 * (size_t)idx] = re * scale;
+    o[2 * (size_t)idx + 1] = im * scale;
+  }
+}
+
+// fast_corr(query, db[j]) for every j: grid = n_db, block = 256.  corr[t] = sum_{c,d} | 1/sqrt(A) sum_k q*conj(b) e^{+2 pi i k t/A} |
+__global__ void __launch_bounds__(256) k_ring_fast_corr(const float* __restrict__ q, const float* __restrict__ db, int C, int A, int D,
+                                                       float* __restrict__ dist, int* __restrict__ angle, float* __restrict__ corr_out) {
+  extern __shared__ float sm[];
+  float* tw_c = sm;            // A
+  float* tw_s = sm + A;        // A
+  float* corr = sm + 2 * A;    // A (accumulated with atomics in shared memory)
+  float* pr = sm + 3 * A;      // A * D   product real (one channel at a time)
+  float* pi = pr + A * D;      // A * D
+  const int j = blockIdx.x;
+  for (int i = threadIdx.x; i < A; i += blockDim.x) {
+    double sv, cv;
+    sincospi(2.0 * (double)i / (double)A, &sv, &cv);
+    tw_c[i] = (float)cv;
+    tw_s[i] = (float)sv;
+    corr[i] = 0.f;
+  }
+  const float scale = (float)(1.0 / sqrt((double)A));
+  for (int c = 0; c < C; c++) {
+    __syncthreads();
+    const float* qa = q + (size_t)c * A * D * 2;
+    const float* ba = db + ((size_t)j * C + c) * A * D * 2;
+    for (int i = threadIdx.x; i < A * D; i += blockDim.x) {
+      const float ar = qa[2 * i], ai = qa[2 * i + 1], br = ba[2 * i], bi = -ba[2 * i + 1];
+      pr[i] = ar * br - ai * bi;
+      pi[i] = fmaf(ar, bi, ai * br);
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < A * D; idx += blockDim.x) {
+      const int t = idx / D, d = idx - t * D;
+      float re = 0.f, im = 0.f;
+      int ph = 0;
+      for (int k = 0; k < A; k++) {
+        const float xr = pr[k * D + d], xi = pi[k * D + d];
+        re += xr * tw_c[ph] - xi * tw_s[ph];
+        im += fmaf(xr, tw_s[ph], xi * tw_c[ph]);
+        ph += t;
+        if (ph >= A) ph -= A;
+      }
+      atomicAdd(&corr[t], sqrtf(re * re + im * im) * scale);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    // fftshift1d (util.py:306-337): roll by ceil(A/2); then max / argmax (first maximum)
+    const int nsh = (A + 1) / 2;
+    int am = 0;
+    float best = corr[nsh % A];
+    for (int i = 1; i < A; i++) {
+      const float v = corr[(i + nsh) % A];
+      if (v > best) {
+        best = v;
+        am = i;
+      }
+    }
+    dist[j] = 1.0f - best / (float)(0.15 * A * D);
+    angle[j] = -am + A / 2;
+  }
+  if (corr_out) {
+    const int nsh = (A + 1) / 2;
+    for (int i = threadIdx.x; i < A; i += blockDim.x) corr_out[(size_t)j * A + i] = corr[(i + nsh) % A];
+  }
+}
+
+struct RadonScratch {
+  DevBuf<float> stats, sino;
+};
+static RadonScratch& rs() {
+  static RadonScratch s;
+  return s;
+}
+
+static int radon_launch(const float* d_img, int batch, int H, int W, const float* d_angles, int n_angles, int det_count,
+                        float det_spacing, int interp, int fast_trig, float* d_sino) {
+  if (batch <= 0 || n_angles <= 0 || det_count <= 0) return MRSLAM_OK;
+  cudaStream_t st = rt().stream;
+  dim3 grid((n_angles + ANGLES_PER_BLOCK - 1) / ANGLES_PER_BLOCK, batch);
+  size_t smem = (size_t)H * W * sizeof(float);
+  if (smem <= 200 * 1024) {
+    MR_CUDA(cudaFuncSetAttribute(k_radon_forward<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_radon_forward<true><<<grid, RADON_THREADS, smem, st>>>(d_img, H, W, d_angles, n_angles, det_count, det_spacing, interp, fast_trig, d_sino);
+  } else {
+    k_radon_forward<false><<<grid, RADON_THREADS, 0, st>>>(d_img, H, W, d_angles, n_angles, det_count, det_spacing, interp, fast_trig, d_sino);
+  }
+  count_launch(1);
+  MR_CUDA(cudaGetLastError());
+  return MRSLAM_OK;
+}
+
+static int tiring_launch(const float* d_sino, int items, int C, int A, int D, float* d_tiring) {
+  if (items <= 0) return MRSLAM_OK;
+  cudaStream_t st = rt().stream;
+  RadonScratch& S = rs();
+  MR_CHECK(S.stats.reserve((size_t)items * 2));
+  k_ring_stats<<<items, 256, 0, st>>>(d_sino, C * A * D, S.stats.p);
+  size_t smem = ((size_t)A * D + 2 * A) * sizeof(float);
+  if (smem > 200 * 1024) {
+    set_error("ring_tiring: sinogram %dx%d does not fit shared memory", A, D);
+    return MRSLAM_ERR_ARG;
+  }
+  MR_CUDA(cudaFuncSetAttribute(k_ring_tiring, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_ring_tiring<<<dim3(C, items), 256, smem, st>>>(d_sino, S.stats.p, C, A, D, d_tiring);
+  count_launch(2);
+  MR_CUDA(cudaGetLastError());
+  return MRSLAM_OK;
+}
+
+}  // namespace mrslam
+
+using namespace mrslam;
+
+extern "C" {
+
+int mrslam_radon_forward(const float* d_img, int batch, int height, int width, const float* d_angles, int n_angles, int det_count,
+                         float det_spacing, int interp, int fast_trig, float* d_sino) {
+  MR_CHECK(ensure_init());
+  std::lock_guard<std::mutex> lk(rt().mu);
+  return radon_launch(d_img, batch, height, width, d_angles, n_angles, det_count, det_spacing, interp, fast_trig, d_sino);
+}
+
+int mrslam_ring_tiring(const float* d_sino, int items, int channels, int n_angles, int det_count, float* d_tiring) {
+  MR_CHECK(ensure_init());
+  std::lock_guard<std::mutex> lk(rt().mu);
+  return tiring_launch(d_sino, items, channels, n_angles, det_count, d_tiring);
+}
+
+int mrslam_ring_fast_corr(const float* d_query, const float* d_db, int n_db, int channels, int n_angles, int det_count, float* d_dist,
+                          int* d_angle, float* d_corr_opt) {
+  MR_CHECK(ensure_init());
+  if (n_db <= 0) return MRSLAM_OK;
+  std::lock_guard<std::mutex> lk(rt().mu);
+  size_t smem = ((size_t)3 * n_angles + 2 * (size_t)n_angles * det_count) * sizeof(float);
+  if (smem > 200 * 1024) {
+    set_error("ring_fast_corr: descriptor %dx%d does not fit shared memory", n_angles, det_count);
+    return MRSLAM_ERR_ARG;
+  }
+  MR_CUDA(cudaFuncSetAttribute(k_ring_fast_corr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_ring_fast_corr<<<n_db, 256, smem, rt().stream>>>(d_query, d_db, channels, n_angles, det_count, d_dist, d_angle, d_corr_opt);
+  count_launch(1);
+  MR_CUDA(cudaGetLastError());
+  return MRSLAM_OK;
+}
+
+int mrslam_ring_generate(const float* d_bev, int batch, int size, const float* d_angles, int n_angles, int interp, int fast_trig,
+                         float* d_sino_opt, float* d_tiring) {
+  MR_CHECK(ensure_init());
+  std::lock_guard<std::mutex> lk(rt().mu);
+  float* sino = d_sino_opt;
+  if (!sino) {
+    MR_CHECK(rs().sino.reserve((size_t)batch * n_angles * size));
+    sino = rs().sino.p;
+  }
+  // generate_RING: ParallelBeam(num_sector, angles).forward(bev[1, ring, sector]) -> [1, n_angles, det = size]
+  MR_CHECK(radon_launch(d_bev, batch, size, size, d_angles, n_angles, size, 1.0f, interp, fast_trig, sino));
+  return tiring_launch(sino, batch, 1, n_angles, size, d_tiring);
+}
+}

@@ -1,0 +1,57 @@
+"""One-robot-per-GPU sharding of loop-closure batches (new; the reference is single-process: "multi-robot" there means
+N ROS namespaces consumed by one global_manager, GM/src/global_manager.cpp:287-442).
+
+Rank r = GPU r = robot r.  Every rank keeps its own keyframe clouds resident.  A candidate pair (robot a, keyframe i) <->
+(robot b, keyframe j) is refined on rank a (the robot that holds the source/query keyframe); the only exchange step is an
+all-gather of the candidate TARGET clouds (fixed-size slots, 120k x 3 float32 = 1.44 MB each) over NCCL/NVLink at
+loop-closure time, followed by an all-gather of the 4x4 results.  No other collective exists on the path.
+The functions work with any torch.distributed backend (gloo on CPU tensors in the tests, nccl on CUDA tensors)."""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def owner_of_pair(pair, world_size):
+    """pair = (src_robot, src_kf, tgt_robot, tgt_kf) -> rank that refines it (the source robot's GPU)."""
+    return pair[0] % world_size
+
+
+def shard_pairs(pairs, rank, world_size):
+    """Deterministic partition of a global candidate list: indices of the pairs this rank refines."""
+    return [i for i, p in enumerate(pairs) if owner_of_pair(p, world_size) == rank]
+
+
+def requested_targets(pairs, world_size):
+    """For every rank: the sorted list of (tgt_robot, tgt_kf) clouds somebody else needs from it."""
+    need = [set() for _ in range(world_size)]
+    for p in pairs:
+        if owner_of_pair(p, world_size) != p[2] % world_size:
+            need[p[2] % world_size].add((p[2], p[3]))
+    return [sorted(s) for s in need]
+
+
+def allgather_slots(local_slots):
+    """local_slots: tensor [S, N, 3] (same S, N on every rank; pad with NaN rows if a robot contributes fewer clouds).
+    Returns [world, S, N, 3] on every rank.  One collective per loop-closure batch."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return local_slots.unsqueeze(0)
+    world = dist.get_world_size()
+    out = torch.empty((world,) + tuple(local_slots.shape), dtype=local_slots.dtype, device=local_slots.device)
+    dist.all_gather_into_tensor(out, local_slots.contiguous())
+    return out
+
+
+def gather_results(local_T, local_ids, n_total):
+    """local_T: [n_local,4,4] float32, local_ids: global pair indices.  Returns [n_total,4,4] on every rank."""
+    T = torch.zeros((n_total, 4, 4), dtype=torch.float32, device=local_T.device)
+    if len(local_ids):
+        T[torch.as_tensor(local_ids, device=local_T.device, dtype=torch.long)] = local_T
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(T, op=dist.ReduceOp.SUM)  # disjoint supports: a sum is a gather
+    return T
+
+
+def ring_candidate_pairs(world_size, per_rank):
+    """The benchmark's loop-closure storm (BASELINE config 4): robot r's keyframe i is matched against keyframe i of
+    robot (r+1) % world.  Returns the global pair list."""
+    return [(r, i, (r + 1) % world_size, i) for r in range(world_size) for i in range(per_rank)]

@@ -1,0 +1,84 @@
+"""RING descriptor front end and matcher on the GPU (mirror of LoopDetection/src/RING_ros/util.py:174-200 `generate_RING`
+and :362-374 `fast_corr`), batched: many scans per call instead of one python call per scan.
+
+Data stays on the device between the stages (BEV -> Radon -> normalise -> FFT); descriptors are complex64 torch tensors
+[B, 1, n_angles, det] like the reference's TIRING."""
+import numpy as np
+import torch
+
+from ._lib import check, lib, ptr
+
+NUM_RING = 120     # RING_ros/config.py:8-12
+NUM_SECTOR = 120
+NUM_HEIGHT = 1
+MAX_LENGTH = 1
+MAX_HEIGHT = 1
+
+
+def _sync():
+    check(lib().mrslam_device_synchronize())
+
+
+def bev_batch(points_list, device="cuda:0", num_x=NUM_RING, num_y=NUM_SECTOR):
+    """points_list: list of (N_i,3) float32 arrays already filtered+scaled by load_pc_infer.  Returns the max-height BEV
+    images [B, num_x, num_y] (what generate_RING keeps of voxelocc's output: channel 2)."""
+    offs = np.zeros(len(points_list) + 1, np.int64)
+    for i, p in enumerate(points_list):
+        offs[i + 1] = offs[i] + len(p)
+    host = np.empty(3 * int(offs[-1]), np.float32)
+    for i, p in enumerate(points_list):
+        n = len(p)
+        host[3 * offs[i]:3 * offs[i] + 3 * n] = np.asarray(p, np.float32)[:, :3].T.reshape(-1)  # pc.transpose().flatten()
+    d_pts = torch.from_numpy(host).pin_memory().to(device, non_blocking=True)
+    return bev_batch_device(d_pts, offs, num_x, num_y)
+
+
+def bev_batch_device(d_pts_soa, offsets, num_x=NUM_RING, num_y=NUM_SECTOR):
+    B = len(offsets) - 1
+    bev = torch.empty((B, num_x, num_y), dtype=torch.float32, device=d_pts_soa.device)
+    offs = np.ascontiguousarray(offsets, np.int64)
+    torch.cuda.current_stream(d_pts_soa.device).synchronize()
+    check(lib().mrslam_voxelocc_bev_device(ptr(d_pts_soa), offs.ctypes.data, B, MAX_LENGTH, MAX_HEIGHT, num_x, num_y, ptr(bev)))
+    return bev
+
+
+def ring_angles(device, n=NUM_RING):
+    return torch.from_numpy(np.linspace(0, 2 * np.pi, n).astype(np.float32)).to(device)  # util.py:192 (endpoint inclusive)
+
+
+def generate_RING_batch(bev, angles=None, interp="texture", fast_trig=True, want_sino=False):
+    """bev: CUDA float32 [B, S, S].  Returns (sinogram [B,1,A,S] or None, TIRING complex64 [B,1,A,S])."""
+    B, S, _ = bev.shape
+    ang = angles if angles is not None else ring_angles(bev.device, S)
+    A = ang.numel()
+    tir = torch.empty((B, 1, A, S, 2), dtype=torch.float32, device=bev.device)
+    sino = torch.empty((B, 1, A, S), dtype=torch.float32, device=bev.device) if want_sino else None
+    torch.cuda.current_stream(bev.device).synchronize()
+    check(lib().mrslam_ring_generate(ptr(bev.contiguous()), B, S, ptr(ang.contiguous()), A, 1 if interp == "texture" else 0,
+                                     1 if fast_trig else 0, ptr(sino) if want_sino else None, ptr(tir)))
+    _sync()
+    return sino, torch.view_as_complex(tir)
+
+
+def tiring(sino):
+    """normalise + fft2(dim=-2, ortho) of sinograms [B, C, A, D] (float32 CUDA) -> complex64 [B, C, A, D]"""
+    B, C, A, D = sino.shape
+    tir = torch.empty((B, C, A, D, 2), dtype=torch.float32, device=sino.device)
+    torch.cuda.current_stream(sino.device).synchronize()
+    check(lib().mrslam_ring_tiring(ptr(sino.contiguous()), B, C, A, D, ptr(tir)))
+    _sync()
+    return torch.view_as_complex(tir)
+
+
+def fast_corr_batch(query, database, want_corr=False):
+    """query: complex64 [C, A, D]; database: complex64 [N, C, A, D] (both CUDA).  Returns (dist[N], angle[N]) like fast_corr."""
+    N, C, A, D = database.shape
+    q = torch.view_as_real(query.contiguous()).contiguous()
+    db = torch.view_as_real(database.contiguous()).contiguous()
+    dist = torch.empty(N, dtype=torch.float32, device=db.device)
+    ang = torch.empty(N, dtype=torch.int32, device=db.device)
+    corr = torch.empty((N, A), dtype=torch.float32, device=db.device) if want_corr else None
+    torch.cuda.current_stream(db.device).synchronize()
+    check(lib().mrslam_ring_fast_corr(ptr(q), ptr(db), N, C, A, D, ptr(dist), ptr(ang), ptr(corr) if want_corr else None))
+    _sync()
+    return (dist, ang, corr) if want_corr else (dist, ang)

@@ -66,7 +66,9 @@ void orc_radon_forward(const float* img, int batch, int H, int W, const float* a
         float sy = hypotf(fabsf(vdx) + W * 0.5f, fabsf(vdy) + H * 0.5f);
         float ex = sx, ey = -sy;
         float angle = angles[angle_id];
-        float cs = cosf(angle), sn = sinf(angle);
+        // accurate-trig mode of the CUDA path: the double-precision value rounded to float (bit-identical on CPU/GPU
+        // up to double rounding); the reference kernel itself uses the approximate __cosf/__sinf intrinsics.
+        float cs = (float)cos((double)angle), sn = (float)sin((double)angle);
         float rsx = fmaf(sy, sn, sx * cs);          // sx*cs + sy*sn
         float rsy = fmaf(sy, cs, -sx * sn);         // -sx*sn + sy*cs
         float rdx = fmaf(ey, sn, ex * cs) - rsx;    // ex*cs + ey*sn - rsx
