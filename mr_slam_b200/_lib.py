@@ -48,6 +48,8 @@ def _declare(L):
     L.mrslam_version.restype = C.c_char_p
     L.mrslam_stream.restype = vp
     L.mrslam_kernel_launch_count.restype = C.c_ulonglong
+    L.mrslam_prof_enable.argtypes = [i]
+    L.mrslam_prof_get.argtypes = [i, C.POINTER(d), C.POINTER(ll)]
 
     L.mrslam_cloud_create_host.argtypes = [fp, i, i]
     L.mrslam_cloud_create_host.restype = vp
@@ -132,6 +134,23 @@ def ptr(a):
 
 def init(device=-1):
     check(lib().mrslam_init(int(device)))
+
+
+PROF_IDS = ["knn_search", "cov", "nn1_search", "linearize", "error", "cloud_build", "elev_process", "elev_fuse"]
+
+
+def prof_enable(on=True):
+    check(lib().mrslam_prof_enable(1 if on else 0))
+
+
+def prof_get():
+    """{name: (total_ms, launches)} of the instrumented kernels since prof_enable()"""
+    out = {}
+    for k, name in enumerate(PROF_IDS):
+        ms, n = C.c_double(), C.c_longlong()
+        check(lib().mrslam_prof_get(k, C.byref(ms), C.byref(n)))
+        out[name] = (ms.value, n.value)
+    return out
 
 
 def kernel_launch_count():

@@ -58,6 +58,23 @@ struct Runtime {
 Runtime& rt();
 int ensure_init();  // MRSLAM_OK or error (no device -> MRSLAM_ERR_CUDA; never a CPU fallback)
 
+// ---- optional per-kernel device timing (bench.py's roofline block): CUDA events on the library stream ----
+enum ProfId { PROF_KNN_SEARCH = 0, PROF_COV, PROF_NN1_SEARCH, PROF_LINEARIZE, PROF_ERROR, PROF_CLOUD_BUILD, PROF_ELEV_PROCESS,
+              PROF_ELEV_FUSE, PROF_COUNT };
+bool prof_enabled();
+void prof_begin(int id);
+void prof_end(int id);
+struct ProfScope {
+  int id;
+  bool on;
+  explicit ProfScope(int i) : id(i), on(prof_enabled()) {
+    if (on) prof_begin(id);
+  }
+  ~ProfScope() {
+    if (on) prof_end(id);
+  }
+};
+
 inline void count_launch(int n = 1) { rt().launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 
 // stream-ordered device buffer (cudaMallocAsync pool; grow-only)

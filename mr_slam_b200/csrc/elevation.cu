@@ -292,6 +292,7 @@ static int fuse_sorted(Elev* m, int n, const float* d_h, const float* d_v, const
                        const float* d_I, long long* n_fused) {
   cudaStream_t st = rt().stream;
   const int cells = m->cells();
+  ProfScope ps(PROF_ELEV_FUSE);
   if (n > 0) {
     int bits = 1;
     while ((1ll << bits) <= cells) bits++;
@@ -540,8 +541,11 @@ int mrslam_elev_process_fuse_device(mrslam_elev_t* h, const float* d_x, const fl
   if (n > 0) {
     ProcParams P;
     fill_proc(P, T16, lower, upper, min_r, beam_a, beam_c, sJ, rotVar, CSBT, PCBM, BrBS, near_filter);
-    k_elev_process<<<(n + 255) / 256, 256, 0, st>>>(d_x, d_y, d_z, n, P, m->g, m->lowest.p, nullptr, m->pvar.p, nullptr, nullptr,
-                                                   m->pzt.p, m->keys.p, m->vals.p);
+    {
+      ProfScope ps(PROF_ELEV_PROCESS);
+      k_elev_process<<<(n + 255) / 256, 256, 0, st>>>(d_x, d_y, d_z, n, P, m->g, m->lowest.p, nullptr, m->pvar.p, nullptr, nullptr,
+                                                     m->pzt.p, m->keys.p, m->vals.p);
+    }
     count_launch(1);
   }
   return fuse_sorted(m, n, m->pzt.p, m->pvar.p, nullptr, nullptr, nullptr, nullptr, n_fused);

@@ -37,6 +37,7 @@ struct Cloud {
 
   int build_from_device_raw(const float* d_raw, int n_, int stride) {
     cudaStream_t st = rt().stream;
+    ProfScope ps(PROF_CLOUD_BUILD);
     n = n_;
     npad = ((n + TILE - 1) / TILE) * TILE;
     ntiles = npad / TILE;
@@ -109,9 +110,13 @@ static int dispatch_knn(int k, const KnnParams* d_params, int nproblems, int max
   }
   if (max_tiles <= 0 || nproblems <= 0) return MRSLAM_OK;
   dim3 grid((max_tiles + 3) / 4, nproblems);
-  k_knn_search<<<grid, 128, 0, rt().stream>>>(d_params);
+  {
+    ProfScope ps(PROF_KNN_SEARCH);
+    k_knn_search<<<grid, 128, 0, rt().stream>>>(d_params);
+  }
   count_launch(1);
   if (with_cov) {
+    ProfScope ps(PROF_COV);
     k_cov<<<dim3((max_tiles * TILE + 127) / 128, nproblems), 128, 0, rt().stream>>>(d_params);
     count_launch(1);
   }
@@ -413,8 +418,14 @@ static int run_linearize(Gicp** hs, const std::vector<int>& ids) {
   MR_CUDA(cudaMemcpyAsync(S.d_T.p, S.h_T.p, sizeof(double) * 12 * nmax, cudaMemcpyHostToDevice, st));
   if (maxt > 0) {
     dim3 grid((maxt + 3) / 4, na);
-    k_nn1_search<MODE_LINEARIZE><<<grid, 128, 0, st>>>(S.d_pairs.p, S.d_active.p, S.d_T.p, 0.0, S.stats ? S.d_stat.p : nullptr);
-    k_linearize<<<grid, 128, 0, st>>>(S.d_pairs.p, S.d_active.p, S.d_T.p);
+    {
+      ProfScope ps(PROF_NN1_SEARCH);
+      k_nn1_search<MODE_LINEARIZE><<<grid, 128, 0, st>>>(S.d_pairs.p, S.d_active.p, S.d_T.p, 0.0, S.stats ? S.d_stat.p : nullptr);
+    }
+    {
+      ProfScope ps(PROF_LINEARIZE);
+      k_linearize<<<grid, 128, 0, st>>>(S.d_pairs.p, S.d_active.p, S.d_T.p);
+    }
     k_reduce_partials<<<na, 32 * NRED, 0, st>>>(S.d_pairs.p, S.d_active.p, 0, NRED, S.h_out.p);
     count_launch(3);
   }
@@ -448,7 +459,10 @@ static int run_error(Gicp** hs, const std::vector<int>& ids) {
   }
   if (maxt > 0) {
     dim3 grid((maxt + 3) / 4, na);
-    k_error<<<grid, 128, 0, st>>>(S.d_pairs.p, S.d_active.p, S.d_T.p);
+    {
+      ProfScope ps(PROF_ERROR);
+      k_error<<<grid, 128, 0, st>>>(S.d_pairs.p, S.d_active.p, S.d_T.p);
+    }
     k_reduce_partials<<<na, 32, 0, st>>>(S.d_pairs.p, S.d_active.p, 27, 1, S.h_out.p);
     count_launch(2);
   }

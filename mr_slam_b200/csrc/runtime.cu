@@ -19,6 +19,51 @@ Runtime& rt() {
   return r;
 }
 
+// ---- profiling: event pairs per launch group, resolved lazily ----
+struct ProfRec {
+  int id;
+  cudaEvent_t a, b;
+};
+static bool g_prof = false;
+static std::vector<ProfRec> g_recs;
+static std::vector<cudaEvent_t> g_free_events;
+static double g_prof_ms[PROF_COUNT];
+static long long g_prof_n[PROF_COUNT];
+static cudaEvent_t g_open[PROF_COUNT];
+bool prof_enabled() { return g_prof; }
+static cudaEvent_t get_event() {
+  if (!g_free_events.empty()) {
+    cudaEvent_t e = g_free_events.back();
+    g_free_events.pop_back();
+    return e;
+  }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+void prof_begin(int id) {
+  g_open[id] = get_event();
+  cudaEventRecord(g_open[id], rt().stream);
+}
+void prof_end(int id) {
+  cudaEvent_t b = get_event();
+  cudaEventRecord(b, rt().stream);
+  g_recs.push_back(ProfRec{id, g_open[id], b});
+}
+static void prof_resolve() {
+  cudaStreamSynchronize(rt().stream);
+  for (ProfRec& r : g_recs) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+      g_prof_ms[r.id] += ms;
+      g_prof_n[r.id]++;
+    }
+    g_free_events.push_back(r.a);
+    g_free_events.push_back(r.b);
+  }
+  g_recs.clear();
+}
+
 static int init_device(int device) {
   Runtime& R = rt();
   std::lock_guard<std::mutex> lk(R.mu);
@@ -82,4 +127,24 @@ int mrslam_device_synchronize(void) {
 }
 void* mrslam_stream(void) { return ensure_init() == MRSLAM_OK ? (void*)rt().stream : nullptr; }
 unsigned long long mrslam_kernel_launch_count(void) { return rt().launches.load(); }
+// per-kernel device time (CUDA events on the launching stream); ids: see ProfId in common.cuh
+int mrslam_prof_enable(int on) {
+  MR_CHECK(ensure_init());
+  std::lock_guard<std::mutex> lk(rt().mu);
+  prof_resolve();
+  for (int i = 0; i < PROF_COUNT; i++) {
+    g_prof_ms[i] = 0;
+    g_prof_n[i] = 0;
+  }
+  g_prof = on != 0;
+  return MRSLAM_OK;
+}
+int mrslam_prof_get(int id, double* total_ms, long long* count) {
+  if (id < 0 || id >= PROF_COUNT) return MRSLAM_ERR_ARG;
+  std::lock_guard<std::mutex> lk(rt().mu);
+  prof_resolve();
+  if (total_ms) *total_ms = g_prof_ms[id];
+  if (count) *count = g_prof_n[id];
+  return MRSLAM_OK;
+}
 }

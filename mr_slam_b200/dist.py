@@ -37,7 +37,7 @@ def allgather_slots(local_slots):
         return local_slots.unsqueeze(0)
     world = dist.get_world_size()
     out = torch.empty((world,) + tuple(local_slots.shape), dtype=local_slots.dtype, device=local_slots.device)
-    dist.all_gather_into_tensor(out, local_slots.contiguous())
+    dist.all_gather(list(out.unbind(0)), local_slots.contiguous())  # views into `out`; works for gloo and nccl
     return out
 
 

@@ -1,0 +1,92 @@
+"""Generate tests/golden/{polar,ring}_fixture.npz in the authoring container (needs /root/reference and oracle/_ref).
+
+polar: the reference's own fixtures (DISCO .../multi-layer-polar-cpu/cython/{1,2}.bin, BEV/test.bin; 4096x3 float64 already in
+       [-1,1]) run through the reference's UNMODIFIED CPU twin of the polar voxeliser (oracle/_ref/libpolar_cpu_ref.so).
+ring : the reference's python functions themselves -- LoopDetection/src/RING_ros/util.py is imported (its CUDA-extension and
+       plotting imports are stubbed out, nothing else) and `fast_corr`, `fftshift1d`, `load_pc_infer` plus the two tail lines
+       of `generate_RING` (util.py:197-198) are executed on CPU tensors.
+"""
+import os
+import sys
+import types
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.abspath(os.path.join(HERE, "..", "..")))
+REF = "/root/reference/LoopDetection"
+
+
+def polar():
+    from oracle import ref
+    out = {}
+    files = {"disco1": REF + "/src/disco_ros/tools/multi-layer-polar-cpu/cython/1.bin",
+             "disco2": REF + "/src/disco_ros/tools/multi-layer-polar-cpu/cython/2.bin"}
+    cfgs = [(1, 1, 40, 120, 20, 1), (1, 1, 40, 120, 1, 1), (1, 1, 40, 120, 4, 3)]
+    for name, f in files.items():
+        pts = np.fromfile(f, dtype=np.float64).reshape(-1, 3).astype(np.float32)
+        out[name + "_points"] = pts
+        soa = np.ascontiguousarray(pts.T.reshape(-1))
+        for ci, c in enumerate(cfgs):
+            o = ref.polar_cpu(soa, len(pts), *c)
+            nz = np.nonzero(o)[0].astype(np.int32)
+            out["%s_cfg%d_idx" % (name, ci)] = nz
+            out["%s_cfg%d_val" % (name, ci)] = o[nz]
+    out["cfgs"] = np.array(cfgs, np.int32)
+    np.savez_compressed(os.path.join(HERE, "polar_fixture.npz"), **out)
+    print("polar fixture:", {k: v.shape for k, v in out.items() if k.endswith("points")})
+
+
+def ring():
+    import torch
+    # stub the imports of util.py that need a GPU extension / plotting; everything else is the reference's code
+    for name in ("voxelocc", "voxelfeat", "matplotlib", "matplotlib.pyplot", "mpl_toolkits", "mpl_toolkits.mplot3d", "skimage",
+                 "torch_radon", "torchvision", "torchvision.transforms", "torchvision.transforms.functional"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    sys.modules["mpl_toolkits.mplot3d"].Axes3D = object
+    sys.modules["skimage"].morphology = None
+    for n in ("Radon", "ParallelBeam", "RadonFanbeam"):
+        setattr(sys.modules["torch_radon"], n, object)
+    # torchvision.transforms.functional.normalize on a tensor: tensor.sub_(mean).div_(std) (torchvision/transforms/_functional_tensor.py)
+    sys.modules["torchvision.transforms.functional"].normalize = lambda t, mean, std: (t - mean) / std
+    sys.path.insert(0, REF + "/src/RING_ros")
+    import util  # the reference module
+
+    rng = np.random.default_rng(11)
+    sino = (rng.random((2, 1, 120, 120)) * 30 * (rng.random((2, 1, 120, 120)) < 0.3)).astype(np.float32)
+    out = {"sino": sino}
+    tir = []
+    for i in range(2):
+        pc_RING = torch.from_numpy(sino[i])
+        pc_RING_normalized = util.fn.normalize(pc_RING, mean=pc_RING.mean(), std=pc_RING.std())   # util.py:197
+        pc_TIRING = torch.fft.fft2(pc_RING_normalized, dim=-2, norm="ortho")                          # util.py:198
+        tir.append(pc_TIRING.numpy())
+    out["tiring"] = np.stack(tir)
+    d, a = [], []
+    for i in range(2):
+        for j in range(2):
+            dist, angle = util.fast_corr(torch.from_numpy(tir[i]), torch.from_numpy(tir[j]))          # util.py:362-374
+            d.append(float(dist))
+            a.append(int(angle))
+    out["fast_corr_dist"] = np.array(d, np.float32).reshape(2, 2)
+    out["fast_corr_angle"] = np.array(a, np.int32).reshape(2, 2)
+    # a shifted copy: rolling the sinogram along the angle axis by s must be recovered as the yaw
+    rolled = np.roll(sino[0], 17, axis=-2)
+    pr = torch.from_numpy(rolled)
+    trr = torch.fft.fft2(util.fn.normalize(pr, mean=pr.mean(), std=pr.std()), dim=-2, norm="ortho")
+    dist, angle = util.fast_corr(torch.from_numpy(tir[0]), trr)
+    out["rolled_by"] = np.int32(17)
+    out["rolled_dist"] = np.float32(dist)
+    out["rolled_angle"] = np.int32(angle)
+    # load_pc_infer on a synthetic cloud
+    pc = (rng.random((5000, 4)).astype(np.float32) - 0.5) * np.array([200, 200, 80, 1], np.float32)
+    out["pc"] = pc
+    out["pc_infer"] = util.load_pc_infer(pc)
+    np.savez_compressed(os.path.join(HERE, "ring_fixture.npz"), **out)
+    print("ring fixture: fast_corr dist", out["fast_corr_dist"].tolist(), "angle", out["fast_corr_angle"].tolist(), "rolled ->", int(angle))
+
+
+if __name__ == "__main__":
+    polar()
+    ring()

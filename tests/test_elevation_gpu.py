@@ -1,0 +1,165 @@
+"""GPU parity tests of the elevation process + fuse path: cell indices bit-exact, heights within 1e-5 (north_star) --
+against the CPU oracle and, where oracle/_ref is present, against the reference's own kernels compiled from
+gpu_process.cu (with the Eigen shim)."""
+import numpy as np
+import pytest
+
+import oracle
+from mr_slam_b200 import elevation, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def frame(f, kind):
+    pose = synth.pose_matrix(2.0 * f + 0.3, -1.0 * f, 0.1 * f, 0.3 * f)
+    pts = synth.make_scan(pose, kind, scan_id=100 + f)
+    ei = synth.elevation_inputs(pose)
+    args = (ei["T"], -5.0, 5.0, ei["min_r"], ei["beam_a"], ei["beam_c"], ei["sensorJacobian"], ei["rotationVariance"],
+            ei["C_SB_transpose"], ei["P_mul_C_BM_transpose"], ei["B_r_BS_skew"])
+    x, y, z = (np.ascontiguousarray(pts[:, i]) for i in range(3))
+    return pose, x, y, z, args
+
+
+def colours(n, seed):
+    rng = np.random.default_rng(seed)
+    R = (rng.integers(1, 255, n) * (rng.random(n) < 0.6)).astype(np.int32)
+    G = rng.integers(1, 255, n).astype(np.int32)
+    B = rng.integers(1, 255, n).astype(np.int32)
+    I = rng.random(n).astype(np.float32)
+    return R, G, B, I
+
+
+@pytest.mark.parametrize("L,res,kind", [(1200, 0.1, "hdl64"), (60, 0.2, "vlp16"), (61, 0.2, "vlp16"), (201, 0.15, "vlp16")])
+def test_process_fuse_sequence_vs_oracle(gpu, L, res, kind):
+    g = elevation.ElevationMap()
+    g.Init_GPU_elevationmap(L, res, 2.5, 0.2)
+    o = oracle.ElevationMap(L, res, 2.5, 0.2)
+    for f in range(3):
+        pose, x, y, z, args = frame(f, kind)
+        n = len(x)
+        pos = pose[:3, 3].astype(np.float32)
+        for a, b in zip(g.Move(pos, res, L), o.move(pos)):
+            assert np.array_equal(a, b)
+        rg = g.Process_points(x, y, z, args[0], n, *args[1:])
+        ro = o.process_points(x, y, z, *args)
+        assert np.array_equal(rg[0], ro[0])                    # cell indices: bit-exact
+        for a, b in zip(rg[1:], ro[1:]):
+            assert np.array_equal(a, b)                        # variance and transformed coordinates: bit-exact too
+        assert (rg[0][rg[4] == -1] == -1).all()
+        R, G, B, I = colours(n, f)
+        nf = g.Fuse(L, n, rg[0], R, G, B, I, rg[4], rg[1])
+        assert nf == o.fuse(ro[0], R, G, B, I, ro[4], ro[1])
+        mg, mo = g.get_map(), o.get_map()
+        assert np.abs(mg["elevation"] - mo["elevation"]).max() <= 1e-5   # heights within 1e-5 (they are in fact identical)
+        for k in ("elevation", "variance", "intensity", "R", "G", "B"):
+            assert np.array_equal(mg[k], mo[k]), k
+        g.Mapvar_update(L, 0.001)
+        o.mapvar_update(0.001)
+    out_g = g.Map_optmove(np.array([1.234, -0.77], np.float32), 0.05, res, L)
+    out_o = o.map_optmove(np.array([1.234, -0.77], np.float32), 0.05)
+    assert np.array_equal(out_g, out_o)
+    g.Map_closeloop(np.array([3.3, 0.4], np.float32), -0.02, L, res)
+    o.map_closeloop(np.array([3.3, 0.4], np.float32), -0.02)
+    assert np.array_equal(g.get_map()["elevation"], o.get_map()["elevation"])
+    assert all(np.array_equal(a, b) for a, b in zip(g.state(), o.state()))
+
+
+def test_many_points_per_cell_order_dependence(gpu):
+    """The Mahalanobis branch makes the result depend on the per-cell point order: feed thousands of points into a handful
+    of cells, in an order where sorting by height would give a different answer."""
+    rng = np.random.default_rng(3)
+    L, n = 8, 20000
+    idx = rng.integers(-2, L * L + 3, n).astype(np.int32)          # includes invalid indices on both sides
+    h = (rng.normal(0, 0.5, n) + (rng.random(n) < 0.1) * 3.0).astype(np.float32)
+    h[rng.random(n) < 0.02] = -1.0
+    v = rng.uniform(1e-6, 0.02, n).astype(np.float32)
+    R, G, B, I = colours(n, 9)
+    g = elevation.ElevationMap()
+    g.Init_GPU_elevationmap(L, 0.5, 2.5, 0.2)
+    o = oracle.ElevationMap(L, 0.5, 2.5, 0.2)
+    for rep in range(2):
+        assert g.Fuse(L, n, idx, R, G, B, I, h, v) == o.fuse(idx, R, G, B, I, h, v)
+        mg, mo = g.get_map(), o.get_map()
+        for k in ("elevation", "variance", "intensity", "R", "G", "B"):
+            assert np.array_equal(mg[k], mo[k]), k
+    perm = rng.permutation(n)   # a different point order gives a different map (the fuse is not commutative) ...
+    g2 = elevation.ElevationMap()
+    g2.Init_GPU_elevationmap(L, 0.5, 2.5, 0.2)
+    g2.Fuse(L, n, idx[perm], R[perm], G[perm], B[perm], I[perm], h[perm], v[perm])
+    o2 = oracle.ElevationMap(L, 0.5, 2.5, 0.2)
+    o2.fuse(idx[perm], R[perm], G[perm], B[perm], I[perm], h[perm], v[perm])
+    assert np.array_equal(g2.get_map()["elevation"], o2.get_map()["elevation"])   # ... and the GPU follows it exactly
+
+
+def test_device_fused_path_equals_host_path(gpu):
+    import torch
+    L, res = 1200, 0.1
+    pose, x, y, z, args = frame(1, "hdl64")
+    n = len(x)
+    a = elevation.ElevationMap()
+    a.Init_GPU_elevationmap(L, res, 2.5, 0.2)
+    b = elevation.ElevationMap()
+    b.Init_GPU_elevationmap(L, res, 2.5, 0.2)
+    pos = pose[:3, 3].astype(np.float32)
+    a.Move(pos, res, L)
+    b.Move(pos, res, L)
+    r = a.Process_points(x, y, z, args[0], n, *args[1:])
+    zi = np.zeros(n, np.int32)
+    nf_a = a.Fuse(L, n, r[0], zi, zi, zi, np.zeros(n, np.float32), r[4], r[1])
+    d = [torch.from_numpy(t).cuda() for t in (x, y, z)]
+    nf_b = b.process_fuse_device(d[0], d[1], d[2], n, *args, near_filter=True)
+    assert nf_a == nf_b == int((r[0] >= 0).sum())
+    ma, mb = a.get_map(), b.get_map()
+    assert np.array_equal(ma["elevation"], mb["elevation"]) and np.array_equal(ma["variance"], mb["variance"])
+    # size-independent properties at the full config size: touched cells == distinct valid indices; empty cells are (-10, 1e-4)
+    touched = ma["elevation"] != -10
+    assert touched.sum() == len(np.unique(r[0][r[0] >= 0]))
+    assert (ma["variance"][~touched] == np.float32(0.0001)).all()
+    nf_off = b.process_fuse_device(d[0], d[1], d[2], n, *args, near_filter=False)   # throughput mode keeps every in-range point
+    assert nf_off > nf_b
+
+
+def test_empty_and_invalid_inputs(gpu):
+    g = elevation.ElevationMap()
+    with pytest.raises(Exception):
+        g.Fuse(10, 0, [], [], [], [], [], [], [])          # Init not called
+    g.Init_GPU_elevationmap(10, 0.5, 2.5, 0.2)
+    e = np.zeros(0, np.float32)
+    assert g.Fuse(10, 0, e.astype(np.int32), e.astype(np.int32), e.astype(np.int32), e.astype(np.int32), e, e, e) == 0
+    m = g.get_map()
+    assert (m["elevation"] == -10).all() and (m["variance"] == np.float32(0.0001)).all()
+    with pytest.raises(Exception):
+        g.Fuse(11, 0, e.astype(np.int32), e.astype(np.int32), e.astype(np.int32), e.astype(np.int32), e, e, e)   # wrong length
+
+
+def test_against_reference_kernels(gpu):
+    """The reference's own gpu_process.cu kernels (compiled unmodified against the Eigen shim into oracle/_ref) run next to
+    ours on the same inputs: indices bit-exact, heights within 1e-5.  Small map: the reference's G_fuse is O(cells x points)."""
+    from oracle import ref
+    if not ref.available("elev"):
+        pytest.skip("oracle/_ref/libelev_ref.so not present")
+    L, res = 100, 0.2
+    rk = ref.ElevationRef(L, res)
+    g = elevation.ElevationMap()
+    g.Init_GPU_elevationmap(L, res, 2.5, 0.2)
+    for f in range(3):
+        pose, x, y, z, args = frame(f, "vlp16")
+        n = len(x)
+        pos = pose[:3, 3].astype(np.float32)
+        for a, b in zip(g.Move(pos, res, L), rk.move(pos)):
+            assert np.array_equal(a, b)
+        rg = g.Process_points(x, y, z, args[0], n, *args[1:])
+        rr = rk.process_points(x, y, z, *args)
+        assert np.array_equal(rg[0], rr[0])                               # cell indices bit-exact vs the reference kernel
+        assert np.abs(rg[4] - rr[4]).max() <= 1e-6 and np.abs(rg[2] - rr[2]).max() <= 1e-5
+        assert np.abs(rg[1] - rr[1]).max() <= 1e-6 * max(1.0, np.abs(rr[1]).max())
+        R, G, B, I = colours(n, f)
+        g.Fuse(L, n, rg[0], R, G, B, I, rg[4], rg[1])
+        rk.fuse(rr[0], R, G, B, I, rr[4], rr[1])
+        mg, mr = g.get_map(), rk.get_map()
+        assert np.abs(mg["elevation"] - mr["elevation"]).max() <= 1e-5
+        assert np.abs(mg["variance"] - mr["variance"]).max() <= 1e-6
+        for k in ("R", "G", "B"):
+            assert np.array_equal(mg[k], mr[k])
+        g.Mapvar_update(L, 0.002)
+        rk.mapvar_update(0.002)

@@ -1,0 +1,105 @@
+"""CPU tests of host-side logic: synthetic data determinism, the pygicp.downsample restatement, and the multi-GPU
+sharding / exchange helpers under a 2-process gloo group."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT
+from mr_slam_b200 import dist as mdist
+from mr_slam_b200 import synth
+
+
+def test_synth_is_deterministic_and_sized():
+    a = synth.make_scan(synth.pose_matrix(1, 2, 0, 0.3), "vlp16", scan_id=5)
+    b = synth.make_scan(synth.pose_matrix(1, 2, 0, 0.3), "vlp16", scan_id=5)
+    assert a.shape == (16384, 3) and a.dtype == np.float32 and np.array_equal(a, b)
+    src, tgt, T_gt, T_guess, _, _ = synth.make_pair(3, "vlp16")
+    te, re = synth.pose_error(T_guess, T_gt)
+    assert te < 0.6 and re < np.deg2rad(2.5)
+    # the pair is consistent: transforming the source by T_gt lands on the same surfaces as the target
+    import oracle
+    moved = (src @ T_gt[:3, :3].T + T_gt[:3, 3]).astype(np.float32)
+    _, d2 = oracle.knn(tgt, moved[::16], 1)
+    assert np.median(d2) < 0.05
+
+
+def test_downsample_matches_reference_counts_loosely():
+    """pygicp.downsample (ApproximateVoxelGrid restatement): README reports 17249 pts for the 0.1 m grid of the fixture;
+    our golden (same algorithm, frozen) has 17047 -- here only determinism and voxel-size behaviour are checked."""
+    from mr_slam_b200 import pygicp
+    rng = np.random.default_rng(0)
+    pts = rng.uniform(-5, 5, (20000, 3))
+    a = pygicp.downsample(pts, 0.5)
+    b = pygicp.downsample(pts, 0.5)
+    assert np.array_equal(a, b) and a.shape[1] == 3 and a.dtype == np.float64
+    assert len(pygicp.downsample(pts, 1.0)) < len(a) < len(pts)
+
+
+def test_pair_sharding_is_a_partition():
+    for world in (1, 2, 4, 8):
+        pairs = mdist.ring_candidate_pairs(world, 5)
+        seen = []
+        for r in range(world):
+            mine = mdist.shard_pairs(pairs, r, world)
+            assert all(pairs[i][0] == r for i in mine)
+            seen += mine
+        assert sorted(seen) == list(range(len(pairs)))
+        need = mdist.requested_targets(pairs, world)
+        if world > 1:
+            assert all(len(n) == 5 for n in need)
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        S, N = 3, 50
+        local = torch.full((S, N, 3), float(rank)) + torch.arange(S).view(S, 1, 1)
+        allc = mdist.allgather_slots(local)
+        assert allc.shape == (world, S, N, 3)
+        for r in range(world):
+            assert torch.equal(allc[r], torch.full((S, N, 3), float(r)) + torch.arange(S).view(S, 1, 1))
+        pairs = mdist.ring_candidate_pairs(world, S)
+        mine = mdist.shard_pairs(pairs, rank, world)
+        T_local = torch.stack([torch.eye(4) * (i + 1) for i in mine])
+        T_all = mdist.gather_results(T_local, mine, len(pairs))
+        for i in range(len(pairs)):
+            assert torch.equal(T_all[i], torch.eye(4) * (i + 1))
+        q.put((rank, "ok"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_exchange_helpers_world2_gloo():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    got = sorted(q.get(timeout=5) for _ in range(2))
+    assert got == [(0, "ok"), (1, "ok")]
+
+
+def test_bench_reference_arm_prints_contract_line():
+    import json
+    import subprocess
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
+    assert line["e2e"]["h2d_bytes_per_step"] == 0

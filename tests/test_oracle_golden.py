@@ -1,0 +1,213 @@
+"""CPU tests: the oracle against the reference's own fixtures / known answers / code (tests/golden), and its internal
+consistency.  These pin the checker before the CUDA path is compared with it."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import GOLDEN, rel_l2
+from mr_slam_b200 import synth
+
+
+def test_kdtree_is_exact():
+    rng = np.random.default_rng(0)
+    pts = rng.normal(size=(3000, 3)).astype(np.float32)
+    pts[100:110] = pts[90:100]  # exact duplicates: ties must resolve to the lowest index
+    q = np.concatenate([pts[:500], rng.normal(size=(200, 3)).astype(np.float32)])
+    for k in (1, 5, 15, 20):
+        i1, d1 = oracle.knn(pts, q, k)
+        i2, d2 = oracle.knn(pts, q, k, brute=True)
+        assert np.array_equal(i1, i2) and np.array_equal(d1, d2)
+    # fewer points than k
+    i1, d1 = oracle.knn(pts[:7], q[:10], 15)
+    assert (i1[:, 7:] == -1).all() and np.isinf(d1[:, 7:]).all()
+
+
+def test_gicp_reference_fixture_tolerances(gicp_golden):
+    """FG/src/test/gicp_test.cpp:147-201: forward / backward alignments of the reference's own PCD pair must land within
+    t < 0.05 m, r < 1 deg of data/relative.txt and converge.  Library defaults, identity guess."""
+    rel = gicp_golden["relative"]
+    for name, s, t in (("forward", "source", "target"), ("backward", "target", "source")):
+        g = oracle.FastGICP()
+        g.set_num_threads(4)
+        g.set_input_target(gicp_golden[t])
+        g.set_input_source(gicp_golden[s])
+        g.align()
+        r = g.result()
+        T = r["Td"] if name == "forward" else np.linalg.inv(r["Td"])
+        te, re = synth.pose_error(T, rel)
+        assert te < 0.05 and re < np.deg2rad(1.0) and r["converged"]
+        # frozen known answer of the oracle itself (guards against silent drift of the checker)
+        assert np.abs(r["Td"] - gicp_golden[name + "_T"]).max() < 1e-9
+
+
+def test_gicp_readme_known_answer(readme_golden):
+    """FG/README.md:110-113: fitness_score of fgicp_mt 0.204412 / fgicp_st 0.204379 on the same pair after
+    ApproximateVoxelGrid(0.1)."""
+    g = oracle.FastGICP()
+    g.set_num_threads(4)
+    g.set_input_target(readme_golden["target"])
+    g.set_input_source(readme_golden["source"])
+    g.align()
+    fit = g.get_fitness_score()
+    assert abs(fit - 0.204412) < 5e-4
+    assert abs(fit - float(readme_golden["fitness"])) < 1e-9
+
+
+def test_gicp_swap_source_target(gicp_golden):
+    """gicp_test.cpp:171-200 "swap and set source/target" cases."""
+    rel = gicp_golden["relative"]
+    g = oracle.FastGICP()
+    g.set_num_threads(4)
+    g.set_input_source(gicp_golden["target"])
+    g.swap_source_and_target()
+    g.set_input_source(gicp_golden["source"])
+    g.align()
+    te, re = synth.pose_error(g.result()["Td"], rel)
+    assert te < 0.05 and re < np.deg2rad(1.0)
+
+
+def test_polar_oracle_equals_reference_cpu_twin():
+    """Oracle vs outputs of the reference's unmodified CPU polar voxeliser on the reference's own 1.bin / 2.bin fixtures."""
+    z = np.load(os.path.join(GOLDEN, "polar_fixture.npz"))
+    for name in ("disco1", "disco2"):
+        pts = z[name + "_points"]
+        soa = np.ascontiguousarray(pts.T.reshape(-1))
+        for ci, c in enumerate(z["cfgs"]):
+            o = oracle.polar(soa, len(pts), *[int(v) for v in c])
+            exp = np.zeros_like(o)
+            exp[z["%s_cfg%d_idx" % (name, ci)]] = z["%s_cfg%d_val" % (name, ci)]
+            assert np.array_equal(o, exp)
+
+
+def test_polar_cpu_twin_live():
+    """Same comparison with the compiled reference twin itself when oracle/_ref is present (authoring container / GPU box)."""
+    from oracle import ref
+    if not ref.available("polar_cpu"):
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(4)
+    pts = rng.uniform(-0.99, 0.99, (20000, 3)).astype(np.float32)
+    soa = np.ascontiguousarray(pts.T.reshape(-1))
+    for c in ((1, 1, 40, 120, 20, 1), (1, 1, 40, 120, 4, 3)):
+        o, idx, nd = oracle.polar(soa, len(pts), *c, want_idx=True)
+        assert nd == 0
+        assert np.array_equal(o, ref.polar_cpu(soa, len(pts), *c))
+
+
+def test_voxelocc_oracle_semantics():
+    """manager.cu:64-85 restated in plain python on a small case (sequential scatter in point order)."""
+    rng = np.random.default_rng(1)
+    n, nx, ny, nh = 3000, 12, 10, 3
+    pts = rng.uniform(-1.1, 1.1, (n, 3)).astype(np.float32)
+    pts[5] = 0.0
+    soa = np.ascontiguousarray(pts.T.reshape(-1))
+    out, idx, nd = oracle.voxelocc(soa, n, 1, 1, nx, ny, nh, 1, want_idx=True)
+    exp = np.zeros(nx * ny * nh * 3, np.float32)
+    maxh = np.zeros(nx * ny)
+    gx, gy, gh = (np.float32(2.0 * 1.0 / nx), np.float32(2.0 * 1.0 / ny), np.float32(2.0 * 1.0 / nh))
+    for i in range(n):
+        v = pts[i].copy()
+        v[v == 0] = np.float32(0.0001)
+        v[v > 1] = np.float32(0.9999)
+        v[v < -1] = np.float32(-0.9999)
+        ix, iy, ih = (int(np.floor((np.float64(v[0]) + 1.0) / np.float64(gx))), int(np.floor((np.float64(v[1]) + 1.0) / np.float64(gy))),
+                      int(np.floor((np.float64(v[2]) + 1.0) / np.float64(gh))))
+        assert (ix, iy, ih) == (idx[i], idx[i + n], idx[i + 2 * n])
+        if not (0 <= ix < nx and 0 <= iy < ny and 0 <= ih < nh):
+            continue
+        slot = 3 * (iy + ix * ny + ih * ny * nx)
+        exp[slot], exp[slot + 1] = pts[i, 0], pts[i, 1]
+        if maxh[iy + ix * ny] < pts[i, 2]:
+            exp[slot + 2] = pts[i, 2]
+            maxh[iy + ix * ny] = pts[i, 2]
+    assert np.array_equal(out, exp)
+
+
+def test_elevation_oracle_matches_naive_gfuse():
+    """G_fuse restated literally (per cell, loop over ALL points, gpu_process.cu:477-535) on a tiny case."""
+    rng = np.random.default_rng(2)
+    L, n = 6, 400
+    om = oracle.ElevationMap(L, 0.5)
+    idx = rng.integers(-1, L * L, n).astype(np.int32)
+    h = rng.normal(0, 1.0, n).astype(np.float32)
+    h[rng.random(n) < 0.05] = -1.0
+    v = rng.uniform(1e-5, 0.05, n).astype(np.float32)
+    R = (rng.integers(0, 3, n)).astype(np.int32)
+    G = np.ones(n, np.int32)
+    B = np.ones(n, np.int32)
+    I = rng.random(n).astype(np.float32)
+    om.fuse(idx, R, G, B, I, h, v)
+    m = om.get_map()
+    e = np.full(L * L, -10, np.float32)
+    var = np.full(L * L, -10, np.float32)
+    inten = np.zeros(L * L, np.float32)
+    for c in range(L * L):
+        for i in range(n):
+            if idx[i] != c or h[i] == -1:
+                continue
+            col = R[i] != 0 and G[i] != 0 and B[i] != 0 and I[i] != 0
+            if e[c] == -10:
+                e[c], var[c] = h[i], v[i]
+                if col:
+                    inten[c] = I[i]
+            else:
+                md = np.float32(abs(np.float32(h[i] - e[c]))) / np.float32(np.sqrt(var[c]))
+                if md > 5:
+                    if e[c] < h[i]:
+                        e[c], var[c] = h[i], v[i]
+                        if col:
+                            inten[c] = I[i]
+                else:
+                    ne = np.float32(np.float32(var[c] * h[i]) + np.float32(v[i] * e[c])) / np.float32(var[c] + v[i])
+                    nv = np.float32(v[i] * var[c]) / np.float32(v[i] + var[c])
+                    e[c], var[c] = ne, nv
+                    if col:
+                        inten[c] = I[i]
+        if var[c] < 0.0001:
+            var[c] = 0.0001
+    assert np.allclose(m["elevation"], e, rtol=0, atol=2e-6)  # the naive loop has no FMA contraction: last-bit differences only
+    assert np.allclose(m["variance"], var, rtol=1e-6, atol=0)
+    assert np.array_equal(m["intensity"], inten)
+    assert (m["variance"] >= 0.0001).all()  # empty cells are clamped from -10 to 1e-4, like the reference
+
+
+def test_radon_oracle_vs_reference_analytic():
+    """torch-radon's own test (tests/test_parallel_beam.py:48-70): forward projection of a discretised random phantom vs the
+    analytic line integrals of the reference's symbolic.cpp, tolerance 2e-3*(512/A)*(512/D)."""
+    from oracle import ref
+    if not ref.available("symbolic"):
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(7)
+    H = W = D = 128
+    A = 128
+    f = ref.Symbolic(H, W)
+    for _ in range(30):
+        w, cx, cy = rng.uniform(0, 1), rng.uniform(-W / 2, W / 2), rng.uniform(-H / 2, H / 2)
+        rx, ry = rng.uniform(W / 32, W / 4), rng.uniform(H / 32, H / 4)
+        if rng.integers(0, 2) < 0.25:
+            f.add_ellipse(w, cx, cy, rx, ry)
+        else:
+            f.add_gaussian(w, cx, cy, rx, ry)
+    img = f.discretize()
+    angles = np.linspace(0, 2 * np.pi, A, endpoint=False).astype(np.float32)
+    tol = 2e-3 * (512 / A) * (512 / D)
+    sino_ref = f.forward(angles, D)
+    for wb in (0, 8):
+        sino = oracle.radon_forward(img[None], angles, D, 1.0, wb)[0]
+        assert rel_l2(sino_ref, sino) < tol
+
+
+def test_ring_tail_oracle_vs_reference_python():
+    """Oracle vs golden vectors produced by the reference's own python (util.py:197-198 and fast_corr, :362-374)."""
+    z = np.load(os.path.join(GOLDEN, "ring_fixture.npz"))
+    for i in range(2):
+        _, tir = oracle.ring_tiring(z["sino"][i])
+        assert np.abs(tir - z["tiring"][i]).max() / np.abs(z["tiring"][i]).max() < 1e-5
+    for i in range(2):
+        for j in range(2):
+            d, a, _ = oracle.ring_fast_corr(z["tiring"][i], z["tiring"][j])
+            assert abs(d - z["fast_corr_dist"][i, j]) < 1e-5 and a == z["fast_corr_angle"][i, j]
+    # load_pc_infer restatement used by the bench
+    got = synth.ring_preprocess(z["pc"])
+    assert np.array_equal(got, z["pc_infer"])  # the reference keeps all columns of the surviving rows

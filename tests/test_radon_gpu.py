@@ -1,0 +1,126 @@
+"""GPU parity tests of the Radon forward projection and the RING descriptor tail / matcher.
+Tolerance (north_star): RING descriptor within 1e-4 (relative)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from conftest import GOLDEN, rel_l2
+from mr_slam_b200 import ring
+from mr_slam_b200.torch_radon import ParallelBeam
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+ANG = np.linspace(0, 2 * np.pi, 120).astype(np.float32)   # util.py:192 (endpoint inclusive)
+
+
+def images(b=4, s=120, seed=5):
+    rng = np.random.default_rng(seed)
+    return (rng.random((b, s, s)) * (rng.random((b, s, s)) < 0.2)).astype(np.float32)
+
+
+@pytest.mark.parametrize("interp,wb", [("exact", 0), ("texture", 8)])
+def test_radon_vs_oracle(gpu, interp, wb):
+    img = images()
+    pb = ParallelBeam(120, ANG, interp=interp, fast_trig=False)
+    got = pb.forward(torch.from_numpy(img).cuda()).cpu().numpy()
+    exp = oracle.radon_forward(img, ANG, 120, 1.0, wb)
+    assert got.shape == (4, 120, 120)
+    assert np.abs(got - exp).max() <= TOL * np.abs(exp).max()
+    assert rel_l2(exp, got) < 1e-6
+
+
+def test_radon_shapes_and_linearity(gpu):
+    pb = ParallelBeam(96, (0.0, np.pi, 50), interp="exact", fast_trig=False)     # (start, end, n) tuple form, endpoint=False
+    x = torch.from_numpy(images(6, 80, 1)).cuda().reshape(2, 3, 80, 80)
+    y = pb.forward(x)
+    assert y.shape == (2, 3, 50, 96) and y.is_cuda
+    a, b = x[0, 0], x[1, 2]
+    lin = pb.forward(2.0 * a - 0.5 * b)
+    assert torch.allclose(lin, 2.0 * pb.forward(a) - 0.5 * pb.forward(b), rtol=1e-5, atol=1e-4)   # the projection is linear
+    with pytest.raises(RuntimeError):
+        pb.forward(x.cpu())                                                       # no CPU fallback
+
+
+def test_radon_vs_reference_analytic(gpu):
+    """the reference's own acceptance test (torch-radon/tests/test_parallel_beam.py:48-70)"""
+    from oracle import ref
+    if not ref.available("symbolic"):
+        pytest.skip("oracle/_ref not present")
+    rng = np.random.default_rng(7)
+    H = W = D = A = 128
+    f = ref.Symbolic(H, W)
+    for _ in range(30):
+        args = (rng.uniform(0, 1), rng.uniform(-W / 2, W / 2), rng.uniform(-H / 2, H / 2), rng.uniform(W / 32, W / 4), rng.uniform(H / 32, H / 4))
+        (f.add_ellipse if rng.integers(0, 2) < 0.25 else f.add_gaussian)(*args)
+    img = f.discretize()
+    angles = np.linspace(0, 2 * np.pi, A, endpoint=False).astype(np.float32)
+    sino = ParallelBeam(D, angles).forward(torch.from_numpy(img).cuda()[None])[0].cpu().numpy()
+    assert rel_l2(f.forward(angles, D), sino) < 2e-3 * (512 / A) * (512 / D)
+
+
+def test_radon_vs_reference_kernel(gpu):
+    """Side by side with the reference's own CUDA kernel (hardware texture filtering, __sinf/__cosf).  Our default mode
+    (texture-weight emulation + fast trig) tracks it much closer than exact bilinear does; both deviations are reported in
+    DESIGN.md.  Bounds here are loose upper limits of what was measured."""
+    from oracle import ref
+    if not ref.available("radon"):
+        pytest.skip("oracle/_ref not present")
+    img = images(4, 120, 2)
+    exp = ref.radon_forward(img, ANG, 120, 1.0)
+    x = torch.from_numpy(img).cuda()
+    emu = ParallelBeam(120, ANG, interp="texture", fast_trig=True).forward(x).cpu().numpy()
+    exact = ParallelBeam(120, ANG, interp="exact", fast_trig=False).forward(x).cpu().numpy()
+    e_emu, e_exact = rel_l2(exp, emu), rel_l2(exp, exact)
+    print("relative L2 vs reference kernel: texture-emulation %.3e, exact bilinear %.3e" % (e_emu, e_exact))
+    assert e_emu < 2e-3 and e_exact < 5e-3
+
+
+def test_tiring_and_fast_corr_vs_reference_python(gpu):
+    z = np.load(os.path.join(GOLDEN, "ring_fixture.npz"))
+    tir = ring.tiring(torch.from_numpy(z["sino"]).cuda())
+    assert tir.dtype == torch.complex64 and tuple(tir.shape) == (2, 1, 120, 120)
+    got = tir.cpu().numpy()
+    assert np.abs(got - z["tiring"]).max() <= TOL * np.abs(z["tiring"]).max()
+    db = torch.from_numpy(z["tiring"]).cuda()
+    for i in range(2):
+        dist, ang = ring.fast_corr_batch(db[i], db)
+        assert np.abs(dist.cpu().numpy() - z["fast_corr_dist"][i]).max() < 1e-4
+        assert np.array_equal(ang.cpu().numpy(), z["fast_corr_angle"][i])
+    # yaw recovery: the descriptor of a sinogram rolled by s rows correlates at angle s (reference python gives the same)
+    rolled = torch.from_numpy(np.roll(z["sino"][0], int(z["rolled_by"]), axis=-2)[None]).cuda()
+    dist, ang = ring.fast_corr_batch(db[0], ring.tiring(rolled))
+    assert int(ang[0]) == int(z["rolled_angle"]) and abs(float(dist[0]) - float(z["rolled_dist"])) < 1e-4
+
+
+def test_tiring_vs_torch_fft_on_gpu(gpu):
+    """the reference's two lines (util.py:197-198) run with torch on the GPU, next to our fused kernels"""
+    sino = torch.from_numpy(oracle.radon_forward(images(3), ANG, 120, 1.0, 0)).cuda()[:, None]
+    got = ring.tiring(sino)
+    for i in range(3):
+        x = sino[i]
+        exp = torch.fft.fft2((x - x.mean()) / x.std(), dim=-2, norm="ortho")
+        assert (got[i] - exp).abs().max() <= TOL * exp.abs().max()
+
+
+def test_generate_ring_pipeline_descriptor_tolerance(gpu):
+    """BEV -> Radon -> normalise -> FFT for a batch, against the oracle chain: RING descriptor within 1e-4."""
+    from mr_slam_b200 import synth
+    scans = [synth.ring_preprocess(synth.make_scan(synth.pose_matrix(i, i, 0, 0.5 * i), "vlp16", 60 + i) + np.array([0, 0, 1.8], np.float32))
+             for i in range(4)]
+    bev = ring.bev_batch(scans)
+    sino, tir = ring.generate_RING_batch(bev, interp="exact", fast_trig=False, want_sino=True)
+    for i, p in enumerate(scans):
+        soa = np.ascontiguousarray(p.T.reshape(-1))
+        bev_o = oracle.voxelocc(soa, len(p), 1, 1, 120, 120, 1, 1).reshape(-1, 3)[:, 2].reshape(1, 120, 120)
+        assert np.array_equal(bev[i].cpu().numpy(), bev_o[0])
+        sino_o = oracle.radon_forward(bev_o, ANG, 120, 1.0, 0)
+        assert np.abs(sino[i].cpu().numpy() - sino_o).max() <= TOL * np.abs(sino_o).max()
+        _, tir_o = oracle.ring_tiring(sino_o)
+        assert np.abs(tir[i].cpu().numpy() - tir_o).max() <= TOL * np.abs(tir_o).max()
+    # batch of 256 (BASELINE config 3 size): every descriptor equals its single-image evaluation (batch independence)
+    big = bev.repeat(64, 1, 1)
+    _, tb = ring.generate_RING_batch(big, interp="exact", fast_trig=False)
+    assert torch.equal(tb[:4], tir) and torch.equal(tb[252:], tir)
