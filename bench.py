@@ -53,46 +53,57 @@ def make_pairs(rank, n_pairs):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / throttle reasons sampled DURING the timed region.  NVML (nvidia_ml_py) from a background thread: the
+    `nvidia-smi -lms` loop of the profiling recipe was measured to stall this launch/sync-heavy workload by 3-4x."""
 
-    def __init__(self, index):
-        self.index = index
-        self.proc = None
-        self.lines = []
+    def __init__(self, index, period=0.05):
+        self.index, self.period = index, period
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thr = None
+        self.err = None
 
     def start(self):
-        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except Exception:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception as e:  # noqa: BLE001
+            self.err = "nvml unavailable: %r" % (e,)
+            return
+        self._thr = threading.Thread(target=self._run, daemon=True)
+        self._thr.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception as e:  # noqa: BLE001
+                self.err = repr(e)
+                break
+            self._stop.wait(self.period)
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons = [], None, set()
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1]))
-                mx = float(f[2])
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join(1.0)
+        out = {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+               "reasons": sorted(self.reasons), "samples": len(self.samples), "source": "nvml"}
+        if self.err:
+            out["error"] = self.err
+        return out
 
 
 def oracle_align_sample(pairs, n_sample, threads):
@@ -244,6 +255,7 @@ def main():
             torch.cuda.current_stream().synchronize()
         else:
             tgt_dev = offer_dev
+        tp0 = time.perf_counter()
         regs = new_regs()
         clouds = []
         for i, g in enumerate(regs):
@@ -252,16 +264,20 @@ def main():
             g.set_input_source(cs)
             g.set_input_target(ct)
             clouds += [cs, ct]
+        tp1 = time.perf_counter()
         Ts = pygicp.align_batch(regs, guesses)
+        tp2 = time.perf_counter()
+        if os.environ.get("BENCH_DEBUG"):
+            print("[debug] setup %.2f ms align_batch %.2f ms iters %s" % (1e3 * (tp1 - tp0), 1e3 * (tp2 - tp1), [r.num_iterations() for r in regs]), file=sys.stderr)
         with torch.cuda.stream(lib_stream):
             e1.record()
-        fused = 0
         for i in range(n_pairs):
             emap.Move(pairs[i]["pose"][:3, 3].astype(np.float32), ELEV_RES, ELEV_L)
-            fused += emap.process_fuse_device(soa_dev[i][0], soa_dev[i][1], soa_dev[i][2], N_POINTS, *elev_args(i), near_filter=True)
+            emap.process_fuse_device(soa_dev[i][0], soa_dev[i][1], soa_dev[i][2], N_POINTS, *elev_args(i), near_filter=True, want_count=False)
         with torch.cuda.stream(lib_stream):
             e2.record()
         e2.synchronize()
+        fused = emap.fused_total(reset=True)
         return e0.elapsed_time(e1), e1.elapsed_time(e2), fused, Ts, regs
 
     def step_e2e():

@@ -39,6 +39,9 @@ int mrslam_device_synchronize(void);
 void* mrslam_stream(void);                   /* the cudaStream_t every kernel of this library is launched on */
 /* instrumentation: kernels launched by this library since process start (bench.py "gpu_launches") */
 unsigned long long mrslam_kernel_launch_count(void);
+/* instrumentation: per-kernel device time with CUDA events on the library stream (ids: see ProfId in csrc/common.cuh) */
+int mrslam_prof_enable(int on);
+int mrslam_prof_get(int id, double* total_ms, long long* launches);
 
 /* ------------------------------------------------------------------------------------------ */
 /* FastGICP  --  replaces fast_gicp::FastGICP<PointSource,PointTarget>                          */
@@ -111,6 +114,10 @@ int mrslam_gicp_evaluate_cost(mrslam_gicp_t*, const float* T16, double* H36, dou
 /* test hooks: state of the last linearisation in SOURCE ORIGINAL ORDER (corr = target original index or -1) */
 int mrslam_gicp_debug_last_correspondences(mrslam_gicp_t*, int* corr, float* sq_dist, double* mahalanobis9);
 int mrslam_gicp_compute_error(mrslam_gicp_t*, const double* T16, double* cost); /* FastGICP::compute_error */
+/* instrumentation: distance evaluations (0: kNN, 1: NN-1) and k-min insertion rounds (2) since stats_enable(1) */
+int mrslam_gicp_stats_enable(int on);
+unsigned long long mrslam_gicp_stats_get(int which);
+unsigned long long mrslam_gicp_stats_pairs(void);
 /* kNN building block (calculate_covariances' search): indices (original order) and squared distances, n x k */
 int mrslam_cloud_knn(mrslam_cloud_t*, int k, int* idx_out, float* sqd_out);
 
@@ -145,6 +152,8 @@ int mrslam_elev_process_fuse_device(mrslam_elev_t*, const float* d_x, const floa
                                     const float* sensorJacobian3, const float* rotationVariance9, const float* C_SB_transpose9,
                                     const float* P_mul_C_BM_transpose3, const float* B_r_BS_skew9, int near_filter,
                                     long long* n_fused);
+/* cell fuses accumulated on the device by process_fuse_device calls that passed n_fused == NULL (no per-frame host sync) */
+int mrslam_elev_fused_total(mrslam_elev_t*, int reset, long long* total);
 int mrslam_elev_mapvar_update(mrslam_elev_t*, int length, float var_update);          /* Mapvar_update  :1144 */
 int mrslam_elev_map_optmove(mrslam_elev_t*, const float* opt_p, float height_update, float resolution, int length,
                             float* opt_aligned_position2);                             /* Map_optmove    :1213 */

@@ -104,6 +104,7 @@ def _declare(L):
         L.mrslam_elev_fuse.argtypes = [vp, i, i, ip, ip, ip, ip, fp, fp, fp, C.POINTER(ll)]
         L.mrslam_elev_process_fuse_device.argtypes = [vp, fp, fp, fp, i, fp, d, d, f, f, f] + [fp] * 5 + [i, C.POINTER(ll)]
         L.mrslam_elev_mapvar_update.argtypes = [vp, i, f]
+        L.mrslam_elev_fused_total.argtypes = [vp, i, C.POINTER(ll)]
         L.mrslam_elev_map_optmove.argtypes = [vp, fp, f, f, i, fp]
         L.mrslam_elev_map_closeloop.argtypes = [vp, fp, f, i, f]
         L.mrslam_elev_get_map.argtypes = [vp] + [C.c_void_p] * 7

@@ -301,10 +301,10 @@ static int fuse_sorted(Elev* m, int n, const float* d_h, const float* d_v, const
     MR_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp, dk, dv, n, 0, bits, st));
     MR_CHECK(m->cubtmp.reserve(tmp));
     MR_CUDA(cub::DeviceRadixSort::SortPairs(m->cubtmp.p, tmp, dk, dv, n, 0, bits, st));
-    MR_CUDA(cudaMemsetAsync(m->counter.p, 0, sizeof(unsigned long long), st));
+    if (n_fused) MR_CUDA(cudaMemsetAsync(m->counter.p, 0, sizeof(unsigned long long), st));
     k_elev_fuse_segments<<<(n + 127) / 128, 128, 0, st>>>(dk.Current(), dv.Current(), n, cells, d_h, d_v, d_R, d_G, d_B, d_I,
                                                          m->elevation.p, m->variance.p, m->intensity.p, m->R.p, m->G.p, m->B.p,
-                                                         m->counter.p);
+                                                         n_fused ? m->counter.p : m->counter.p + 1);
     count_launch(1);
   }
   k_elev_clamp_var<<<((cells + 3) / 4 + 255) / 256, 256, 0, st>>>(m->variance.p, cells);
@@ -393,6 +393,8 @@ int mrslam_elev_init(mrslam_elev_t* h, int length, float resolution, float mahal
   k_elev_fill<<<((int)n + 255) / 256, 256, 0, rt().stream>>>(m->elevation.p, m->variance.p, m->intensity.p, m->lowest.p, m->traver.p,
                                                                m->R.p, m->G.p, m->B.p, (int)n, 0);
   count_launch(1);
+  MR_CHECK(m->counter.reserve(2));
+  MR_CUDA(cudaMemsetAsync(m->counter.p, 0, 2 * sizeof(unsigned long long), rt().stream));
   MR_CUDA(cudaGetLastError());
   return MRSLAM_OK;
 }
@@ -549,6 +551,23 @@ int mrslam_elev_process_fuse_device(mrslam_elev_t* h, const float* d_x, const fl
     count_launch(1);
   }
   return fuse_sorted(m, n, m->pzt.p, m->pvar.p, nullptr, nullptr, nullptr, nullptr, n_fused);
+}
+
+// cell fuses accumulated by calls that passed n_fused == NULL (no host sync per frame); optionally reset
+int mrslam_elev_fused_total(mrslam_elev_t* h, int reset, long long* total) {
+  REQ(h);
+  Elev* m = E(h);
+  REQ_INIT(m);
+  std::lock_guard<std::mutex> lk2(m->mu);
+  std::lock_guard<std::mutex> lk(rt().mu);
+  unsigned long long c = 0;
+  if (m->counter.p) {
+    MR_CUDA(cudaMemcpyAsync(&c, m->counter.p + 1, sizeof(c), cudaMemcpyDeviceToHost, rt().stream));
+    if (reset) MR_CUDA(cudaMemsetAsync(m->counter.p + 1, 0, sizeof(c), rt().stream));
+    MR_CUDA(cudaStreamSynchronize(rt().stream));
+  }
+  if (total) *total = (long long)c;
+  return MRSLAM_OK;
 }
 
 int mrslam_elev_mapvar_update(mrslam_elev_t* h, int length, float upd) {

@@ -27,17 +27,13 @@ struct Cloud {
   DevBuf<double> cov;
   DevBuf<int> knn_ids;  // [npad*k] neighbour lists (scratch between k_knn_search and k_cov)
   bool cov_valid = false;
-  // scratch for the build
-  DevBuf<float> raw;
-  DevBuf<unsigned long long> keys, keys_alt;
-  DevBuf<int> vals, vals_alt;
-  DevBuf<unsigned char> cubtmp;
-  DevBuf<unsigned> bbox;
+  bool built = false;   // spatial structures (psort / tb / sb) are produced lazily, batched with the other clouds of a call
+  DevBuf<float> raw;    // staging of host input
   int refs = 1;
 
-  int build_from_device_raw(const float* d_raw, int n_, int stride) {
+  // stage 1 (at setInput time): points into porig (device).  The Morton sort etc. is deferred to build_clouds().
+  int set_from_device_raw(const float* d_raw, int n_, int stride) {
     cudaStream_t st = rt().stream;
-    ProfScope ps(PROF_CLOUD_BUILD);
     n = n_;
     npad = ((n + TILE - 1) / TILE) * TILE;
     ntiles = npad / TILE;
@@ -47,43 +43,18 @@ struct Cloud {
     nsuper_pad = ((nsuper + 31) / 32) * 32;
     if (nsuper_pad == 0) nsuper_pad = 32;
     cov_valid = false;
+    built = false;
     MR_CHECK(porig.reserve(std::max(n, 1)));
-    MR_CHECK(psort.reserve(std::max(npad, 1)));
-    MR_CHECK(tb.reserve((size_t)6 * ntiles_pad));
-    MR_CHECK(sb.reserve((size_t)6 * nsuper_pad));
-    MR_CHECK(keys.reserve(std::max(n, 1)));
-    MR_CHECK(keys_alt.reserve(std::max(n, 1)));
-    MR_CHECK(vals.reserve(std::max(n, 1)));
-    MR_CHECK(vals_alt.reserve(std::max(n, 1)));
-    MR_CHECK(bbox.reserve(8));
     if (n > 0) {
+      ProfScope ps(PROF_CLOUD_BUILD);
       k_pack_points<<<(n + 255) / 256, 256, 0, st>>>(d_raw, n, stride, porig.p);
-      k_bbox_init<<<1, 32, 0, st>>>(bbox.p);
-      int nb = std::min((n + 255) / 256, 148 * 4);
-      k_bbox<<<nb, 256, 0, st>>>(porig.p, n, bbox.p);
-      k_morton<<<(n + 255) / 256, 256, 0, st>>>(porig.p, n, bbox.p, keys.p, vals.p);
-      count_launch(4);
-      cub::DoubleBuffer<unsigned long long> dk(keys.p, keys_alt.p);
-      cub::DoubleBuffer<int> dv(vals.p, vals_alt.p);
-      size_t tmp = 0;
-      MR_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp, dk, dv, n, 0, 48, st));
-      MR_CHECK(cubtmp.reserve(tmp));
-      MR_CUDA(cub::DeviceRadixSort::SortPairs(cubtmp.p, tmp, dk, dv, n, 0, 48, st));
-      const int* order = dv.Current();
-      int warps = ntiles_pad;
-      k_gather_tiles<<<(warps * 32 + 127) / 128, 128, 0, st>>>(porig.p, order, n, ntiles, ntiles_pad, psort.p, tb.p);
       count_launch(1);
-    } else {
-      k_gather_tiles<<<(ntiles_pad * 32 + 127) / 128, 128, 0, st>>>(porig.p, nullptr, 0, 0, ntiles_pad, psort.p, tb.p);
-      count_launch(1);
+      MR_CUDA(cudaGetLastError());
     }
-    k_super_boxes<<<(nsuper_pad * 32 + 127) / 128, 128, 0, st>>>(tb.p, ntiles, ntiles_pad, nsuper_pad, sb.p);
-    count_launch(1);
-    MR_CUDA(cudaGetLastError());
     return MRSLAM_OK;
   }
 
-  int build_from_host(const float* xyz, int n_, int stride) {
+  int set_from_host(const float* xyz, int n_, int stride) {
     if (n_ < 0 || stride < 3 || (n_ > 0 && !xyz)) {
       set_error("cloud: bad arguments (n=%d stride=%d)", n_, stride);
       return MRSLAM_ERR_ARG;
@@ -94,14 +65,91 @@ struct Cloud {
       size_t bytes = ((size_t)(n_ - 1) * stride + 3) * sizeof(float);
       MR_CUDA(cudaMemcpyAsync(raw.p, xyz, bytes, cudaMemcpyHostToDevice, rt().stream));
     }
-    return build_from_device_raw(raw.p, n_, stride);
+    return set_from_device_raw(raw.p, n_, stride);
   }
 
   void release() {
     porig.release(); psort.release(); tb.release(); sb.release(); cov.release(); knn_ids.release(); raw.release();
-    keys.release(); keys_alt.release(); vals.release(); vals_alt.release(); cubtmp.release(); bbox.release();
   }
 };
+
+// scratch of the batched build (process-global, grow-only)
+struct BuildScratch {
+  DevBuf<unsigned long long> keys, keys_alt;
+  DevBuf<int> vals, vals_alt;
+  DevBuf<unsigned char> cubtmp;
+  DevBuf<unsigned> bbox;
+  DevBuf<BuildDesc> d_desc;
+  PinBuf<BuildDesc> h_desc;
+};
+static BuildScratch& build_scratch() {
+  static BuildScratch s;
+  return s;
+}
+
+// stage 2: Morton order, tiles and boxes of every not-yet-built cloud in `clouds`, ONE pass over the whole batch:
+// per-cloud bounding cube -> (cloud id, 48-bit Morton) keys -> one radix sort -> gather + tile boxes -> super-tile boxes.
+static int build_clouds(const std::vector<Cloud*>& clouds) {
+  std::vector<Cloud*> todo;
+  for (Cloud* c : clouds)
+    if (c && !c->built && std::find(todo.begin(), todo.end(), c) == todo.end()) todo.push_back(c);
+  if (todo.empty()) return MRSLAM_OK;
+  cudaStream_t st = rt().stream;
+  BuildScratch& S = build_scratch();
+  ProfScope ps(PROF_CLOUD_BUILD);
+  const int nc = (int)todo.size();
+  if (nc >= (1 << 15)) {
+    set_error("too many clouds in one batch (%d)", nc);
+    return MRSLAM_ERR_ARG;
+  }
+  MR_CHECK(S.h_desc.reserve(nc));
+  MR_CHECK(S.d_desc.reserve(nc));
+  long long total = 0;
+  int max_n = 0, max_tiles_pad = 0, max_super_pad = 0;
+  for (int i = 0; i < nc; i++) {
+    Cloud* c = todo[i];
+    MR_CHECK(c->psort.reserve(std::max(c->npad, 1)));
+    MR_CHECK(c->tb.reserve((size_t)6 * c->ntiles_pad));
+    MR_CHECK(c->sb.reserve((size_t)6 * c->nsuper_pad));
+    BuildDesc d;
+    d.porig = c->porig.p; d.psort = c->psort.p; d.tb = c->tb.p; d.sb = c->sb.p;
+    d.n = c->n; d.ntiles = c->ntiles; d.ntiles_pad = c->ntiles_pad; d.nsuper_pad = c->nsuper_pad;
+    d.offset = total;
+    S.h_desc.p[i] = d;
+    total += c->n;
+    max_n = std::max(max_n, c->n);
+    max_tiles_pad = std::max(max_tiles_pad, c->ntiles_pad);
+    max_super_pad = std::max(max_super_pad, c->nsuper_pad);
+  }
+  MR_CUDA(cudaMemcpyAsync(S.d_desc.p, S.h_desc.p, sizeof(BuildDesc) * nc, cudaMemcpyHostToDevice, st));
+  size_t tot = (size_t)std::max<long long>(total, 1);
+  MR_CHECK(S.keys.reserve(tot)); MR_CHECK(S.keys_alt.reserve(tot));
+  MR_CHECK(S.vals.reserve(tot)); MR_CHECK(S.vals_alt.reserve(tot));
+  MR_CHECK(S.bbox.reserve((size_t)6 * nc));
+  const int* order = S.vals.p;
+  if (total > 0) {
+    k_bbox_init<<<(nc * 6 + 127) / 128, 128, 0, st>>>(S.bbox.p, nc);
+    int gx = std::max(1, std::min((max_n + 255) / 256, 148 * 2));
+    k_bbox<<<dim3(gx, nc), 256, 0, st>>>(S.d_desc.p, S.bbox.p);
+    k_morton<<<dim3((max_n + 255) / 256, nc), 256, 0, st>>>(S.d_desc.p, S.bbox.p, S.keys.p, S.vals.p);
+    count_launch(3);
+    int bits = 48;
+    while ((1 << (bits - 48)) < nc) bits++;
+    cub::DoubleBuffer<unsigned long long> dk(S.keys.p, S.keys_alt.p);
+    cub::DoubleBuffer<int> dv(S.vals.p, S.vals_alt.p);
+    size_t tmp = 0;
+    MR_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp, dk, dv, (int)total, 0, bits, st));
+    MR_CHECK(S.cubtmp.reserve(tmp));
+    MR_CUDA(cub::DeviceRadixSort::SortPairs(S.cubtmp.p, tmp, dk, dv, (int)total, 0, bits, st));
+    order = dv.Current();
+  }
+  k_gather_tiles<<<dim3((max_tiles_pad * 32 + 127) / 128, nc), 128, 0, st>>>(S.d_desc.p, order);
+  k_super_boxes<<<dim3((max_super_pad * 32 + 127) / 128, nc), 128, 0, st>>>(S.d_desc.p);
+  count_launch(2);
+  MR_CUDA(cudaGetLastError());
+  for (Cloud* c : todo) c->built = true;
+  return MRSLAM_OK;
+}
 
 static int dispatch_knn(int k, const KnnParams* d_params, int nproblems, int max_tiles, bool with_cov) {
   if (k < 1 || k > 32) {
@@ -322,8 +370,18 @@ static void iso_to_T12(const Iso& x, double* T) {
 }
 
 // covariances for every distinct cloud of the batch that lacks them: one launch per k-capacity
+static int ensure_built(Gicp** hs, int n) {
+  std::vector<Cloud*> cs;
+  for (int i = 0; i < n; i++) {
+    cs.push_back(hs[i]->src);
+    cs.push_back(hs[i]->tgt);
+  }
+  return build_clouds(cs);
+}
+
 static int compute_covariances(Gicp** hs, int n) {
   BatchScratch& S = scratch();
+  MR_CHECK(ensure_built(hs, n));
   std::vector<Cloud*> todo;
   std::vector<int> ks, regs;
   for (int i = 0; i < n; i++)
@@ -634,6 +692,10 @@ static int fitness_batch(Gicp** hs, int n, double max_range, double* out) {
       return MRSLAM_ERR_STATE;
     }
     MR_CHECK(ensure_pair_buffers(g));
+    {
+      Gicp* one[1] = {g};
+      MR_CHECK(ensure_built(one, 1));
+    }
     S.h_pairs.p[i] = make_pair_params(g);
     S.h_active.p[i] = i;
     // final_transformation_ is the float cast of x0; the kernel casts the doubles below to float itself
@@ -685,7 +747,7 @@ mrslam_cloud_t* mrslam_cloud_create_host(const float* xyz, int n, int stride_flo
   if (ensure_init() != MRSLAM_OK) return nullptr;
   LOCK();
   Cloud* c = new Cloud();
-  if (c->build_from_host(xyz, n, stride_floats) != MRSLAM_OK) {
+  if (c->set_from_host(xyz, n, stride_floats) != MRSLAM_OK) {
     c->release();
     delete c;
     return nullptr;
@@ -700,7 +762,7 @@ mrslam_cloud_t* mrslam_cloud_create_device(const float* d_xyz, int n, int stride
     return nullptr;
   }
   Cloud* c = new Cloud();
-  if (c->build_from_device_raw(d_xyz, n, stride_floats) != MRSLAM_OK) {
+  if (c->set_from_device_raw(d_xyz, n, stride_floats) != MRSLAM_OK) {
     c->release();
     delete c;
     return nullptr;
@@ -720,6 +782,7 @@ int mrslam_cloud_knn(mrslam_cloud_t* h, int k, int* idx_out, float* sqd_out) {
   LOCK();
   Cloud* c = reinterpret_cast<Cloud*>(h);
   BatchScratch& S = scratch();
+  MR_CHECK(build_clouds(std::vector<Cloud*>(1, c)));
   MR_CHECK(S.h_knn.reserve(1));
   MR_CHECK(S.d_knn.reserve(1));
   DevBuf<int> di;
@@ -815,7 +878,7 @@ static int set_input_host(mrslam_gicp_t* h, bool source, const float* xyz, int n
   MR_CHECK(ensure_init());
   LOCK();
   Cloud* c = new Cloud();
-  int s = c->build_from_host(xyz, n, stride);
+  int s = c->set_from_host(xyz, n, stride);
   if (s != MRSLAM_OK) {
     c->release();
     delete c;
@@ -858,6 +921,7 @@ static int set_covs(mrslam_gicp_t* h, bool source, const double* cov16, int n) {
     set_error("setCovariances: cloud not set or size mismatch");
     return MRSLAM_ERR_STATE;
   }
+  MR_CHECK(build_clouds(std::vector<Cloud*>(1, c)));
   DevBuf<double> tmp;
   MR_CHECK(tmp.reserve((size_t)std::max(n, 1) * 16));
   MR_CHECK(c->cov.reserve((size_t)std::max(c->npad, 1) * 6));
@@ -880,6 +944,7 @@ static int get_covs(mrslam_gicp_t* h, bool source, double* cov16, int n) {
     set_error("getCovariances: cloud not set or size mismatch");
     return MRSLAM_ERR_STATE;
   }
+  MR_CHECK(build_clouds(std::vector<Cloud*>(1, c)));
   if (!c->cov_valid) {
     // compute for this cloud only
     Gicp tmpg = Gicp();

@@ -39,15 +39,28 @@ __global__ void k_pack_points(const float* __restrict__ raw, int n, int stride, 
   porig[i] = make_float4(p[0], p[1], p[2], 1.0f);
 }
 
-__global__ void k_bbox_init(unsigned* bb) {
-  if (threadIdx.x < 3) bb[threadIdx.x] = 0xffffffffu;
-  else if (threadIdx.x < 6) bb[threadIdx.x] = 0u;
+// ---- batched cloud build: every kernel handles all clouds of a batch (blockIdx.y = cloud) ----
+struct BuildDesc {
+  const float4* porig;
+  float4* psort;
+  float* tb;
+  float* sb;
+  int n, ntiles, ntiles_pad, nsuper_pad;
+  long long offset;  // position of this cloud's keys in the concatenated sort arrays
+};
+
+__global__ void k_bbox_init(unsigned* bb, int nclouds) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nclouds * 6) return;
+  bb[i] = (i % 6) < 3 ? 0xffffffffu : 0u;
 }
 
-__global__ void k_bbox(const float4* __restrict__ p, int n, unsigned* bb) {
+__global__ void k_bbox(const BuildDesc* __restrict__ descs, unsigned* bball) {
+  const BuildDesc D = descs[blockIdx.y];
+  unsigned* bb = bball + 6 * blockIdx.y;
   float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    float4 v = p[i];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < D.n; i += gridDim.x * blockDim.x) {
+    float4 v = D.porig[i];
     if (isfinite(v.x) && isfinite(v.y) && isfinite(v.z)) {
       mn[0] = fminf(mn[0], v.x); mn[1] = fminf(mn[1], v.y); mn[2] = fminf(mn[2], v.z);
       mx[0] = fmaxf(mx[0], v.x); mx[1] = fmaxf(mx[1], v.y); mx[2] = fmaxf(mx[2], v.z);
@@ -76,14 +89,17 @@ __device__ __forceinline__ unsigned long long spread16(unsigned v) {  // 16 bits
   return x;
 }
 
-__global__ void k_morton(const float4* __restrict__ p, int n, const unsigned* __restrict__ bb, unsigned long long* keys, int* vals) {
+// key = (cloud << 48) | 48-bit Morton code of the point in its cloud's bounding cube; value = index inside the cloud
+__global__ void k_morton(const BuildDesc* __restrict__ descs, const unsigned* __restrict__ bball, unsigned long long* keys, int* vals) {
+  const BuildDesc D = descs[blockIdx.y];
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  if (i >= D.n) return;
+  const unsigned* bb = bball + 6 * blockIdx.y;
   float mn[3] = {ord2f(bb[0]), ord2f(bb[1]), ord2f(bb[2])};
   float mx[3] = {ord2f(bb[3]), ord2f(bb[4]), ord2f(bb[5])};
   float ext = fmaxf(fmaxf(mx[0] - mn[0], mx[1] - mn[1]), fmaxf(mx[2] - mn[2], 1e-6f));
   float s = 65535.0f / ext;
-  float4 v = p[i];
+  float4 v = D.porig[i];
   float c[3] = {v.x, v.y, v.z};
   unsigned q[3];
 #pragma unroll
@@ -92,29 +108,30 @@ __global__ void k_morton(const float4* __restrict__ p, int n, const unsigned* __
     f = isfinite(f) ? fminf(fmaxf(f, 0.0f), 65535.0f) : 65535.0f;
     q[a] = (unsigned)f;
   }
-  keys[i] = spread16(q[0]) | (spread16(q[1]) << 1) | (spread16(q[2]) << 2);
-  vals[i] = i;
+  keys[D.offset + i] = ((unsigned long long)blockIdx.y << 48) | spread16(q[0]) | (spread16(q[1]) << 1) | (spread16(q[2]) << 2);
+  vals[D.offset + i] = i;
 }
 
 // one warp per tile: gather the sorted points, pad, and reduce the tile's bounding box
-__global__ void k_gather_tiles(const float4* __restrict__ porig, const int* __restrict__ order, int n, int ntiles, int ntiles_pad,
-                               float4* __restrict__ psort, float* __restrict__ tb) {
+__global__ void k_gather_tiles(const BuildDesc* __restrict__ descs, const int* __restrict__ order_all) {
+  const BuildDesc D = descs[blockIdx.y];
   int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
-  if (t >= ntiles_pad) return;
+  if (t >= D.ntiles_pad) return;
+  const int* order = order_all + D.offset;
   float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
-  if (t < ntiles) {
+  if (t < D.ntiles) {
     int s = t * TILE + lane;
     float4 v;
-    if (s < n) {
+    if (s < D.n) {
       int o = order[s];
-      v = porig[o];
+      v = D.porig[o];
       v.w = __int_as_float(o);
       mn[0] = mx[0] = v.x; mn[1] = mx[1] = v.y; mn[2] = mx[2] = v.z;
     } else {
       v = make_float4(PAD_COORD, PAD_COORD, PAD_COORD, __int_as_float(PAD_IDX));
     }
-    psort[s] = v;
+    D.psort[s] = v;
   }
 #pragma unroll
   for (int a = 0; a < 3; a++) {
@@ -122,15 +139,42 @@ __global__ void k_gather_tiles(const float4* __restrict__ porig, const int* __re
     mx[a] = warp_max(mx[a]);
   }
   if (lane == 0) {
-    bool real = t < ntiles;
+    bool real = t < D.ntiles;
 #pragma unroll
     for (int a = 0; a < 3; a++) {
-      tb[(size_t)a * ntiles_pad + t] = real ? mn[a] : PAD_COORD;
-      tb[(size_t)(3 + a) * ntiles_pad + t] = real ? mx[a] : PAD_COORD;
+      D.tb[(size_t)a * D.ntiles_pad + t] = real ? mn[a] : PAD_COORD;
+      D.tb[(size_t)(3 + a) * D.ntiles_pad + t] = real ? mx[a] : PAD_COORD;
     }
   }
 }
 
+// one warp per super tile: box of its (real) tiles
+__global__ void k_super_boxes(const BuildDesc* __restrict__ descs) {
+  const BuildDesc D = descs[blockIdx.y];
+  int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (s >= D.nsuper_pad) return;
+  int t = s * 32 + lane;
+  bool real = t < D.ntiles;
+  float mn[3], mx[3];
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+    mn[a] = warp_min(real ? D.tb[(size_t)a * D.ntiles_pad + t] : FLT_MAX);
+    mx[a] = warp_max(real ? D.tb[(size_t)(3 + a) * D.ntiles_pad + t] : -FLT_MAX);
+  }
+  bool any = __any_sync(FULL, real);
+  if (lane == 0) {
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      D.sb[(size_t)a * D.nsuper_pad + s] = any ? mn[a] : PAD_COORD;
+      D.sb[(size_t)(3 + a) * D.nsuper_pad + s] = any ? mx[a] : PAD_COORD;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// shared search pieces
+// ---------------------------------------------------------------------------------------------
 // ---------------------------------------------------------------------------------------------
 // shared search pieces
 // ---------------------------------------------------------------------------------------------

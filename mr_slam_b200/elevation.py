@@ -81,6 +81,12 @@ class ElevationMap:
                                                       C.byref(nf) if want_count else None))
         return nf.value if want_count else None
 
+    def fused_total(self, reset=True):
+        """cell fuses accumulated on the device by process_fuse_device(..., want_count=False) calls"""
+        t = C.c_longlong()
+        check(self._L.mrslam_elev_fused_total(self._h, int(bool(reset)), C.byref(t)))
+        return t.value
+
     def Mapvar_update(self, length, var_update):
         check(self._L.mrslam_elev_mapvar_update(self._h, int(length), float(var_update)))
 
