@@ -339,7 +339,7 @@ __device__ __forceinline__ u64 warp_sort_keys(u64 key, int lane) {
 }
 
 // grid = (ceil(ntiles/4), n_clouds), block = 128; one warp per query tile, queries served one by one
-__global__ void __launch_bounds__(128) k_knn_search(const KnnParams* __restrict__ plist) {
+__global__ void __launch_bounds__(128, 8) k_knn_search(const KnnParams* __restrict__ plist) {
   const KnnParams P = plist[blockIdx.y];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int qt = blockIdx.x * 4 + wib;

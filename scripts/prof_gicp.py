@@ -24,3 +24,13 @@ for rep in range(reps):
     print(f"   knn pair evals/query {L.mrslam_gicp_stats_get(0)/(B*2*120000):.0f}, nn1 pair evals/query/pass {L.mrslam_gicp_stats_get(1)/(B*nl*120000):.0f} ({nl} passes), knn insert rounds/query {L.mrslam_gicp_stats_get(2)/(B*2*120000):.1f}")
     print(f"rep {rep}: batch {B}: {dt*1e3:.2f} ms, {B/dt:.1f} aligns/s, pair evals {pairs:.3e} ({pairs/B/ (2*120000):.0f} per query-pass avg over passes), err {synth.pose_error(Ts[0], Tgt)}")
     L.mrslam_gicp_stats_enable(0)
+    _lib.prof_enable(True)
+    regs2 = []
+    for i in range(B):
+        g = pygicp.FastGICP(); g.set_correspondence_randomness(15); g.set_max_correspondence_distance(100.0)
+        g.set_maximum_iterations(50); g.set_transformation_epsilon(1e-3)
+        g.set_input_source(src); g.set_input_target(tgt)
+        regs2.append(g)
+    pygicp.align_batch(regs2, np.stack([Tg] * B))
+    pr = _lib.prof_get(); _lib.prof_enable(False)
+    print("   per-kernel ms:", {k: round(v[0], 3) for k, v in pr.items() if v[1]}, " => knn us/cloud %.1f, nn1 us/pair-pass %.1f" % (1e3 * pr["knn_search"][0] / (2 * B), 1e3 * pr["nn1_search"][0] / (B * nl)))
