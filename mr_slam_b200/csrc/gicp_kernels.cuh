@@ -322,6 +322,7 @@ __device__ __forceinline__ float key_dist(u64 k) { return __uint_as_float((unsig
 __device__ __forceinline__ int key_idx(u64 k) { return (int)(unsigned)(k & 0xffffffffull); }
 constexpr u64 KEY_NONE = ((u64)0x7f800000u << 32) | 0x7fffffffu;  // (+inf, PAD_IDX)
 constexpr int PF = 4;  // candidate tiles fetched ahead of their (serial) processing
+constexpr int CAND = 64;  // candidate tiles a warp collects for its shared nearest-first walk (2 per lane)
 
 // ascending bitonic sort of one key per lane
 __device__ __forceinline__ u64 warp_sort_keys(u64 key, int lane) {
@@ -562,8 +563,147 @@ struct PairParams {
 
 enum { MODE_LINEARIZE = 0, MODE_FITNESS = 1 };
 
+// squared distance between two boxes (a: query-warp box, b: box t of an SoA table)
+__device__ __forceinline__ float box_box_dist2(const float a[6], const float* __restrict__ b, int stride, int t) {
+  float gx = fmaxf(0.0f, fmaxf(b[t] - a[3], a[0] - b[3 * stride + t]));
+  float gy = fmaxf(0.0f, fmaxf(b[stride + t] - a[4], a[1] - b[4 * stride + t]));
+  float gz = fmaxf(0.0f, fmaxf(b[2 * stride + t] - a[5], a[2] - b[5 * stride + t]));
+  return gx * gx + gy * gy + gz * gz;
+}
+
+__device__ __forceinline__ unsigned warp_sort_u32(unsigned key, int lane) {
+#pragma unroll
+  for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      const unsigned other = __shfl_xor_sync(FULL, key, stride);
+      const bool take_min = ((lane & size) == 0) == ((lane & stride) == 0);
+      key = take_min ? min(key, other) : max(key, other);
+    }
+  }
+  return key;
+}
+
+// Warp-cooperative exact NN-1 of ONE query (all lanes hold the same query); the 32 lanes evaluate the 32 points of a
+// candidate tile in parallel.  (key0,pos0) is a known candidate (seed) or (KEY_NONE,-1).  Returns the best (key,pos).
+__device__ __forceinline__ void warp_query_nn1(const PairParams& P, float qx, float qy, float qz, u64 key0, int pos0, int seed_tile,
+                                               float cap, int lane, unsigned long long& tiles_done, u64& out_key, int& out_pos) {
+  const int ntp = P.tgt_ntiles_pad, nsp = P.tgt_nsuper_pad;
+  u64 bkey = lane == 0 ? key0 : KEY_NONE;
+  int bp = lane == 0 ? pos0 : -1;
+  float rad = fminf(key_dist(key0), cap);
+
+  auto eval_tile = [&](const float4 c, int t) {
+    const float d = dist2(qx, qy, qz, c.x, c.y, c.z);
+    const u64 ckey = make_key(d, __float_as_int(c.w));
+    if (ckey < bkey) {
+      bkey = ckey;
+      bp = t * TILE + lane;
+    }
+    rad = fminf(rad, __uint_as_float(__reduce_min_sync(FULL, __float_as_uint(d))));
+    tiles_done++;
+  };
+
+  if (seed_tile >= 0) {
+    eval_tile(P.tgt_sort[(size_t)seed_tile * TILE + lane], seed_tile);  // e.g. the tile of the previous query's NN
+    rad = fminf(rad, cap);
+  } else if (pos0 < 0) {
+    // no candidate at all: start with the tile whose box is closest to the query
+    float mb = INFINITY;
+    int ms = 0;
+    for (int s0 = lane; s0 < P.tgt_nsuper; s0 += 32) {
+      const float b = pt_box_dist2(qx, qy, qz, P.tgt_sb, nsp, s0);
+      if (b < mb) {
+        mb = b;
+        ms = s0;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(FULL, mb, o);
+      const int os = __shfl_xor_sync(FULL, ms, o);
+      if (ob < mb || (ob == mb && os < ms)) {
+        mb = ob;
+        ms = os;
+      }
+    }
+    int mt = ms * 32 + lane;
+    float tbd = (mt < P.tgt_ntiles) ? pt_box_dist2(qx, qy, qz, P.tgt_tb, ntp, mt) : INFINITY;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(FULL, tbd, o);
+      const int ot = __shfl_xor_sync(FULL, mt, o);
+      if (ob < tbd || (ob == tbd && ot < mt)) {
+        tbd = ob;
+        mt = ot;
+      }
+    }
+    eval_tile(P.tgt_sort[(size_t)mt * TILE + lane], mt);
+    rad = fminf(rad, cap);
+  }
+#pragma unroll 1
+  for (int g0 = 0; g0 < nsp; g0 += 32 * SGROUP) {
+    float b1[SGROUP];
+#pragma unroll
+    for (int u = 0; u < SGROUP; u++) {
+      const int s1 = g0 + u * 32 + lane;
+      b1[u] = (s1 < P.tgt_nsuper) ? pt_box_dist2(qx, qy, qz, P.tgt_sb, nsp, s1) : INFINITY;
+    }
+#pragma unroll
+    for (int u = 0; u < SGROUP; u++) {
+      unsigned ms = __ballot_sync(FULL, b1[u] * CULL_SAFETY <= rad);
+      while (ms) {
+        const int js = __ffs(ms) - 1;
+        ms &= ms - 1;
+        if (__shfl_sync(FULL, b1[u], js) * CULL_SAFETY > rad) continue;
+        const int sidx = g0 + u * 32 + js;
+        const int t = sidx * 32 + lane;
+        const float bt = pt_box_dist2(qx, qy, qz, P.tgt_tb, ntp, t);
+        unsigned mt = __ballot_sync(FULL, t < P.tgt_ntiles && bt * CULL_SAFETY <= rad);
+        while (mt) {
+          float4 cc[PF];
+          float bb[PF];
+          int tt[PF];
+#pragma unroll
+          for (int f = 0; f < PF; f++) {
+            bb[f] = INFINITY;
+            tt[f] = 0;
+            if (mt) {
+              const int jt = __ffs(mt) - 1;
+              mt &= mt - 1;
+              bb[f] = __shfl_sync(FULL, bt, jt);
+              tt[f] = sidx * 32 + jt;
+              cc[f] = P.tgt_sort[(size_t)tt[f] * TILE + lane];
+            }
+          }
+#pragma unroll
+          for (int f = 0; f < PF; f++)
+            if (bb[f] * CULL_SAFETY <= rad) eval_tile(cc[f], tt[f]);
+        }
+      }
+    }
+  }
+  // warp arg-min of the per-lane bests (key order == (distance, index) order)
+  const unsigned hi = (unsigned)(bkey >> 32), lo = (unsigned)(bkey & 0xffffffffull);
+  const unsigned mhi = __reduce_min_sync(FULL, hi);
+  const unsigned mlo = __reduce_min_sync(FULL, hi == mhi ? lo : 0xffffffffu);
+  const int win = __ffs(__ballot_sync(FULL, hi == mhi && lo == mlo)) - 1;
+  out_pos = __shfl_sync(FULL, bp, win);
+  out_key = ((u64)mhi << 32) | mlo;
+}
+
 // grid = (ceil(src_ntiles/4), n_active), block = 128.  MODE_LINEARIZE: writes nnpos/sqd.
 // MODE_FITNESS: per-block partial (sum of d <= max_range, count) into partials[.. + 0/1].
+//
+// Hybrid exact search per warp (= 32 spatially coherent source points):
+//  phase A  (seeded passes) every lane takes its seed = NN of the previous iteration.  Lanes whose seed distance is within
+//           4x (squared) of the warp's 24th smallest are "coherent": they share ONE candidate-tile walk.  Tiles whose box
+//           is within R0 = max coherent best of the warp's bounding box are collected (<= 64), visited NEAREST FIRST,
+//           staged in shared memory, and each lane scans the 32 points for its own query (lane-per-query brute force,
+//           ~9 instructions per pair, no warp reductions inside).  The walk stops when the nearest remaining tile is
+//           farther than every coherent best; a lane is final unless the list overflowed below its best.
+//  phase B  all other lanes (isolated points, overflow leftovers, and every lane in the unseeded first pass) run the
+//           warp-cooperative single-query search, so one far outlier cannot inflate the walk of the other 31 queries.
 template <int MODE>
 __global__ void __launch_bounds__(128) k_nn1_search(const PairParams* __restrict__ plist, const int* __restrict__ active,
                                                     const double* __restrict__ Tbuf, double max_range,
@@ -571,161 +711,168 @@ __global__ void __launch_bounds__(128) k_nn1_search(const PairParams* __restrict
   const int pid = active[blockIdx.y];
   const PairParams P = plist[pid];
   __shared__ double s_red[4][2];
+  __shared__ float4 s_tile[4][TILE];
+  __shared__ u64 s_cand[4][CAND];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int qt = blockIdx.x * 4 + wib;
   if (blockIdx.x * 4 >= P.src_ntiles) return;  // block-uniform
   const bool wvalid = qt < P.src_ntiles;
   const double* Td = Tbuf + (size_t)pid * 12;
-  float res_d = INFINITY;  // result of this lane's own query
+  float res_d = INFINITY;
   int res_pos = -1;
   bool qvalid = false;
-  if (wvalid) {
+  if (wvalid && P.tgt_ntiles > 0) {
     float Tf[12];
 #pragma unroll
     for (int i = 0; i < 12; i++) Tf[i] = (float)Td[i];
     const size_t s = (size_t)qt * TILE + lane;
     const float4 p = P.src_sort[s];
     qvalid = __float_as_int(p.w) != PAD_IDX;
-    const float qxm = xform_row(Tf + 0, p.x, p.y, p.z);
-    const float qym = xform_row(Tf + 4, p.x, p.y, p.z);
-    const float qzm = xform_row(Tf + 8, p.x, p.y, p.z);
-    const int seed_mine = P.use_seed ? P.nnpos[s] : -1;
+    const float qx = xform_row(Tf + 0, p.x, p.y, p.z);
+    const float qy = xform_row(Tf + 4, p.x, p.y, p.z);
+    const float qz = xform_row(Tf + 8, p.x, p.y, p.z);
     const int ntp = P.tgt_ntiles_pad, nsp = P.tgt_nsuper_pad;
     const float cap = (MODE == MODE_LINEARIZE) ? (float)fmin(P.thr2, (double)FLT_MAX) : (float)fmin(max_range, (double)FLT_MAX);
     unsigned long long tiles_done = 0;
-    int prev_pos = -1;  // NN of the previous query of this tile: the seed when no stored seed exists
+    u64 bkey = KEY_NONE;
+    int bp = -1;
 
-#pragma unroll 1
-    for (int qi = 0; qi < TILE; qi++) {
-      if (!__shfl_sync(FULL, (int)qvalid, qi)) continue;
-      const float qx = __shfl_sync(FULL, qxm, qi), qy = __shfl_sync(FULL, qym, qi), qz = __shfl_sync(FULL, qzm, qi);
-      // per-lane best over the candidates this lane evaluated; rad = warp-uniform best distance so far
-      u64 bkey = KEY_NONE;
-      int bp = -1;
-      float rad = INFINITY;
-
-      auto eval_tile = [&](const float4 c, int t) {
-        const float d = dist2(qx, qy, qz, c.x, c.y, c.z);
-        const u64 ckey = make_key(d, __float_as_int(c.w));
-        if (ckey < bkey) {
-          bkey = ckey;
-          bp = t * TILE + lane;
-        }
-        rad = fminf(rad, __uint_as_float(__reduce_min_sync(FULL, __float_as_uint(d))));
-        tiles_done++;
-      };
-
-      if (P.tgt_ntiles > 0) {
-        int sp = __shfl_sync(FULL, seed_mine, qi);
-        if (sp < 0) sp = prev_pos;
-        // loads that do not depend on each other go out together: seed tile + super-tile boxes
-        float4 cseed = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (sp >= 0) cseed = P.tgt_sort[(size_t)(sp >> 5) * TILE + lane];
-        float b1[SGROUP];
-#pragma unroll
-        for (int u = 0; u < SGROUP; u++) {
-          const int s1 = u * 32 + lane;
-          b1[u] = (s1 < P.tgt_nsuper) ? pt_box_dist2(qx, qy, qz, P.tgt_sb, nsp, s1) : INFINITY;
-        }
-        int seed_tile = -1;
-        if (sp >= 0) {
-          seed_tile = sp >> 5;
-          eval_tile(cseed, seed_tile);  // the whole tile of the seed: 32 candidates for one coalesced load
-        } else {
-          // no seed at all (first query of a tile in the first iteration): start with the closest box
-          float mb = INFINITY;
-          int ms = 0;
-          for (int s0 = lane; s0 < P.tgt_nsuper; s0 += 32) {
-            const float b = pt_box_dist2(qx, qy, qz, P.tgt_sb, nsp, s0);
-            if (b < mb) {
-              mb = b;
-              ms = s0;
-            }
-          }
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            const float ob = __shfl_xor_sync(FULL, mb, o);
-            const int os = __shfl_xor_sync(FULL, ms, o);
-            if (ob < mb || (ob == mb && os < ms)) {
-              mb = ob;
-              ms = os;
-            }
-          }
-          int mt = ms * 32 + lane;
-          float tbd = (mt < P.tgt_ntiles) ? pt_box_dist2(qx, qy, qz, P.tgt_tb, ntp, mt) : INFINITY;
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            const float ob = __shfl_xor_sync(FULL, tbd, o);
-            const int ot = __shfl_xor_sync(FULL, mt, o);
-            if (ob < tbd || (ob == tbd && ot < mt)) {
-              tbd = ob;
-              mt = ot;
-            }
-          }
-          seed_tile = mt;
-          eval_tile(P.tgt_sort[(size_t)mt * TILE + lane], mt);
-        }
-        rad = fminf(rad, cap);
-#pragma unroll 1
-        for (int g0 = 0; g0 < nsp; g0 += 32 * SGROUP) {
-          if (g0 > 0) {
-#pragma unroll
-            for (int u = 0; u < SGROUP; u++) {
-              const int s1 = g0 + u * 32 + lane;
-              b1[u] = (s1 < P.tgt_nsuper) ? pt_box_dist2(qx, qy, qz, P.tgt_sb, nsp, s1) : INFINITY;
-            }
-          }
-#pragma unroll
-          for (int u = 0; u < SGROUP; u++) {
-            unsigned ms = __ballot_sync(FULL, b1[u] * CULL_SAFETY <= rad);
-            while (ms) {
-              const int js = __ffs(ms) - 1;
-              ms &= ms - 1;
-              if (__shfl_sync(FULL, b1[u], js) * CULL_SAFETY > rad) continue;
-              const int sidx = g0 + u * 32 + js;
-              const int t = sidx * 32 + lane;
-              const float bt = pt_box_dist2(qx, qy, qz, P.tgt_tb, ntp, t);
-              unsigned mt = __ballot_sync(FULL, t < P.tgt_ntiles && t != seed_tile && bt * CULL_SAFETY <= rad);
-              while (mt) {
-                float4 cc[PF];
-                float bb[PF];
-                int tt[PF];
-#pragma unroll
-                for (int f = 0; f < PF; f++) {  // fetch up to PF passing tiles, then evaluate them in order
-                  bb[f] = INFINITY;
-                  tt[f] = 0;
-                  if (mt) {
-                    const int jt = __ffs(mt) - 1;
-                    mt &= mt - 1;
-                    bb[f] = __shfl_sync(FULL, bt, jt);
-                    tt[f] = sidx * 32 + jt;
-                    cc[f] = P.tgt_sort[(size_t)tt[f] * TILE + lane];
-                  }
-                }
-#pragma unroll
-                for (int f = 0; f < PF; f++)
-                  if (bb[f] * CULL_SAFETY <= rad) eval_tile(cc[f], tt[f]);
-              }
-            }
+    // lane-per-query scan of one target tile (staged in shared memory)
+    auto scan_tile = [&](int t) {
+      const float4 c = P.tgt_sort[(size_t)t * TILE + lane];
+      __syncwarp();
+      s_tile[wib][lane] = c;
+      __syncwarp();
+      float bd = key_dist(bkey);
+#pragma unroll 8
+      for (int j = 0; j < TILE; j++) {
+        const float4 c4 = s_tile[wib][j];
+        const float d = dist2(qx, qy, qz, c4.x, c4.y, c4.z);
+        if (d <= bd) {
+          const u64 ckey = make_key(d, __float_as_int(c4.w));
+          if (ckey < bkey) {
+            bkey = ckey;
+            bp = t * TILE + j;
+            bd = d;
           }
         }
       }
-      // warp arg-min of the per-lane bests (key order == (distance, index) order)
-      const unsigned hi = (unsigned)(bkey >> 32), lo = (unsigned)(bkey & 0xffffffffull);
-      const unsigned mhi = __reduce_min_sync(FULL, hi);
-      const unsigned mlo = __reduce_min_sync(FULL, hi == mhi ? lo : 0xffffffffu);
-      const int win = __ffs(__ballot_sync(FULL, hi == mhi && lo == mlo)) - 1;
-      const int wpos = __shfl_sync(FULL, bp, win);
-      prev_pos = wpos;
-      if (lane == qi) {
-        res_d = __uint_as_float(mhi);
-        res_pos = wpos;
+      tiles_done++;
+    };
+
+    // ---- phase A: seeds ----
+    const int sp = P.use_seed ? P.nnpos[s] : -1;
+    if (qvalid && sp >= 0) {
+      const float4 c = P.tgt_sort[sp];
+      bkey = make_key(dist2(qx, qy, qz, c.x, c.y, c.z), __float_as_int(c.w));
+      bp = sp;
+    }
+    const unsigned vmask = __ballot_sync(FULL, qvalid);
+    unsigned cmask = 0;
+    if (P.use_seed) {
+      // coherent set: best within 4x of the warp's 24th smallest (squared distances)
+      const unsigned mybits = (qvalid && sp >= 0) ? __float_as_uint(key_dist(bkey)) : 0xffffffffu;
+      const unsigned sorted = warp_sort_u32(mybits, lane);
+      const float d24 = __uint_as_float(__shfl_sync(FULL, sorted, 23));
+      const float thr = fmaxf(4.0f * d24, 1e-6f);
+      bool coherent = qvalid && sp >= 0 && key_dist(bkey) <= thr;
+      cmask = __ballot_sync(FULL, coherent);
+      if (cmask) {
+        float wb[6];  // bounding box of the coherent queries
+        wb[0] = ord2f(__reduce_min_sync(FULL, coherent ? f2ord(qx) : 0xffffffffu));
+        wb[1] = ord2f(__reduce_min_sync(FULL, coherent ? f2ord(qy) : 0xffffffffu));
+        wb[2] = ord2f(__reduce_min_sync(FULL, coherent ? f2ord(qz) : 0xffffffffu));
+        wb[3] = ord2f(__reduce_max_sync(FULL, coherent ? f2ord(qx) : 0u));
+        wb[4] = ord2f(__reduce_max_sync(FULL, coherent ? f2ord(qy) : 0u));
+        wb[5] = ord2f(__reduce_max_sync(FULL, coherent ? f2ord(qz) : 0u));
+        const float R0 = fminf(__uint_as_float(__reduce_max_sync(FULL, coherent ? __float_as_uint(key_dist(bkey)) : 0u)), cap);
+        // collect the candidate tiles (box within R0 of the warp box), at most CAND of them
+        int cnt = 0;
+        float dropped = INFINITY;
+        const unsigned lt = (1u << lane) - 1u;
+#pragma unroll 1
+        for (int g0 = 0; g0 < nsp; g0 += 32) {
+          const int s1 = g0 + lane;
+          const float b1 = (s1 < P.tgt_nsuper) ? box_box_dist2(wb, P.tgt_sb, nsp, s1) : INFINITY;
+          unsigned ms = __ballot_sync(FULL, b1 * CULL_SAFETY <= R0);
+          while (ms) {
+            const int js = __ffs(ms) - 1;
+            ms &= ms - 1;
+            const int t = (g0 + js) * 32 + lane;
+            const float bt = box_box_dist2(wb, P.tgt_tb, ntp, t);
+            const bool pass = t < P.tgt_ntiles && bt * CULL_SAFETY <= R0;
+            const unsigned mt = __ballot_sync(FULL, pass);
+            if (pass) {
+              const int pos = cnt + __popc(mt & lt);
+              if (pos < CAND) s_cand[wib][pos] = ((u64)__float_as_uint(bt) << 32) | (unsigned)t;
+              else dropped = fminf(dropped, bt);
+            }
+            cnt += __popc(mt);
+          }
+        }
+        const bool overflow = cnt > CAND;
+        const float dropped_min = overflow ? warp_min(dropped) : INFINITY;
+        const int n = min(cnt, CAND);
+        __syncwarp();
+        u64 e0 = lane < n ? s_cand[wib][lane] : KEY_NONE;
+        u64 e1 = lane + 32 < n ? s_cand[wib][lane + 32] : KEY_NONE;
+        // nearest-first walk: stop as soon as the nearest remaining tile is farther than every coherent best
+        while (true) {
+          const u64 m = e0 < e1 ? e0 : e1;
+          const unsigned hi = (unsigned)(m >> 32);
+          const unsigned mhi = __reduce_min_sync(FULL, hi);
+          if (mhi >= 0x7f800000u) break;  // list exhausted
+          const unsigned mlo = __reduce_min_sync(FULL, hi == mhi ? (unsigned)(m & 0xffffffffull) : 0xffffffffu);
+          const u64 pick = ((u64)mhi << 32) | mlo;
+          if (e0 == pick) e0 = KEY_NONE;
+          else if (e1 == pick) e1 = KEY_NONE;
+          const float R = __uint_as_float(__reduce_max_sync(FULL, coherent ? __float_as_uint(key_dist(bkey)) : 0u));
+          if (__uint_as_float(mhi) * CULL_SAFETY > fminf(R, cap)) break;
+          scan_tile((int)mlo);
+        }
+        // with an overflowing candidate list some tiles at distance >= dropped_min were never looked at:
+        // coherent lanes whose best is not provably closer go to phase B
+        if (overflow) {
+          coherent = coherent && key_dist(bkey) < dropped_min * CULL_SAFETY;
+          cmask = __ballot_sync(FULL, coherent);
+        }
       }
     }
-    if (stat_pairs && lane == 0) atomicAdd(stat_pairs + 1, tiles_done * 32ull);
+    // ---- phase B: the remaining queries, one at a time (seeded with whatever is known for them) ----
+    unsigned omask = vmask & ~cmask;
+    int prev_tile = -1;
+    while (omask) {
+      const int qi = __ffs(omask) - 1;
+      omask &= omask - 1;
+      const float ox = __shfl_sync(FULL, qx, qi), oy = __shfl_sync(FULL, qy, qi), oz = __shfl_sync(FULL, qz, qi);
+      const u64 k0 = __shfl_sync(FULL, bkey, qi);
+      const int p0 = __shfl_sync(FULL, bp, qi);
+      u64 ok;
+      int op;
+      // without any candidate (first pass) the tile of the previous query's NN is the seed
+      warp_query_nn1(P, ox, oy, oz, k0, p0, p0 < 0 ? prev_tile : -1, cap, lane, tiles_done, ok, op);
+      prev_tile = op >= 0 ? (op >> 5) : -1;
+      if (lane == qi) {
+        bkey = ok;
+        bp = op;
+      }
+    }
+    res_d = key_dist(bkey);
+    res_pos = bp;
+    if (stat_pairs && lane == 0) {
+      atomicAdd(stat_pairs + 1, tiles_done * 32ull);
+      atomicMax(stat_pairs + 3, tiles_done);
+    }
     if (MODE == MODE_LINEARIZE && qvalid) {
       P.nnpos[s] = res_pos;
       P.sqd[s] = res_d;
+    }
+  } else if (wvalid && MODE == MODE_LINEARIZE) {
+    const size_t s = (size_t)qt * TILE + lane;
+    qvalid = __float_as_int(P.src_sort[s].w) != PAD_IDX;
+    if (qvalid) {  // empty target
+      P.nnpos[s] = -1;
+      P.sqd[s] = INFINITY;
     }
   }
   if (MODE == MODE_FITNESS) {
