@@ -23,7 +23,7 @@ namespace mrslam {
 struct Cloud {
   int n = 0, npad = 0, ntiles = 0, ntiles_pad = 0, nsuper = 0, nsuper_pad = 0;
   DevBuf<float4> porig, psort;
-  DevBuf<float> tb, sb;
+  DevBuf<float> tb, sb, qp;
   DevBuf<double> cov;
   DevBuf<int> knn_ids;  // [npad*k] neighbour lists (scratch between k_knn_search and k_cov)
   bool cov_valid = false;
@@ -69,7 +69,7 @@ struct Cloud {
   }
 
   void release() {
-    porig.release(); psort.release(); tb.release(); sb.release(); cov.release(); knn_ids.release(); raw.release();
+    porig.release(); psort.release(); tb.release(); sb.release(); qp.release(); cov.release(); knn_ids.release(); raw.release();
   }
 };
 
@@ -111,8 +111,9 @@ static int build_clouds(const std::vector<Cloud*>& clouds) {
     MR_CHECK(c->psort.reserve(std::max(c->npad, 1)));
     MR_CHECK(c->tb.reserve((size_t)6 * c->ntiles_pad));
     MR_CHECK(c->sb.reserve((size_t)6 * c->nsuper_pad));
+    MR_CHECK(c->qp.reserve(4));
     BuildDesc d;
-    d.porig = c->porig.p; d.psort = c->psort.p; d.tb = c->tb.p; d.sb = c->sb.p;
+    d.porig = c->porig.p; d.psort = c->psort.p; d.tb = c->tb.p; d.sb = c->sb.p; d.qp = c->qp.p;
     d.n = c->n; d.ntiles = c->ntiles; d.ntiles_pad = c->ntiles_pad; d.nsuper_pad = c->nsuper_pad;
     d.offset = total;
     S.h_desc.p[i] = d;
@@ -345,6 +346,8 @@ static PairParams make_pair_params(Gicp* g) {
   p.tgt_sort = g->tgt->psort.p;
   p.tgt_tb = g->tgt->tb.p;
   p.tgt_sb = g->tgt->sb.p;
+  p.tgt_qp = g->tgt->qp.p;
+  p.tgt_n = g->tgt->n;
   p.tgt_cov = g->tgt->cov.p;
   p.tgt_ntiles = g->tgt->ntiles;
   p.tgt_ntiles_pad = g->tgt->ntiles_pad;
