@@ -217,7 +217,10 @@ def main():
     src_host = [torch.from_numpy(p["src"]).pin_memory() for p in pairs]
     tgt_host = [torch.from_numpy(p["tgt"]).pin_memory() for p in pairs]
     soa_dev = [torch.from_numpy(np.ascontiguousarray(p["src"].T)).to(dev) for p in pairs]  # elevation inputs x,y,z SoA
-    soa_host = [np.ascontiguousarray(p["src"].T) for p in pairs]
+    soa_host = [torch.from_numpy(np.ascontiguousarray(p["src"].T)).pin_memory().numpy() for p in pairs]  # page-locked x,y,z
+    pin = lambda dt: torch.zeros(N_POINTS, dtype=dt).pin_memory().numpy()
+    elev_out = (pin(torch.int32), pin(torch.float32), pin(torch.float32), pin(torch.float32), pin(torch.float32))
+    zeros_i_pin, zeros_f_pin = pin(torch.int32), pin(torch.float32)
     elev_in = [synth.elevation_inputs(p["pose"]) for p in pairs]
 
     emap = elevation.ElevationMap()
@@ -290,13 +293,12 @@ def main():
             g.set_input_source(src_host[i].numpy())
             g.set_input_target(tgt_host[i].numpy())
         Ts = pygicp.align_batch(regs, guesses)  # reads back 32 x 4x4
-        zeros_i = np.zeros(N_POINTS, np.int32)
-        zeros_f = np.zeros(N_POINTS, np.float32)
+        zeros_i, zeros_f = zeros_i_pin, zeros_f_pin
         fused = 0
         for i in range(n_pairs):
             emap.Move(pairs[i]["pose"][:3, 3].astype(np.float32), ELEV_RES, ELEV_L)
             x, y, z = soa_host[i]
-            r = emap.Process_points(x, y, z, elev_args(i)[0], N_POINTS, *elev_args(i)[1:])
+            r = emap.Process_points(x, y, z, elev_args(i)[0], N_POINTS, *elev_args(i)[1:], out=elev_out)
             fused += emap.Fuse(ELEV_L, N_POINTS, r[0], zeros_i, zeros_i, zeros_i, zeros_f, r[4], r[1])
         with torch.cuda.stream(lib_stream):
             e1.record()

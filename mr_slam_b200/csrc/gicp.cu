@@ -130,7 +130,7 @@ static int build_clouds(const std::vector<Cloud*>& clouds) {
   const int* order = S.vals.p;
   if (total > 0) {
     k_bbox_init<<<(nc * 6 + 127) / 128, 128, 0, st>>>(S.bbox.p, nc);
-    int gx = std::max(1, std::min((max_n + 255) / 256, 148 * 2));
+    int gx = std::max(1, std::min((max_n + 255) / 256, 32));
     k_bbox<<<dim3(gx, nc), 256, 0, st>>>(S.d_desc.p, S.bbox.p);
     k_morton<<<dim3((max_n + 255) / 256, nc), 256, 0, st>>>(S.d_desc.p, S.bbox.p, S.keys.p, S.vals.p);
     count_launch(3);

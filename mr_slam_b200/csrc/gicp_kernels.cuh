@@ -56,9 +56,10 @@ __global__ void k_bbox_init(unsigned* bb, int nclouds) {
   bb[i] = (i % 6) < 3 ? 0xffffffffu : 0u;
 }
 
-__global__ void k_bbox(const BuildDesc* __restrict__ descs, unsigned* bball) {
+__global__ void __launch_bounds__(256) k_bbox(const BuildDesc* __restrict__ descs, unsigned* bball) {
   const BuildDesc D = descs[blockIdx.y];
   unsigned* bb = bball + 6 * blockIdx.y;
+  __shared__ float s_mn[8][3], s_mx[8][3];
   float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < D.n; i += gridDim.x * blockDim.x) {
     float4 v = D.porig[i];
@@ -72,12 +73,24 @@ __global__ void k_bbox(const BuildDesc* __restrict__ descs, unsigned* bball) {
     mn[a] = warp_min(mn[a]);
     mx[a] = warp_max(mx[a]);
   }
+  const int w = threadIdx.x >> 5;
   if ((threadIdx.x & 31) == 0) {
 #pragma unroll
     for (int a = 0; a < 3; a++) {
-      atomicMin(&bb[a], f2ord(mn[a]));
-      atomicMax(&bb[3 + a], f2ord(mx[a]));
+      s_mn[w][a] = mn[a];
+      s_mx[w][a] = mx[a];
     }
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {  // one atomic pair per block and axis (8x fewer than per warp: the six addresses are contended)
+    const int a = threadIdx.x;
+    float lo = s_mn[0][a], hi = s_mx[0][a];
+    for (int k = 1; k < 8; k++) {
+      lo = fminf(lo, s_mn[k][a]);
+      hi = fmaxf(hi, s_mx[k][a]);
+    }
+    atomicMin(&bb[a], f2ord(lo));
+    atomicMax(&bb[3 + a], f2ord(hi));
   }
 }
 

@@ -49,10 +49,15 @@ class ElevationMap:
         return c, s, a
 
     def Process_points(self, x, y, z, T, n, lower, upper, min_r, beam_a, beam_c, sensorJacobian, rotationVariance, C_SB_transpose,
-                       P_mul_C_BM_transpose, B_r_BS_skew):
+                       P_mul_C_BM_transpose, B_r_BS_skew, out=None):
+        """`out` (optional): caller-owned (map_index int32, var, x_ts, y_ts, z_ts float32) arrays of length n -- the reference's
+        calling convention (caller-owned output arrays); pass page-locked arrays to get DMA copies."""
         x, y, z = _f32(x), _f32(y), _f32(z)
-        mi = np.zeros(n, np.int32)
-        var, xt, yt, zt = (np.zeros(n, np.float32) for _ in range(4))
+        if out is not None:
+            mi, var, xt, yt, zt = out
+        else:
+            mi = np.zeros(n, np.int32)
+            var, xt, yt, zt = (np.zeros(n, np.float32) for _ in range(4))
         args = [_f32(T).reshape(16), _f32(sensorJacobian).reshape(3), _f32(rotationVariance).reshape(9), _f32(C_SB_transpose).reshape(9),
                 _f32(P_mul_C_BM_transpose).reshape(3), _f32(B_r_BS_skew).reshape(9)]
         check(self._L.mrslam_elev_process_points(self._h, ptr(mi), ptr(x), ptr(y), ptr(z), ptr(var), ptr(xt), ptr(yt), ptr(zt),
