@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmrslam_b200.so")
+LIB_PATH = os.environ.get("MRSLAM_LIB", os.path.join(_HERE, "libmrslam_b200.so"))  # MRSLAM_LIB: development variants only
 _LIB = None
 
 

@@ -26,7 +26,16 @@ constexpr int TILE = 32;
 constexpr int PAD_IDX = INT_MAX;
 constexpr float PAD_COORD = 3.0e18f;
 constexpr float CULL_SAFETY = 0.99999f;  // box distance is a lower bound only up to a few ulp
-constexpr int HOME_RADIUS = 2;           // tiles qt-2..qt+2 are searched first (they seed the cull radius)
+#ifndef MR_HOME_RADIUS
+#define MR_HOME_RADIUS 1
+#endif
+#ifndef MR_PF
+#define MR_PF 2
+#endif
+#ifndef MR_SGROUP
+#define MR_SGROUP 2
+#endif
+constexpr int HOME_RADIUS = MR_HOME_RADIUS;  // tiles qt-R..qt+R are searched first (they seed the cull radius)
 constexpr int NRED = 28;                 // 21 (H upper) + 6 (b) + 1 (cost)
 
 // ---------------------------------------------------------------------------------------------
@@ -231,6 +240,27 @@ __device__ __forceinline__ float pt_box_dist2(float x, float y, float z, const f
   return gx * gx + gy * gy + gz * gz;
 }
 
+// squared distance between two boxes (a: query-warp box, b: box t of an SoA table)
+__device__ __forceinline__ float box_box_dist2(const float a[6], const float* __restrict__ b, int stride, int t) {
+  float gx = fmaxf(0.0f, fmaxf(b[t] - a[3], a[0] - b[3 * stride + t]));
+  float gy = fmaxf(0.0f, fmaxf(b[stride + t] - a[4], a[1] - b[4 * stride + t]));
+  float gz = fmaxf(0.0f, fmaxf(b[2 * stride + t] - a[5], a[2] - b[5 * stride + t]));
+  return gx * gx + gy * gy + gz * gz;
+}
+
+__device__ __forceinline__ unsigned warp_sort_u32(unsigned key, int lane) {
+#pragma unroll
+  for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      const unsigned other = __shfl_xor_sync(FULL, key, stride);
+      const bool take_min = ((lane & size) == 0) == ((lane & stride) == 0);
+      key = take_min ? min(key, other) : max(key, other);
+    }
+  }
+  return key;
+}
+
 // symmetric 3x3 eigen-decomposition, cyclic Jacobi (double); eigenvalues descending; same operation
 // order as the oracle's sym_eig3 so that covariances agree bit for bit.
 __device__ __forceinline__ void sym_eig3(const double A[9], double w[3], double V[9]) {
@@ -329,7 +359,7 @@ struct KnnParams {
   unsigned long long* stat_pairs;  // optional: number of (query,candidate) distance evaluations
 };
 
-constexpr int SGROUP = 4;  // super-tile box tests kept in flight together (4 x 32 boxes)
+constexpr int SGROUP = MR_SGROUP;  // super-tile box tests kept in flight together (SGROUP x 32 boxes)
 
 // (distance, index) packed into one 64-bit key: distances are >= +0, so their bit patterns order like
 // unsigned integers and key order == lexicographic (distance, index) order.
@@ -338,7 +368,7 @@ __device__ __forceinline__ u64 make_key(float d, int idx) { return ((u64)__float
 __device__ __forceinline__ float key_dist(u64 k) { return __uint_as_float((unsigned)(k >> 32)); }
 __device__ __forceinline__ int key_idx(u64 k) { return (int)(unsigned)(k & 0xffffffffull); }
 constexpr u64 KEY_NONE = ((u64)0x7f800000u << 32) | 0x7fffffffu;  // (+inf, PAD_IDX)
-constexpr int PF = 4;  // candidate tiles fetched ahead of their (serial) processing
+constexpr int PF = MR_PF;  // candidate tiles fetched ahead of their (serial) processing
 constexpr int CAND = 64;  // candidate tiles a warp collects for its shared nearest-first walk (2 per lane)
 
 // ascending bitonic sort of one key per lane
@@ -356,126 +386,130 @@ __device__ __forceinline__ u64 warp_sort_keys(u64 key, int lane) {
   return key;
 }
 
-// grid = (ceil(ntiles/4), n_clouds), block = 128; one warp per query tile, queries served one by one
+// Warp-cooperative exact kNN of ONE query (all lanes hold the same query): the k-best list lives one key per lane.
+// Returns this lane's entry of the sorted list (lane j = j-th neighbour).
+__device__ __forceinline__ u64 warp_query_knn(const KnnParams& P, float qx, float qy, float qz, int qt, int k, int lane,
+                                              unsigned long long& tiles_done, unsigned long long& inserts) {
+  const int ntp = P.ntiles_pad, nsp = P.nsuper_pad;
+  // super-tile box tests do not depend on the list: issue their loads first
+  float b1[SGROUP];
+#pragma unroll
+  for (int u = 0; u < SGROUP; u++) {
+    const int s1 = u * 32 + lane;
+    b1[u] = (s1 < P.nsuper) ? pt_box_dist2(qx, qy, qz, P.sb, nsp, s1) : INFINITY;
+  }
+  u64 my_key;
+  u64 wkey;
+  {  // own tile: all 32 candidates enter the (empty) list -> one bitonic sort instead of 32 insertions
+    const float4 c = P.psort[(size_t)qt * TILE + lane];
+    my_key = warp_sort_keys(make_key(dist2(qx, qy, qz, c.x, c.y, c.z), __float_as_int(c.w)), lane);
+    wkey = __shfl_sync(FULL, my_key, k - 1);
+    tiles_done++;
+  }
+  auto merge_tile = [&](const float4 c) {
+    const u64 ckey = make_key(dist2(qx, qy, qz, c.x, c.y, c.z), __float_as_int(c.w));
+    unsigned m = __ballot_sync(FULL, ckey < wkey);
+    if (m) {
+      // A candidate that no longer beats the (tightened) k-th entry only touches lanes >= k, which are
+      // never read -- so no re-check and no refresh of wkey inside the loop.
+      while (m) {
+        const int j = __ffs(m) - 1;
+        m &= m - 1;
+        const u64 ck = __shfl_sync(FULL, ckey, j);
+        const u64 up = __shfl_up_sync(FULL, my_key, 1);
+        if (ck < my_key) my_key = (lane > 0 && ck < up) ? up : ck;
+        inserts++;
+      }
+      wkey = __shfl_sync(FULL, my_key, k - 1);
+    }
+    tiles_done++;
+  };
+#pragma unroll 1
+  for (int o = 1; o <= HOME_RADIUS; o++) {
+    if (qt - o >= 0) merge_tile(P.psort[(size_t)(qt - o) * TILE + lane]);
+    if (qt + o < P.ntiles) merge_tile(P.psort[(size_t)(qt + o) * TILE + lane]);
+  }
+#pragma unroll 1
+  for (int g0 = 0; g0 < nsp; g0 += 32 * SGROUP) {
+    if (g0 > 0) {
+#pragma unroll
+      for (int u = 0; u < SGROUP; u++) {
+        const int s1 = g0 + u * 32 + lane;
+        b1[u] = (s1 < P.nsuper) ? pt_box_dist2(qx, qy, qz, P.sb, nsp, s1) : INFINITY;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < SGROUP; u++) {
+      unsigned ms = __ballot_sync(FULL, b1[u] * CULL_SAFETY <= key_dist(wkey));
+      while (ms) {
+        const int js = __ffs(ms) - 1;
+        ms &= ms - 1;
+        if (__shfl_sync(FULL, b1[u], js) * CULL_SAFETY > key_dist(wkey)) continue;
+        const int sidx = g0 + u * 32 + js;
+        const int t = sidx * 32 + lane;
+        const float bt = pt_box_dist2(qx, qy, qz, P.tb, ntp, t);
+        const int dt = t - qt;
+        unsigned mt = __ballot_sync(FULL, t < P.ntiles && (dt > HOME_RADIUS || dt < -HOME_RADIUS) && bt * CULL_SAFETY <= key_dist(wkey));
+        while (mt) {
+          float4 cc[PF];
+          float bb[PF];
+#pragma unroll
+          for (int f = 0; f < PF; f++) {  // fetch up to PF passing tiles before touching the list
+            bb[f] = INFINITY;
+            if (mt) {
+              const int jt = __ffs(mt) - 1;
+              mt &= mt - 1;
+              bb[f] = __shfl_sync(FULL, bt, jt);
+              cc[f] = P.psort[(size_t)(sidx * 32 + jt) * TILE + lane];
+            }
+          }
+#pragma unroll
+          for (int f = 0; f < PF; f++)
+            if (bb[f] * CULL_SAFETY <= key_dist(wkey)) merge_tile(cc[f]);
+        }
+      }
+    }
+  }
+  return my_key;
+}
+
+__device__ __forceinline__ void knn_write_warp_list(const KnnParams& P, u64 my_key, size_t spos, int qidx, int k, int lane) {
+  if (lane < k) {
+    const int my_i = key_idx(my_key);
+    P.ids[spos * k + lane] = my_i;
+    if (P.knn_idx) {
+      const bool real = my_i != PAD_IDX;
+      P.knn_idx[(size_t)qidx * k + lane] = real ? my_i : -1;
+      if (P.knn_sqd) P.knn_sqd[(size_t)qidx * k + lane] = real ? key_dist(my_key) : INFINITY;
+    }
+  }
+}
+
+// one warp per query tile, queries served one by one by warp_query_knn
 __global__ void __launch_bounds__(128, 8) k_knn_search(const KnnParams* __restrict__ plist) {
   const KnnParams P = plist[blockIdx.y];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int qt = blockIdx.x * 4 + wib;
   if (qt >= P.ntiles) return;  // warp-uniform; no block-level barrier in this kernel
   const float4 qmine = P.psort[(size_t)qt * TILE + lane];
-  const int k = P.k;
-  const int ntp = P.ntiles_pad, nsp = P.nsuper_pad;
   unsigned long long tiles_done = 0, inserts = 0;
-  // the home tiles are the same for every query of this warp: keep them in registers
-  float4 home[2 * HOME_RADIUS + 1];
-#pragma unroll
-  for (int o = 0; o < 2 * HOME_RADIUS + 1; o++) {
-    const int t = qt + o - HOME_RADIUS;
-    home[o] = (t >= 0 && t < P.ntiles) ? P.psort[(size_t)t * TILE + lane]
-                                       : make_float4(PAD_COORD, PAD_COORD, PAD_COORD, __int_as_float(PAD_IDX));
-  }
-
 #pragma unroll 1
   for (int qi = 0; qi < TILE; qi++) {
     const float qx = __shfl_sync(FULL, qmine.x, qi), qy = __shfl_sync(FULL, qmine.y, qi), qz = __shfl_sync(FULL, qmine.z, qi);
     const int qidx = __shfl_sync(FULL, __float_as_int(qmine.w), qi);
     if (qidx == PAD_IDX) continue;
-    // super-tile box tests do not depend on the list: issue their loads first
-    float b1[SGROUP];
-#pragma unroll
-    for (int u = 0; u < SGROUP; u++) {
-      const int s1 = u * 32 + lane;
-      b1[u] = (s1 < P.nsuper) ? pt_box_dist2(qx, qy, qz, P.sb, nsp, s1) : INFINITY;
-    }
-    // k-best list, one key per lane, ascending; wkey = current k-th entry
-    u64 my_key;
-    u64 wkey;
-    {  // own tile: all 32 candidates enter the (empty) list -> one bitonic sort instead of 32 insertions
-      const float4 c = home[HOME_RADIUS];
-      my_key = warp_sort_keys(make_key(dist2(qx, qy, qz, c.x, c.y, c.z), __float_as_int(c.w)), lane);
-      wkey = __shfl_sync(FULL, my_key, k - 1);
-      tiles_done++;
-    }
-    auto merge_tile = [&](const float4 c) {
-      const u64 ckey = make_key(dist2(qx, qy, qz, c.x, c.y, c.z), __float_as_int(c.w));
-      unsigned m = __ballot_sync(FULL, ckey < wkey);
-      if (m) {
-        // A candidate that no longer beats the (tightened) k-th entry only touches lanes >= k, which are
-        // never read -- so no re-check and no refresh of wkey inside the loop.
-        while (m) {
-          const int j = __ffs(m) - 1;
-          m &= m - 1;
-          const u64 ck = __shfl_sync(FULL, ckey, j);
-          const u64 up = __shfl_up_sync(FULL, my_key, 1);
-          if (ck < my_key) my_key = (lane > 0 && ck < up) ? up : ck;
-          inserts++;
-        }
-        wkey = __shfl_sync(FULL, my_key, k - 1);
-      }
-      tiles_done++;
-    };
-#pragma unroll
-    for (int o = 1; o <= HOME_RADIUS; o++) {
-      if (qt - o >= 0) merge_tile(home[HOME_RADIUS - o]);
-      if (qt + o < P.ntiles) merge_tile(home[HOME_RADIUS + o]);
-    }
-
-#pragma unroll 1
-    for (int g0 = 0; g0 < nsp; g0 += 32 * SGROUP) {
-      if (g0 > 0) {
-#pragma unroll
-        for (int u = 0; u < SGROUP; u++) {
-          const int s1 = g0 + u * 32 + lane;
-          b1[u] = (s1 < P.nsuper) ? pt_box_dist2(qx, qy, qz, P.sb, nsp, s1) : INFINITY;
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < SGROUP; u++) {
-        unsigned ms = __ballot_sync(FULL, b1[u] * CULL_SAFETY <= key_dist(wkey));
-        while (ms) {
-          const int js = __ffs(ms) - 1;
-          ms &= ms - 1;
-          if (__shfl_sync(FULL, b1[u], js) * CULL_SAFETY > key_dist(wkey)) continue;
-          const int sidx = g0 + u * 32 + js;
-          const int t = sidx * 32 + lane;
-          const float bt = pt_box_dist2(qx, qy, qz, P.tb, ntp, t);
-          const int dt = t - qt;
-          unsigned mt = __ballot_sync(FULL, t < P.ntiles && (dt > HOME_RADIUS || dt < -HOME_RADIUS) && bt * CULL_SAFETY <= key_dist(wkey));
-          while (mt) {
-            float4 cc[PF];
-            float bb[PF];
-#pragma unroll
-            for (int f = 0; f < PF; f++) {  // fetch up to PF passing tiles before touching the list
-              bb[f] = INFINITY;
-              if (mt) {
-                const int jt = __ffs(mt) - 1;
-                mt &= mt - 1;
-                bb[f] = __shfl_sync(FULL, bt, jt);
-                cc[f] = P.psort[(size_t)(sidx * 32 + jt) * TILE + lane];
-              }
-            }
-#pragma unroll
-            for (int f = 0; f < PF; f++)
-              if (bb[f] * CULL_SAFETY <= key_dist(wkey)) merge_tile(cc[f]);
-          }
-        }
-      }
-    }
-    if (lane < k) {
-      const int my_i = key_idx(my_key);
-      P.ids[((size_t)qt * TILE + qi) * k + lane] = my_i;
-      if (P.knn_idx) {
-        const bool real = my_i != PAD_IDX;
-        P.knn_idx[(size_t)qidx * k + lane] = real ? my_i : -1;
-        if (P.knn_sqd) P.knn_sqd[(size_t)qidx * k + lane] = real ? key_dist(my_key) : INFINITY;
-      }
-    }
+    const u64 my_key = warp_query_knn(P, qx, qy, qz, qt, P.k, lane, tiles_done, inserts);
+    knn_write_warp_list(P, my_key, (size_t)qt * TILE + qi, qidx, P.k, lane);
   }
   if (P.stat_pairs && lane == 0) {
     atomicAdd(P.stat_pairs, tiles_done * 32ull);
     atomicAdd(P.stat_pairs + 2, inserts);
   }
 }
+
+// (A lane-per-query variant with per-lane sorted lists in registers -- the scheme that pays off for NN-1 -- was measured
+// 5x slower here: with 32 neighbouring queries almost every scanned candidate enters SOME lane's list, so the whole warp
+// executes the O(k) register insertion for nearly every candidate.  The warp-shuffle k-min above stays the kNN kernel.)
 
 // covariance of the k neighbours (double), one thread per SORTED point; grid = (ceil(npad/128), n_clouds)
 __global__ void __launch_bounds__(128) k_cov(const KnnParams* __restrict__ plist) {
@@ -580,27 +614,6 @@ struct PairParams {
 };
 
 enum { MODE_LINEARIZE = 0, MODE_FITNESS = 1 };
-
-// squared distance between two boxes (a: query-warp box, b: box t of an SoA table)
-__device__ __forceinline__ float box_box_dist2(const float a[6], const float* __restrict__ b, int stride, int t) {
-  float gx = fmaxf(0.0f, fmaxf(b[t] - a[3], a[0] - b[3 * stride + t]));
-  float gy = fmaxf(0.0f, fmaxf(b[stride + t] - a[4], a[1] - b[4 * stride + t]));
-  float gz = fmaxf(0.0f, fmaxf(b[2 * stride + t] - a[5], a[2] - b[5 * stride + t]));
-  return gx * gx + gy * gy + gz * gz;
-}
-
-__device__ __forceinline__ unsigned warp_sort_u32(unsigned key, int lane) {
-#pragma unroll
-  for (int size = 2; size <= 32; size <<= 1) {
-#pragma unroll
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      const unsigned other = __shfl_xor_sync(FULL, key, stride);
-      const bool take_min = ((lane & size) == 0) == ((lane & stride) == 0);
-      key = take_min ? min(key, other) : max(key, other);
-    }
-  }
-  return key;
-}
 
 // Warp-cooperative exact NN-1 of ONE query (all lanes hold the same query); the 32 lanes evaluate the 32 points of a
 // candidate tile in parallel.  (key0,pos0) is a known candidate (seed) or (KEY_NONE,-1).  Returns the best (key,pos).
