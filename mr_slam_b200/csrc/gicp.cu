@@ -25,6 +25,7 @@ struct Cloud {
   int n = 0, npad = 0, ntiles = 0, ntiles_pad = 0, nsuper = 0, nsuper_pad = 0;
   DevBuf<float4> porig, psort;
   DevBuf<float> tb, sb, qp;
+  DevBuf<unsigned long long> skeys;
   DevBuf<double> cov;
   DevBuf<int> knn_ids;  // [npad*k] neighbour lists (scratch between k_knn_search and k_cov)
   bool cov_valid = false;
@@ -70,7 +71,7 @@ struct Cloud {
   }
 
   void release() {
-    porig.release(); psort.release(); tb.release(); sb.release(); qp.release(); cov.release(); knn_ids.release(); raw.release();
+    porig.release(); psort.release(); tb.release(); sb.release(); qp.release(); skeys.release(); cov.release(); knn_ids.release(); raw.release();
   }
 };
 
@@ -113,7 +114,9 @@ static int build_clouds(const std::vector<Cloud*>& clouds) {
     MR_CHECK(c->tb.reserve((size_t)6 * c->ntiles_pad));
     MR_CHECK(c->sb.reserve((size_t)6 * c->nsuper_pad));
     MR_CHECK(c->qp.reserve(4));
+    MR_CHECK(c->skeys.reserve(std::max(c->n, 1)));
     BuildDesc d;
+    d.skeys = c->skeys.p;
     d.porig = c->porig.p; d.psort = c->psort.p; d.tb = c->tb.p; d.sb = c->sb.p; d.qp = c->qp.p;
     d.n = c->n; d.ntiles = c->ntiles; d.ntiles_pad = c->ntiles_pad; d.nsuper_pad = c->nsuper_pad;
     d.offset = total;
@@ -129,6 +132,7 @@ static int build_clouds(const std::vector<Cloud*>& clouds) {
   MR_CHECK(S.vals.reserve(tot)); MR_CHECK(S.vals_alt.reserve(tot));
   MR_CHECK(S.bbox.reserve((size_t)6 * nc));
   const int* order = S.vals.p;
+  const unsigned long long* keys_sorted = S.keys.p;
   if (total > 0) {
     k_bbox_init<<<(nc * 6 + 127) / 128, 128, 0, st>>>(S.bbox.p, nc);
     int gx = std::max(1, std::min((max_n + 255) / 256, 32));
@@ -144,8 +148,9 @@ static int build_clouds(const std::vector<Cloud*>& clouds) {
     MR_CHECK(S.cubtmp.reserve(tmp));
     MR_CUDA(cub::DeviceRadixSort::SortPairs(S.cubtmp.p, tmp, dk, dv, (int)total, 0, bits, st));
     order = dv.Current();
+    keys_sorted = dk.Current();
   }
-  k_gather_tiles<<<dim3((max_tiles_pad * 32 + 127) / 128, nc), 128, 0, st>>>(S.d_desc.p, order);
+  k_gather_tiles<<<dim3((max_tiles_pad * 32 + 127) / 128, nc), 128, 0, st>>>(S.d_desc.p, order, keys_sorted);
   k_super_boxes<<<dim3((max_super_pad * 32 + 127) / 128, nc), 128, 0, st>>>(S.d_desc.p);
   count_launch(2);
   MR_CUDA(cudaGetLastError());
@@ -348,6 +353,7 @@ static PairParams make_pair_params(Gicp* g) {
   p.tgt_tb = g->tgt->tb.p;
   p.tgt_sb = g->tgt->sb.p;
   p.tgt_qp = g->tgt->qp.p;
+  p.tgt_keys = g->tgt->skeys.p;
   p.tgt_n = g->tgt->n;
   p.tgt_cov = g->tgt->cov.p;
   p.tgt_ntiles = g->tgt->ntiles;

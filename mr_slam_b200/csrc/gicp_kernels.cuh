@@ -54,6 +54,7 @@ struct BuildDesc {
   float4* psort;
   float* tb;
   float* sb;
+  unsigned long long* skeys;  // [n] sorted curve keys of this cloud (binary-search seeds of the first NN-1 pass)
   float* qp;  // [4] quantisation frame of the Morton keys: min x,y,z and scale (kept for Morton look-ups)
   int n, ntiles, ntiles_pad, nsuper_pad;
   long long offset;  // position of this cloud's keys in the concatenated sort arrays
@@ -112,12 +113,38 @@ __device__ __forceinline__ unsigned long long spread16(unsigned v) {  // 16 bits
   return x;
 }
 
+#ifndef MR_HILBERT
+#define MR_HILBERT 1
+#endif
+// 48-bit space-filling-curve key of a point in the cloud's bounding cube (16 bits per axis): Hilbert order (Skilling's
+// axes-to-transpose transform + bit interleave) keeps 32 consecutive points in tighter boxes than Morton order does.
 __device__ __forceinline__ unsigned long long morton48(float x, float y, float z, float mnx, float mny, float mnz, float s) {
   float f0 = (x - mnx) * s, f1 = (y - mny) * s, f2 = (z - mnz) * s;
   f0 = isfinite(f0) ? fminf(fmaxf(f0, 0.0f), 65535.0f) : 65535.0f;
   f1 = isfinite(f1) ? fminf(fmaxf(f1, 0.0f), 65535.0f) : 65535.0f;
   f2 = isfinite(f2) ? fminf(fmaxf(f2, 0.0f), 65535.0f) : 65535.0f;
-  return spread16((unsigned)f0) | (spread16((unsigned)f1) << 1) | (spread16((unsigned)f2) << 2);
+  unsigned X0 = (unsigned)f0, X1 = (unsigned)f1, X2 = (unsigned)f2;
+#if MR_HILBERT
+#pragma unroll
+  for (unsigned Q = 0x8000u; Q > 1; Q >>= 1) {
+    const unsigned P = Q - 1;
+    if (X0 & Q) X0 ^= P;  // i = 0: invert (the exchange branch is a no-op for i = 0)
+    if (X1 & Q) X0 ^= P;
+    else { const unsigned t = (X0 ^ X1) & P; X0 ^= t; X1 ^= t; }
+    if (X2 & Q) X0 ^= P;
+    else { const unsigned t = (X0 ^ X2) & P; X0 ^= t; X2 ^= t; }
+  }
+  X1 ^= X0;
+  X2 ^= X1;
+  unsigned t = 0;
+#pragma unroll
+  for (unsigned Q = 0x8000u; Q > 1; Q >>= 1)
+    if (X2 & Q) t ^= Q - 1;
+  X0 ^= t; X1 ^= t; X2 ^= t;
+  return (spread16(X0) << 2) | (spread16(X1) << 1) | spread16(X2);
+#else
+  return spread16(X0) | (spread16(X1) << 1) | (spread16(X2) << 2);
+#endif
 }
 
 // key = (cloud << 48) | 48-bit Morton code of the point in its cloud's bounding cube; value = index inside the cloud
@@ -139,7 +166,8 @@ __global__ void k_morton(const BuildDesc* __restrict__ descs, const unsigned* __
 }
 
 // one warp per tile: gather the sorted points, pad, and reduce the tile's bounding box
-__global__ void k_gather_tiles(const BuildDesc* __restrict__ descs, const int* __restrict__ order_all) {
+__global__ void k_gather_tiles(const BuildDesc* __restrict__ descs, const int* __restrict__ order_all,
+                               const unsigned long long* __restrict__ keys_sorted) {
   const BuildDesc D = descs[blockIdx.y];
   int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
@@ -153,6 +181,7 @@ __global__ void k_gather_tiles(const BuildDesc* __restrict__ descs, const int* _
       int o = order[s];
       v = D.porig[o];
       v.w = __int_as_float(o);
+      D.skeys[s] = keys_sorted[D.offset + s] & 0xffffffffffffull;
       mn[0] = mx[0] = v.x; mn[1] = mx[1] = v.y; mn[2] = mx[2] = v.z;
     } else {
       v = make_float4(PAD_COORD, PAD_COORD, PAD_COORD, __int_as_float(PAD_IDX));
@@ -601,7 +630,8 @@ struct PairParams {
   const float4* tgt_sort;
   const float* tgt_tb;
   const float* tgt_sb;
-  const float* tgt_qp;  // Morton quantisation frame of the target (4 floats)
+  const float* tgt_qp;  // quantisation frame of the target's curve keys (4 floats)
+  const unsigned long long* tgt_keys;  // sorted curve keys of the target
   const double* tgt_cov;
   int tgt_n, tgt_ntiles, tgt_ntiles_pad, tgt_nsuper, tgt_nsuper_pad;
   int* corr;       // [src_npad] target SORTED position, -1 = none
@@ -803,8 +833,7 @@ __global__ void __launch_bounds__(128) k_nn1_search(const PairParams* __restrict
       int lo = 0, hi = P.tgt_n;  // first position whose key is >= kq
       while (lo < hi) {
         const int mid = (lo + hi) >> 1;
-        const float4 c = P.tgt_sort[mid];
-        if (morton48(c.x, c.y, c.z, mnx, mny, mnz, sc) < kq) lo = mid + 1;
+        if (P.tgt_keys[mid] < kq) lo = mid + 1;
         else hi = mid;
       }
       sp = min(lo, P.tgt_n - 1);
