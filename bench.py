@@ -53,16 +53,17 @@ def make_pairs(rank, n_pairs):
 
 
 class ClockSampler:
-    """SM clock / throttle reasons sampled DURING the timed region.  NVML (nvidia_ml_py) from a background thread: the
-    `nvidia-smi -lms` loop of the profiling recipe was measured to stall this launch/sync-heavy workload by 3-4x."""
+    """SM clock / throttle reasons sampled DURING the timed region through NVML (nvidia_ml_py), once between consecutive
+    timed steps.  Both alternatives were measured to perturb this launch/sync-heavy workload: the recipe's
+    `nvidia-smi -lms` loop slowed the steps 3-4x, and a background NVML polling thread (50 ms) still cost ~25 %
+    (NVML queries serialise with CUDA driver calls)."""
 
-    def __init__(self, index, period=0.05):
-        self.index, self.period = index, period
+    def __init__(self, index):
+        self.index = index
         self.samples, self.reasons = [], set()
         self.max_mhz = None
-        self._stop = threading.Event()
-        self._thr = None
         self.err = None
+        self.nv = None
 
     def start(self):
         try:
@@ -73,34 +74,28 @@ class ClockSampler:
             self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
         except Exception as e:  # noqa: BLE001
             self.err = "nvml unavailable: %r" % (e,)
-            return
-        self._thr = threading.Thread(target=self._run, daemon=True)
-        self._thr.start()
+            self.nv = None
 
-    def _run(self):
+    def sample(self):
         nv = self.nv
+        if nv is None:
+            return
         names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
                  "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
                  "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
                  "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
-        while not self._stop.is_set():
-            try:
-                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
-                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                for k, bit in names.items():
-                    if r & bit:
-                        self.reasons.add(k)
-            except Exception as e:  # noqa: BLE001
-                self.err = repr(e)
-                break
-            self._stop.wait(self.period)
+        try:
+            self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+            r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            for k, bit in names.items():
+                if r & bit:
+                    self.reasons.add(k)
+        except Exception as e:  # noqa: BLE001
+            self.err = repr(e)
 
     def stop(self):
-        self._stop.set()
-        if self._thr is not None:
-            self._thr.join(1.0)
         out = {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
-               "reasons": sorted(self.reasons), "samples": len(self.samples), "source": "nvml"}
+               "reasons": sorted(self.reasons), "samples": len(self.samples), "source": "nvml, one sample after every timed step"}
         if self.err:
             out["error"] = self.err
         return out
@@ -281,6 +276,8 @@ def main():
             e2.record()
         e2.synchronize()
         fused = emap.fused_total(reset=True)
+        if os.environ.get("BENCH_DEBUG"):
+            print("[debug] events: gicp %.2f ms elev %.2f ms; host since step start %.2f ms" % (e0.elapsed_time(e1), e1.elapsed_time(e2), 1e3 * (time.perf_counter() - tp0)), file=sys.stderr)
         return e0.elapsed_time(e1), e1.elapsed_time(e2), fused, Ts, regs
 
     def step_e2e():
@@ -334,7 +331,6 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    _lib.prof_enable(True)
     launches0 = _lib.kernel_launch_count()
     barrier()
     t_g, t_e, fused_tot, n_lin, n_err = 0.0, 0.0, 0, 0, 0
@@ -348,12 +344,28 @@ def main():
             a, b = r.eval_counts()
             n_lin += a
             n_err += b
+        if rank == 0:
+            sampler.sample()  # the GPU has been busy for the whole step that just ended
     barrier()
     wall = time.perf_counter() - wall0
     launches = _lib.kernel_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    # per-kernel device times for the roofline block: the same steps again with CUDA events around every launch group on
+    # the library stream (kept out of the region above: ~300 extra event records per step would be timed with it)
+    PROF_STEPS = 2
+    _lib.prof_enable(True)
+    p_lin = p_err = 0
+    tgp = 0.0
+    for _ in range(PROF_STEPS):
+        tg_, _te, _f, _Ts, regs_ = step_device()
+        tgp += tg_
+        for r in regs_:
+            a, b = r.eval_counts()
+            p_lin += a
+            p_err += b
     prof = _lib.prof_get()
     _lib.prof_enable(False)
-    clocks = sampler.stop() if rank == 0 else None
+    barrier()
     t_total_ms = reduce_max(t_g + t_e)
     t_g_ms, t_e_ms = reduce_max(t_g), reduce_max(t_e)
     aligns_total = n_pairs * args.steps * world
@@ -401,10 +413,10 @@ def main():
         clouds_per_step = 2 * n_pairs
         groups = {
             "knn_search+cov": dict(ms=prof["knn_search"][0] + prof["cov"][0], launches=prof["knn_search"][1],
-                                   bytes=36.0 * N_POINTS * clouds_per_step * args.steps),
+                                   bytes=36.0 * N_POINTS * clouds_per_step * PROF_STEPS),
             "nn1_search+linearize": dict(ms=prof["nn1_search"][0] + prof["linearize"][0], launches=prof["nn1_search"][1],
-                                         bytes=100.0 * N_POINTS * n_lin),
-            "error": dict(ms=prof["error"][0], launches=prof["error"][1], bytes=52.0 * N_POINTS * n_err),
+                                         bytes=100.0 * N_POINTS * p_lin),
+            "error": dict(ms=prof["error"][0], launches=prof["error"][1], bytes=52.0 * N_POINTS * p_err),
         }
         dom = max(groups, key=lambda k: groups[k]["ms"])
         gd = groups[dom]
@@ -412,9 +424,10 @@ def main():
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                     "traffic": None, "peak_source": peak_src,
                     "ms_per_launch": gd["ms"] / max(gd["launches"], 1), "launches": gd["launches"],
-                    "share_of_gicp_time": gd["ms"] / t_g if t_g > 0 else None,
+                    "share_of_gicp_time": gd["ms"] / tgp if tgp > 0 else None,
+                    "timed_over": "%d extra steps of the same workload with per-kernel CUDA events on the launch stream" % PROF_STEPS,
                     "note": "exact search kernels are instruction-latency bound (warp-serial k-min), not HBM bound; see DESIGN.md",
-                    "all_kernels_ms": {k: round(v[0], 3) for k, v in prof.items()}}
+                    "all_kernels_ms_per_step": {k: round(v[0] / PROF_STEPS, 3) for k, v in prof.items()}}
         line = {
             "metric": "gicp_aligns_per_s", "value": value, "unit": "aligns/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": t_total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64",

@@ -173,6 +173,14 @@ int mrslam_voxelocc_transform(const float* point, int size, int max_length, int 
                               int num_height, int enough_large, float* out);
 int mrslam_polar_transform(const float* point, int size, int max_length, int max_height, int num_ring, int num_sector,
                            int num_height, int enough_large, float* out);
+/* voxelfeat (RING++) -- BEVF = LoopDetection/generate_bev_pointfeat_cython: GPUFeatureExtractor::get_features
+ * (BEVF/src/manager.cu:127-181, kernel.cu:16-104; point AoS xyz, neighbours int[size*k], eigens float[size*5], out float[size*featsize])
+ * and the feature-BEV GPUTransformer (BEVF/src/manager.cu:18-101, kernel.cu:106-164; point SoA with featsize channels,
+ * out float[num_x*num_y*featsize]; num_height must be 1).  Host pointers. */
+int mrslam_voxelfeat_features(const float* point_aos, int size, int featsize, int k, const int* neighbors, const float* eigens,
+                              float* feature_out);
+int mrslam_voxelfeat_transform(const float* point, int size, int max_length, int max_height, int num_x, int num_y,
+                               int num_height, int featsize, float* out);
 /* device batch variant used by the RING pipeline: points SoA per scan on the device, offsets[b]..offsets[b+1];
  * writes only what generate_RING keeps (channel 2, the max-height image) as d_bev[batch][num_x][num_y]. */
 int mrslam_voxelocc_bev_device(const float* d_points_soa, const long long* offsets_host, int batch, int max_length,

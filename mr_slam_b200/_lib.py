@@ -112,6 +112,8 @@ def _declare(L):
     if hasattr(L, "mrslam_voxelocc_transform"):
         L.mrslam_voxelocc_transform.argtypes = [fp, i, i, i, i, i, i, i, fp]
         L.mrslam_polar_transform.argtypes = [fp, i, i, i, i, i, i, i, fp]
+        L.mrslam_voxelfeat_features.argtypes = [fp, i, i, i, ip, fp, fp]
+        L.mrslam_voxelfeat_transform.argtypes = [fp, i, i, i, i, i, i, i, fp]
         L.mrslam_voxelocc_bev_device.argtypes = [fp, C.c_void_p, i, i, i, i, i, fp]
     if hasattr(L, "mrslam_radon_forward"):
         L.mrslam_radon_forward.argtypes = [fp, i, i, i, fp, i, i, f, i, i, fp]

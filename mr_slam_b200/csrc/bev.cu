@@ -191,6 +191,71 @@ __global__ void k_fill_i32(int* p, int n, int v) {
   if (i < n) p[i] = v;
 }
 
+// ---- voxelfeat (RING++): generate_bev_pointfeat_cython/src/kernel.cu:16-104 (features) and :106-164 (feature BEV) ----
+__global__ void k_voxelfeat_features(const float* __restrict__ pc, int size, int featsize, int k, const int* __restrict__ nbr,
+                                     const float* __restrict__ eig, float* __restrict__ feature) {
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= size) return;
+  const float eps = 0.0f;
+  float e3[3], e2[2];
+  float s3 = 0.f, p3 = 1.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 5; i++) {
+    if (i < 3) {
+      e3[i] = eig[(size_t)g * 5 + i];
+      s3 += e3[i];
+      p3 = p3 * e3[i];
+    } else {
+      e2[i - 3] = eig[(size_t)g * 5 + i];
+      s2 += e2[i - 3];
+    }
+  }
+  const float C_ = e3[2] / (s3 + eps);
+  const float O_ = (float)pow((double)p3 / (pow((double)s3, 3.0) + (double)eps), 1.0 / 3.0);
+  const float L_ = (e3[0] - e3[1]) / (e3[0] + eps);
+  float E_ = 0.f;
+#pragma unroll
+  for (int i = 0; i < 3; i++) E_ += (e3[i] / (s3 + eps)) * logf(e3[i] / (s3 + eps));
+  E_ = -E_;
+  const float P_ = (e3[1] - e3[2]) / e3[0];
+  const float S_ = e3[2] / e3[0];
+  const float A_ = (e3[0] - e3[2]) / e3[0];
+  const float D_ = (float)((double)(3 * k) / ((4 * 3.14159265358979323846 * (double)p3) + (double)eps));
+  const float L_2 = e2[1] / e2[0];
+  float mean = 0.f, mn = 10000.0f;
+  const int* nb = nbr + (size_t)g * k;
+  for (int i = 0; i < k; i++) {
+    const float z = pc[(size_t)nb[i] * 3 + 2];
+    mean += z;
+    if (z < mn) mn = z;
+  }
+  mean = mean / k;
+  float dZ = -100000.0f, vZ = 0.f;
+  for (int i = 0; i < k; i++) {
+    const float z = pc[(size_t)nb[i] * 3 + 2];
+    const float diff = z - mn;
+    vZ = (float)((double)vZ + pow((double)fabsf(z - mean), 2.0));
+    if (diff > dZ) dZ = diff;
+  }
+  vZ = vZ / k;
+  float* f = feature + (size_t)g * featsize;
+  f[0] = C_; f[1] = O_; f[2] = L_; f[3] = E_; f[4] = P_; f[5] = S_; f[6] = A_; f[7] = s3; f[8] = D_; f[9] = s2; f[10] = L_2;
+  f[11] = dZ; f[12] = vZ;
+}
+
+// per-cell, per-channel maximum of the positive values (the race-free result the reference's compare-then-write intends)
+__global__ void k_voxelfeat_bev(const float* __restrict__ pt, VoxCfg c, int featsize, int* __restrict__ out_bits) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c.size) return;
+  int ix, iy, ih;
+  if (!cart_index(pt, i, c, ix, iy, ih) || ih != 0) return;
+  int* o = out_bits + (size_t)featsize * (iy + ix * c.num_y);
+  for (int j = 0; j < featsize; j++) {
+    const float v = pt[i + (size_t)j * c.size];
+    if (v > 0.0f) atomicMax(&o[j], __float_as_int(v));
+  }
+}
+
 struct BevScratch {
   DevBuf<float> pts, out;
   DevBuf<int> a, b, keys, keys_alt, vals, vals_alt, layer;
@@ -295,6 +360,65 @@ int mrslam_voxelocc_transform(const float* point, int size, int max_length, int 
 int mrslam_polar_transform(const float* point, int size, int max_length, int max_height, int num_ring, int num_sector, int num_height,
                            int enough_large, float* out) {
   return transform_host(true, point, size, max_length, max_height, num_ring, num_sector, num_height, enough_large, out);
+}
+
+int mrslam_voxelfeat_features(const float* point_aos, int size, int featsize, int k, const int* neighbors, const float* eigens,
+                              float* feature_out) {
+  MR_CHECK(ensure_init());
+  if (size < 0 || featsize < 13 || k < 1 || k > 30 || !feature_out) {
+    set_error("GPUFeatureExtractor: bad arguments (featsize >= 13, 1 <= k <= 30)");
+    return MRSLAM_ERR_ARG;
+  }
+  if (size == 0) return MRSLAM_OK;
+  std::lock_guard<std::mutex> lk(rt().mu);
+  cudaStream_t st = rt().stream;
+  BevScratch& S = bs();
+  MR_CHECK(S.pts.reserve((size_t)size * 3));
+  MR_CHECK(S.out.reserve((size_t)size * featsize));
+  MR_CHECK(S.keys.reserve((size_t)size * k));
+  DevBuf<float> deig;
+  MR_CHECK(deig.reserve((size_t)size * 5));
+  MR_CUDA(cudaMemcpyAsync(S.pts.p, point_aos, sizeof(float) * 3 * (size_t)size, cudaMemcpyHostToDevice, st));
+  MR_CUDA(cudaMemcpyAsync(S.keys.p, neighbors, sizeof(int) * (size_t)size * k, cudaMemcpyHostToDevice, st));
+  MR_CUDA(cudaMemcpyAsync(deig.p, eigens, sizeof(float) * 5 * (size_t)size, cudaMemcpyHostToDevice, st));
+  MR_CUDA(cudaMemsetAsync(S.out.p, 0, sizeof(float) * (size_t)size * featsize, st));
+  k_voxelfeat_features<<<(size + 255) / 256, 256, 0, st>>>(S.pts.p, size, featsize, k, S.keys.p, deig.p, S.out.p);
+  count_launch(1);
+  MR_CUDA(cudaGetLastError());
+  MR_CUDA(cudaMemcpyAsync(feature_out, S.out.p, sizeof(float) * (size_t)size * featsize, cudaMemcpyDeviceToHost, st));
+  MR_CUDA(cudaStreamSynchronize(st));
+  deig.release();
+  return MRSLAM_OK;
+}
+
+int mrslam_voxelfeat_transform(const float* point, int size, int max_length, int max_height, int num_x, int num_y, int num_height,
+                               int featsize, float* out) {
+  MR_CHECK(ensure_init());
+  if (size < 0 || num_x <= 0 || num_y <= 0 || num_height != 1 || featsize < 3 || !out) {
+    set_error("voxelfeat GPUTransformer: bad arguments (num_height must be 1, the only configuration RING++ uses)");
+    return MRSLAM_ERR_ARG;
+  }
+  std::lock_guard<std::mutex> lk(rt().mu);
+  cudaStream_t st = rt().stream;
+  BevScratch& S = bs();
+  VoxCfg c;
+  c.size = size; c.num_x = num_x; c.num_y = num_y; c.num_h = 1; c.enough_large = 1; c.max_height = (float)max_height;
+  c.gap_x = (float)(2.0 * (double)(float)max_length / (double)(float)num_x);
+  c.gap_y = (float)(2.0 * (double)(float)max_length / (double)(float)num_y);
+  c.gap_h = (float)(2.0 * (double)(float)max_height / 1.0);
+  const size_t out_n = (size_t)num_x * num_y * featsize;
+  MR_CHECK(S.pts.reserve(std::max<size_t>((size_t)size * featsize, 1)));
+  MR_CHECK(S.out.reserve(out_n));
+  MR_CUDA(cudaMemsetAsync(S.out.p, 0, sizeof(float) * out_n, st));
+  if (size > 0) {
+    MR_CUDA(cudaMemcpyAsync(S.pts.p, point, sizeof(float) * (size_t)size * featsize, cudaMemcpyHostToDevice, st));
+    k_voxelfeat_bev<<<(size + 255) / 256, 256, 0, st>>>(S.pts.p, c, featsize, (int*)S.out.p);
+    count_launch(1);
+  }
+  MR_CUDA(cudaGetLastError());
+  MR_CUDA(cudaMemcpyAsync(out, S.out.p, sizeof(float) * out_n, cudaMemcpyDeviceToHost, st));
+  MR_CUDA(cudaStreamSynchronize(st));
+  return MRSLAM_OK;
 }
 
 int mrslam_voxelocc_bev_device(const float* d_points_soa, const long long* offsets_host, int batch, int max_length, int max_height,

@@ -164,13 +164,23 @@ __global__ void k_elev_keys(const int* __restrict__ idx, const float* __restrict
   vals[i] = i;
 }
 
-// One thread per run of equal cell keys (points inside a run are in ascending point index because the
-// radix sort is stable): the sequential recurrence of G_fuse, gpu_process.cu:477-535.
-__global__ void k_elev_fuse_segments(const int* __restrict__ keys, const int* __restrict__ order, int n, int cells,
-                                     const float* __restrict__ ph, const float* __restrict__ pv, const int* __restrict__ cR,
-                                     const int* __restrict__ cG, const int* __restrict__ cB, const float* __restrict__ inten,
-                                     float* __restrict__ elevation, float* __restrict__ variance, float* __restrict__ intensity,
-                                     int* __restrict__ R, int* __restrict__ G, int* __restrict__ B, unsigned long long* n_fused) {
+// gather the per-point inputs into sorted (cell, point-index) order so that the run walk below reads contiguous memory
+__global__ void k_elev_gather(const int* __restrict__ order, int n, const float* __restrict__ ph, const float* __restrict__ pv,
+                              const int* __restrict__ cR, const int* __restrict__ cG, const int* __restrict__ cB,
+                              const float* __restrict__ inten, float2* __restrict__ hv, int4* __restrict__ col) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const int pi = order[j];
+  hv[j] = make_float2(ph[pi], pv[pi]);
+  if (col) col[j] = make_int4(cR[pi], cG[pi], cB[pi], __float_as_int(inten[pi]));
+}
+
+// One thread per run of equal cell keys (points inside a run are in ascending point index because the radix sort is
+// stable): the sequential recurrence of G_fuse, gpu_process.cu:477-535, over the gathered (height, variance) stream.
+__global__ void k_elev_fuse_segments(const int* __restrict__ keys, int n, int cells, const float2* __restrict__ hv,
+                                     const int4* __restrict__ col, float* __restrict__ elevation, float* __restrict__ variance,
+                                     float* __restrict__ intensity, int* __restrict__ R, int* __restrict__ G, int* __restrict__ B,
+                                     unsigned long long* n_fused) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int c = keys[i];
@@ -182,37 +192,41 @@ __global__ void k_elev_fuse_segments(const int* __restrict__ keys, const int* __
   bool colour_written = false;
   int cnt = 0;
   for (int j = i; j < n && keys[j] == c; j++) {
-    const int pi = order[j];
-    const float h = ph[pi], hv = pv[pi];
+    const float2 m = hv[j];
+    const float h = m.x, hvv = m.y;
     cnt++;
     bool colour = false;
-    if (cR) colour = cR[pi] != 0 && cG[pi] != 0 && cB[pi] != 0 && inten[pi] != 0.f;
+    int4 cc = make_int4(0, 0, 0, 0);
+    if (col) {
+      cc = col[j];
+      colour = cc.x != 0 && cc.y != 0 && cc.z != 0 && __int_as_float(cc.w) != 0.f;
+    }
     bool wc = false;
     if (e == -10.f) {
       e = h;
-      v = hv;
+      v = hvv;
       wc = colour;
     } else {
       const float md = fabsf(h - e) / sqrtf(v);
       if (md > 5.f) {
         if (e < h) {
           e = h;
-          v = hv;
+          v = hvv;
           wc = colour;
         }
       } else {
-        const float ne = fmaf(v, h, hv * e) / (v + hv);
-        const float nv = (hv * v) / (hv + v);
+        const float ne = fmaf(v, h, hvv * e) / (v + hvv);
+        const float nv = (hvv * v) / (hvv + v);
         e = ne;
         v = nv;
         wc = colour;
       }
     }
     if (wc) {
-      ci = inten[pi];
-      cr = cR[pi];
-      cg = cG[pi];
-      cb = cB[pi];
+      ci = __int_as_float(cc.w);
+      cr = cc.x;
+      cg = cc.y;
+      cb = cc.z;
       colour_written = true;
     }
   }
@@ -264,6 +278,8 @@ struct Elev {
   // per-frame buffers
   DevBuf<float> px, py, pz, pvar, pxt, pyt, pzt, pint, ph;
   DevBuf<int> pidx, pR, pG, pB, keys, keys_alt, vals, vals_alt;
+  DevBuf<float2> ghv;
+  DevBuf<int4> gcol;
   DevBuf<unsigned char> cubtmp;
   DevBuf<unsigned long long> counter;
   std::mutex mu;  // Fuse and Mapvar_update may be called from two threads (ElevationMapping.cpp:393-394)
@@ -277,6 +293,8 @@ struct Elev {
     MR_CHECK(pidx.reserve(m)); MR_CHECK(pR.reserve(m)); MR_CHECK(pG.reserve(m)); MR_CHECK(pB.reserve(m));
     MR_CHECK(keys.reserve(m)); MR_CHECK(keys_alt.reserve(m)); MR_CHECK(vals.reserve(m)); MR_CHECK(vals_alt.reserve(m));
     MR_CHECK(counter.reserve(2));
+    MR_CHECK(ghv.reserve(m));
+    MR_CHECK(gcol.reserve(m));
     return MRSLAM_OK;
   }
   void release() {
@@ -284,6 +302,8 @@ struct Elev {
     for (DevBuf<int>* b : {&R, &G, &B, &pidx, &pR, &pG, &pB, &keys, &keys_alt, &vals, &vals_alt}) b->release();
     cubtmp.release();
     counter.release();
+    ghv.release();
+    gcol.release();
   }
 };
 
@@ -302,10 +322,11 @@ static int fuse_sorted(Elev* m, int n, const float* d_h, const float* d_v, const
     MR_CHECK(m->cubtmp.reserve(tmp));
     MR_CUDA(cub::DeviceRadixSort::SortPairs(m->cubtmp.p, tmp, dk, dv, n, 0, bits, st));
     if (n_fused) MR_CUDA(cudaMemsetAsync(m->counter.p, 0, sizeof(unsigned long long), st));
-    k_elev_fuse_segments<<<(n + 127) / 128, 128, 0, st>>>(dk.Current(), dv.Current(), n, cells, d_h, d_v, d_R, d_G, d_B, d_I,
-                                                         m->elevation.p, m->variance.p, m->intensity.p, m->R.p, m->G.p, m->B.p,
+    k_elev_gather<<<(n + 255) / 256, 256, 0, st>>>(dv.Current(), n, d_h, d_v, d_R, d_G, d_B, d_I, m->ghv.p, d_R ? m->gcol.p : nullptr);
+    k_elev_fuse_segments<<<(n + 127) / 128, 128, 0, st>>>(dk.Current(), n, cells, m->ghv.p, d_R ? m->gcol.p : nullptr, m->elevation.p,
+                                                         m->variance.p, m->intensity.p, m->R.p, m->G.p, m->B.p,
                                                          n_fused ? m->counter.p : m->counter.p + 1);
-    count_launch(1);
+    count_launch(2);
   }
   k_elev_clamp_var<<<((cells + 3) / 4 + 255) / 256, 256, 0, st>>>(m->variance.p, cells);
   count_launch(1);

@@ -137,6 +137,13 @@ int mrslam_prof_enable(int on) {
     g_prof_n[i] = 0;
   }
   g_prof = on != 0;
+  if (g_prof) {  // pre-create the event pool so that no cudaEventCreate lands inside a measured region
+    while (g_free_events.size() < 2048) {
+      cudaEvent_t e;
+      if (cudaEventCreate(&e) != cudaSuccess) break;
+      g_free_events.push_back(e);
+    }
+  }
   return MRSLAM_OK;
 }
 int mrslam_prof_get(int id, double* total_ms, long long* count) {

@@ -77,6 +77,8 @@ def _decl(L):
 
     L.orc_voxelocc.argtypes = [_p(np.float32), i, i, i, i, i, i, i, _p(np.float32), C.c_void_p, C.POINTER(i)]
     L.orc_polar.argtypes = [_p(np.float32), i, i, i, i, i, i, i, _p(np.float32), C.c_void_p, C.POINTER(i)]
+    L.orc_voxelfeat_features.argtypes = [_p(np.float32), i, i, i, _p(np.int32), _p(np.float32), _p(np.float32)]
+    L.orc_voxelfeat_bev.argtypes = [_p(np.float32), i, i, i, i, i, i, i, _p(np.float32), C.POINTER(i)]
     L.orc_radon_forward.argtypes = [_p(np.float32), i, i, i, _p(np.float32), i, i, f, i, _p(np.float32)]
     L.orc_ring_tiring.argtypes = [_p(np.float32), i, i, i, C.c_void_p, _p(np.float32)]
     L.orc_ring_fast_corr.argtypes = [_p(np.float32), _p(np.float32), i, i, i, _p(np.float32), C.POINTER(f), C.POINTER(i)]
@@ -286,6 +288,19 @@ def polar(point_soa, size, max_length, max_height, num_ring, num_sector, num_hei
     lib().orc_polar(p, size, max_length, max_height, num_ring, num_sector, num_height, enough_large, out,
                     idx.ctypes.data if want_idx else None, C.byref(nd))
     return (out, idx, nd.value) if want_idx else out
+
+
+def voxelfeat_features(pc_aos, size, featsize, k, neighbors, eigens):
+    out = np.zeros(size * featsize, np.float32)
+    lib().orc_voxelfeat_features(_f32(pc_aos), size, featsize, k, np.ascontiguousarray(neighbors, np.int32), _f32(eigens), out)
+    return out
+
+
+def voxelfeat_bev(point_soa, size, max_length, max_height, num_x, num_y, num_height, featsize):
+    out = np.zeros(num_x * num_y * num_height * featsize, np.float32)
+    nd = C.c_int()
+    lib().orc_voxelfeat_bev(_f32(point_soa), size, max_length, max_height, num_x, num_y, num_height, featsize, out, C.byref(nd))
+    return out
 
 
 def radon_forward(img, angles, det_count=None, det_spacing=1.0, weight_bits=0):

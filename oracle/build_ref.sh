@@ -25,6 +25,8 @@ V=$LD/generate_bev_cython_binary/src
 run $NVCC -arch=sm_100 -O2 -w -Xcompiler -fPIC -shared -I"$V" -DREF_FN=ref_voxelocc_gpu -o "$OUT/libvoxelocc_ref.so" "$HERE/ref_wrap/voxel_gpu_wrap.cu" "$V/manager.cu"
 G=$LD/src/disco_ros/tools/multi-layer-polar-gpu/cython/src
 run $NVCC -arch=sm_100 -O2 -w -Xcompiler -fPIC -shared -I"$G" -DREF_FN=ref_polar_gpu -o "$OUT/libpolar_gpu_ref.so" "$HERE/ref_wrap/voxel_gpu_wrap.cu" "$G/manager.cu"
+F=$LD/generate_bev_pointfeat_cython/src
+run $NVCC -arch=sm_100 -O2 -w -Xcompiler -fPIC -shared -I"$F" -o "$OUT/libvoxelfeat_ref.so" "$HERE/ref_wrap/voxelfeat_gpu_wrap.cu" "$F/manager.cu"
 # 4. torch-radon forward projection (reference CUDA kernel with hardware texture filtering), sm_100
 run $NVCC -arch=sm_100 -O2 -w -std=c++17 -Xcompiler -fPIC -shared -I"$T/include" -o "$OUT/libradon_ref.so" "$HERE/ref_wrap/radon_wrap.cu" "$T/src/forward.cu" "$T/src/texture.cu" "$T/src/parameter_classes.cu" "$T/src/log.cpp"
 # 5. elevation mapping kernels against the minimal Eigen shim (oracle/eigen_shim), sm_100

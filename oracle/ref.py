@@ -46,6 +46,25 @@ def voxelocc_gpu(soa, size, max_length, max_height, num_x, num_y, num_height, en
     return _vox("voxelocc", "ref_voxelocc_gpu", soa, size, max_length, max_height, num_x, num_y, num_height, enough_large)
 
 
+def voxelfeat_features(pc_aos, size, featsize, k, nbr, eig):
+    L = _lib("voxelfeat")
+    L.ref_voxelfeat_features.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    pc, eig = _f32(pc_aos).copy(), _f32(eig).copy()
+    nbr = np.ascontiguousarray(nbr, np.int32).copy()
+    out = np.zeros(size * featsize, np.float32)
+    L.ref_voxelfeat_features(pc.ctypes.data, size, featsize, k, nbr.ctypes.data, eig.ctypes.data, out.ctypes.data)
+    return out
+
+
+def voxelfeat_bev(soa, size, max_length, max_height, num_x, num_y, num_height, featsize):
+    L = _lib("voxelfeat")
+    L.ref_voxelfeat_bev.argtypes = [C.c_void_p] + [C.c_int] * 7 + [C.c_void_p]
+    p = _f32(soa).copy()
+    out = np.zeros(num_x * num_y * num_height * featsize, np.float32)
+    L.ref_voxelfeat_bev(p.ctypes.data, size, max_length, max_height, num_x, num_y, num_height, featsize, out.ctypes.data)
+    return out
+
+
 def radon_forward(img, angles, det_count, det_spacing=1.0):
     L = _lib("radon")
     L.ref_radon_forward.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p]

@@ -92,3 +92,55 @@ def test_empty_and_argument_errors(gpu):
     with pytest.raises(ValueError):
         voxelocc.GPUTransformer(np.zeros(3, np.float32), 5, 1, 1, 120, 120, 1, 1)   # buffer shorter than 3*size
     assert out.shape == (3,)
+
+
+def _feat_inputs(n=6000, k=30, seed=8):
+    rng = np.random.default_rng(seed)
+    pc = rng.uniform(-1, 1, (n, 3)).astype(np.float32)
+    nbr = rng.integers(0, n, (n, k)).astype(np.int32)
+    e3 = np.sort(rng.uniform(1e-4, 1.0, (n, 3)).astype(np.float32), axis=1)[:, ::-1]
+    e2 = np.sort(rng.uniform(1e-4, 1.0, (n, 2)).astype(np.float32), axis=1)[:, ::-1]
+    eig = np.ascontiguousarray(np.concatenate([e3, e2], 1), np.float32)
+    return pc, nbr, eig
+
+
+def test_voxelfeat_features(gpu):
+    """RING++ point features (BEVF/src/kernel.cu:16-104): 13 features per point, vs the oracle and the reference kernel."""
+    from mr_slam_b200 import voxelfeat
+    pc, nbr, eig = _feat_inputs()
+    n, k = nbr.shape
+    fe = voxelfeat.GPUFeatureExtractor(pc.reshape(-1), n, 13, k, nbr.reshape(-1), eig.reshape(-1))
+    got = fe.get_features().reshape(n, 13)
+    exp = oracle.voxelfeat_features(pc.reshape(-1), n, 13, k, nbr.reshape(-1), eig.reshape(-1)).reshape(n, 13)
+    assert np.allclose(got, exp, rtol=2e-5, atol=1e-6)      # logf / pow differ by an ulp or two between glibc and CUDA
+    from oracle import ref
+    if ref.available("voxelfeat"):
+        r = ref.voxelfeat_features(pc.reshape(-1), n, 13, k, nbr.reshape(-1), eig.reshape(-1)).reshape(n, 13)
+        assert np.allclose(got, r, rtol=2e-6, atol=1e-7)     # same device math library: last-bit agreement
+
+
+def test_voxelfeat_bev(gpu):
+    """feature BEV (BEVF/src/kernel.cu:106-164): per cell / channel maximum of the positive values."""
+    from mr_slam_b200 import voxelfeat
+    rng = np.random.default_rng(9)
+    n, fs = 40000, 9
+    pts = rng.uniform(-1.05, 1.05, (n, fs)).astype(np.float32)
+    soa = np.ascontiguousarray(pts.T.reshape(-1))
+    t = voxelfeat.GPUTransformer(soa, n, 1, 1, 120, 120, 1, fs)
+    t.transform()
+    got = t.retreive()
+    assert got.shape == (120 * 120 * fs,)
+    assert np.array_equal(got, oracle.voxelfeat_bev(soa, n, 1, 1, 120, 120, 1, fs))
+    from oracle import ref
+    if ref.available("voxelfeat"):
+        # the reference update is a non-atomic compare-then-write: compare on an input without collisions (one point per cell)
+        gx, gy = np.meshgrid(np.arange(120), np.arange(120), indexing="ij")
+        cx = ((gx.reshape(-1) + 0.5) / 60.0 - 1.0).astype(np.float32)
+        cy = ((gy.reshape(-1) + 0.5) / 60.0 - 1.0).astype(np.float32)
+        m = len(cx)
+        p2 = rng.uniform(-0.9, 0.9, (m, fs)).astype(np.float32)
+        p2[:, 0], p2[:, 1] = cx, cy
+        soa2 = np.ascontiguousarray(p2.T.reshape(-1))
+        t2 = voxelfeat.GPUTransformer(soa2, m, 1, 1, 120, 120, 1, fs)
+        t2.transform()
+        assert np.array_equal(t2.retreive(), ref.voxelfeat_bev(soa2, m, 1, 1, 120, 120, 1, fs))
