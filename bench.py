@@ -240,33 +240,39 @@ def main():
                 e["C_SB_transpose"], e["P_mul_C_BM_transpose"], e["B_r_BS_skew"])
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
+    exch_ms = [0.0]
+    step_trace = []
 
     def step_device():
-        """inputs resident in HBM; returns (t_gicp_ms, t_elev_ms, n_fused, results) measured with events on the library stream"""
-        e0, e1, e2 = ev(), ev(), ev()
+        """inputs resident in HBM; returns (t_gicp_ms, t_elev_ms, n_fused, results) measured with events on the library stream.
+        Order inside a step: start the exchange (NCCL stream) -> local work that does not need it (source tiles + covariances,
+        elevation fuse of the robot's own scans) on the library stream -> wait -> target tiles + covariances + LM."""
+        e0, e1, e2, e3 = ev(), ev(), ev(), ev()
         with torch.cuda.stream(lib_stream):
             e0.record()
         # exchange step: candidate clouds of the neighbouring robot (NCCL all-gather over NVLink); none at N=1
+        work = None
         if world > 1:
-            allc = mdist.allgather_slots(offer_dev)
+            allc, work = mdist.allgather_slots(offer_dev, async_op=True)
             tgt_dev = allc[(rank + 1) % world]
-            torch.cuda.current_stream().synchronize()
         else:
             tgt_dev = offer_dev
-        tp0 = time.perf_counter()
+        tm = [time.perf_counter()]
+        mark = lambda: tm.append(time.perf_counter())
         regs = new_regs()
-        clouds = []
-        for i, g in enumerate(regs):
-            cs = pygicp.Cloud(device_ptr=src_dev[i].data_ptr(), n=N_POINTS, stride=3)
-            ct = pygicp.Cloud(device_ptr=tgt_dev[i].data_ptr(), n=N_POINTS, stride=3)
+        mark()
+        flow = os.environ.get("BENCH_FLOW", "")
+        if "percloud" in flow:
+            src_clouds = [pygicp.Cloud(device_ptr=src_dev[i].data_ptr(), n=N_POINTS, stride=3) for i in range(n_pairs)]
+        else:
+            src_clouds = pygicp.Cloud.from_device_batch([src_dev[i].data_ptr() for i in range(n_pairs)], N_POINTS, 3)
+        mark()
+        for g, cs in zip(regs, src_clouds):
             g.set_input_source(cs)
-            g.set_input_target(ct)
-            clouds += [cs, ct]
-        tp1 = time.perf_counter()
-        Ts = pygicp.align_batch(regs, guesses)
-        tp2 = time.perf_counter()
-        if os.environ.get("BENCH_DEBUG"):
-            print("[debug] setup %.2f ms align_batch %.2f ms iters %s" % (1e3 * (tp1 - tp0), 1e3 * (tp2 - tp1), [r.num_iterations() for r in regs]), file=sys.stderr)
+        mark()
+        if "noprepare" not in flow:
+            pygicp.prepare_batch(regs, pygicp.SOURCE)
+        mark()
         with torch.cuda.stream(lib_stream):
             e1.record()
         for i in range(n_pairs):
@@ -274,11 +280,37 @@ def main():
             emap.process_fuse_device(soa_dev[i][0], soa_dev[i][1], soa_dev[i][2], N_POINTS, *elev_args(i), near_filter=True, want_count=False)
         with torch.cuda.stream(lib_stream):
             e2.record()
-        e2.synchronize()
+        mark()
+        tx0 = time.perf_counter()
+        if work is not None:
+            work.wait()                       # orders torch's current stream after the collective (no host block)
+            done = torch.cuda.Event()
+            done.record()
+            lib_stream.wait_event(done)       # ... and the library stream after that
+        exch_ms[0] += 1e3 * (time.perf_counter() - tx0)
+        mark()
+        if "percloud" in flow:
+            tgt_clouds = [pygicp.Cloud(device_ptr=tgt_dev[i].data_ptr(), n=N_POINTS, stride=3) for i in range(n_pairs)]
+        else:
+            tgt_clouds = pygicp.Cloud.from_device_batch([tgt_dev[i].data_ptr() for i in range(n_pairs)], N_POINTS, 3)
+        for g, ct in zip(regs, tgt_clouds):
+            g.set_input_target(ct)
+        mark()
+        Ts = pygicp.align_batch(regs, guesses)
+        mark()
+        with torch.cuda.stream(lib_stream):
+            e3.record()
+        e3.synchronize()
         fused = emap.fused_total(reset=True)
+        t_gicp = e0.elapsed_time(e1) + e2.elapsed_time(e3)
+        t_elev = e1.elapsed_time(e2)
+        step_trace.append((round(e0.elapsed_time(e1), 2), round(t_elev, 2), round(e2.elapsed_time(e3), 2), round(1e3 * (tm[-1] - tm[-2]), 2)))
         if os.environ.get("BENCH_DEBUG"):
-            print("[debug] events: gicp %.2f ms elev %.2f ms; host since step start %.2f ms" % (e0.elapsed_time(e1), e1.elapsed_time(e2), 1e3 * (time.perf_counter() - tp0)), file=sys.stderr)
-        return e0.elapsed_time(e1), e1.elapsed_time(e2), fused, Ts, regs
+            names = ["new_regs", "pack src", "set src", "prepare src", "elev launches", "exchange wait", "pack+set tgt", "align_batch"]
+            print("[debug] host ms: " + ", ".join("%s %.2f" % (n_, 1e3 * (tm[i + 1] - tm[i])) for i, n_ in enumerate(names)) +
+                  "; events: src prepare %.2f elev %.2f targets+LM %.2f ms; iters %s" %
+                  (e0.elapsed_time(e1), t_elev, e2.elapsed_time(e3), [r.num_iterations() for r in regs]), file=sys.stderr)
+        return t_gicp, t_elev, fused, Ts, regs
 
     def step_e2e():
         """same step through the C-ABI with HOST buffers (pinned): H2D of every cloud, D2H of the results"""
@@ -323,17 +355,24 @@ def main():
         return float(t.item())
 
     # ---- warm-up (also grows the memory pools) ----
-    for _ in range(args.warmup):
-        step_device()
-    barrier()
-
-    # ---- timed region: device-resident ----
+    # The clock sampler is started and exercised here too: the FIRST NVML query of a process was measured to stall the CUDA
+    # calls of the following step by 50-200 ms on some boxes (lazy NVML/driver initialisation); the samples taken during the
+    # warm-up are discarded, the ones reported are taken between the timed steps.
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        step_device()
+        if rank == 0:
+            sampler.sample()
+    sampler.samples, sampler.reasons = [], set()
+    barrier()
+
+    # ---- timed region: device-resident ----
     launches0 = _lib.kernel_launch_count()
     barrier()
     t_g, t_e, fused_tot, n_lin, n_err = 0.0, 0.0, 0, 0, 0
+    exch_ms[0] = 0.0
     wall0 = time.perf_counter()
     for _ in range(args.steps):
         tg, te, fused, Ts, regs = step_device()
@@ -347,8 +386,11 @@ def main():
         if rank == 0:
             sampler.sample()  # the GPU has been busy for the whole step that just ended
     barrier()
+    if os.environ.get("BENCH_TRACE") and rank == 0:
+        print("[trace] per step (src prepare, elev, targets+LM events ms; align_batch host ms): %s" % step_trace, file=sys.stderr)
     wall = time.perf_counter() - wall0
     launches = _lib.kernel_launch_count() - launches0
+    exchange_ms_per_step = exch_ms[0] / args.steps
     clocks = sampler.stop() if rank == 0 else None
     # per-kernel device times for the roofline block: the same steps again with CUDA events around every launch group on
     # the library stream (kept out of the region above: ~300 extra event records per step would be timed with it)
@@ -435,7 +477,9 @@ def main():
             "config": {"workload": "cfg2: 32 pairwise GICP refines of 120k-pt synthetic 64-beam scans + elevation fuse @0.1 m (1200x1200)",
                        "pairs_per_rank": n_pairs, "points_per_scan": N_POINTS, "k": K_CORR, "max_iter": MAX_ITER,
                        "parallelism": "robot-per-gpu x%d" % world,
-                       "exchange": "nccl all_gather of candidate clouds per step" if world > 1 else "none (single robot)",
+                       "exchange": ("nccl all_gather of candidate clouds per step, %d MB received per rank, overlapped with the local source-cloud "
+                                    "preparation and elevation fuse (host waited %.2f ms per step for it)" %
+                                    (world * n_pairs * N_POINTS * 12 // 1000000, exchange_ms_per_step)) if world > 1 else "none (single robot)",
                        "l2": "per-step working set (64 clouds x ~10 MB + map) exceeds the 126 MB L2; clouds are rebuilt every step"},
             "gicp": {"aligns_per_s": aligns_total / (t_g_ms * 1e-3), "ms_per_step": t_g_ms / args.steps,
                      "mean_linearize_per_align": n_lin / float(n_pairs * args.steps), "mean_error_evals_per_align": n_err / float(n_pairs * args.steps),

@@ -61,6 +61,10 @@ enum { MRSLAM_OPT_LM = 0, MRSLAM_OPT_GN = 1 };
  * `stride_floats` floats apart (3 = packed xyz, 4 = pcl::PointXYZ, 8 = pcl::PointXYZI / PointNormal). */
 mrslam_cloud_t* mrslam_cloud_create_host(const float* xyz, int n, int stride_floats);
 mrslam_cloud_t* mrslam_cloud_create_device(const float* d_xyz, int n, int stride_floats); /* device pointer (e.g. NCCL recv buffer) */
+/* `count` clouds from device pointers packed by ONE kernel launch (a loop-closure batch out of an NCCL receive buffer);
+ * out[count] receives the handles.  The inputs are consumed in stream order: they may be reused after the call returns
+ * only by work ordered after mrslam_stream(). */
+int mrslam_cloud_create_device_batch(const float* const* d_xyz, const int* n, int stride_floats, int count, mrslam_cloud_t** out);
 void mrslam_cloud_destroy(mrslam_cloud_t*);
 int mrslam_cloud_size(const mrslam_cloud_t*);
 
@@ -97,6 +101,10 @@ int mrslam_gicp_align(mrslam_gicp_t*, const float* guess16);
 /* n registrations advanced in lock step (one kernel launch per LM phase for the whole batch):
  * the loop-closure-storm entry point (BASELINE configs 2 and 4).  guesses16: n x 16 or NULL. */
 int mrslam_gicp_align_batch(mrslam_gicp_t** handles, int n, const float* guesses16);
+/* Spatial structures + covariances (fast_gicp_impl.hpp:72-90 kd-tree build, :241-297 calculate_covariances) of the source
+ * (which & 1) and / or target (which & 2) clouds of n registrations, ahead of align: lets a caller work on the clouds it
+ * already holds while the others are still in flight on NVLink.  align / align_batch skip what is already prepared. */
+int mrslam_gicp_prepare_batch(mrslam_gicp_t** handles, int n, int which);
 
 int mrslam_gicp_get_final_transformation(const mrslam_gicp_t*, float* T16);   /* getFinalTransformation (x0.cast<float>()) */
 int mrslam_gicp_get_final_transformation_d(const mrslam_gicp_t*, double* T16);

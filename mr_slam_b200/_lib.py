@@ -55,6 +55,7 @@ def _declare(L):
     L.mrslam_cloud_create_host.restype = vp
     L.mrslam_cloud_create_device.argtypes = [fp, i, i]
     L.mrslam_cloud_create_device.restype = vp
+    L.mrslam_cloud_create_device_batch.argtypes = [C.POINTER(vp), C.POINTER(C.c_int), i, i, C.POINTER(vp)]
     L.mrslam_cloud_destroy.argtypes = [vp]
     L.mrslam_cloud_size.argtypes = [vp]
     L.mrslam_cloud_knn.argtypes = [vp, i, ip, fp]
@@ -77,6 +78,7 @@ def _declare(L):
         getattr(L, "mrslam_gicp_" + name).argtypes = [vp, dp, i]
     L.mrslam_gicp_align.argtypes = [vp, fp]
     L.mrslam_gicp_align_batch.argtypes = [C.POINTER(vp), i, fp]
+    L.mrslam_gicp_prepare_batch.argtypes = [C.POINTER(vp), i, i]
     L.mrslam_gicp_get_final_transformation.argtypes = [vp, fp]
     L.mrslam_gicp_get_final_transformation_d.argtypes = [vp, dp]
     L.mrslam_gicp_has_converged.argtypes = [vp]

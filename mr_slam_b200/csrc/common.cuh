@@ -121,6 +121,26 @@ struct PinBuf {
   }
 };
 
+// Guards a pinned staging buffer that an async H2D copy reads: wait() before the host rewrites it, mark() after the copy
+// has been queued.  (Only matters when two batched calls follow each other without a stream synchronisation in between.)
+struct StageFence {
+  cudaEvent_t ev = nullptr;
+  bool pending = false;
+  int wait() {
+    if (pending) {
+      MR_CUDA(cudaEventSynchronize(ev));
+      pending = false;
+    }
+    return MRSLAM_OK;
+  }
+  int mark(cudaStream_t st) {
+    if (!ev) MR_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    MR_CUDA(cudaEventRecord(ev, st));
+    pending = true;
+    return MRSLAM_OK;
+  }
+};
+
 // ---- device helpers --------------------------------------------------------------------------
 #ifdef __CUDACC__
 constexpr unsigned FULL = 0xffffffffu;

@@ -34,6 +34,20 @@ struct Cloud {
   int refs = 1;
 
   // stage 1 (at setInput time): points into porig (device).  The Morton sort etc. is deferred to build_clouds().
+  int set_sizes(int n_) {
+    n = n_;
+    npad = ((n + TILE - 1) / TILE) * TILE;
+    ntiles = npad / TILE;
+    ntiles_pad = ((ntiles + 31) / 32) * 32;
+    if (ntiles_pad == 0) ntiles_pad = 32;
+    nsuper = (ntiles + 31) / 32;
+    nsuper_pad = ((nsuper + 31) / 32) * 32;
+    if (nsuper_pad == 0) nsuper_pad = 32;
+    cov_valid = false;
+    built = false;
+    return porig.reserve(std::max(n, 1));
+  }
+
   int set_from_device_raw(const float* d_raw, int n_, int stride) {
     cudaStream_t st = rt().stream;
     n = n_;
@@ -104,6 +118,7 @@ struct BuildScratch {
   DevBuf<unsigned> bbox;
   DevBuf<BuildDesc> d_desc;
   PinBuf<BuildDesc> h_desc;
+  StageFence fence;
 };
 static BuildScratch& build_scratch() {
   static BuildScratch s;
@@ -125,6 +140,7 @@ static int build_clouds(const std::vector<Cloud*>& clouds) {
     set_error("too many clouds in one batch (%d)", nc);
     return MRSLAM_ERR_ARG;
   }
+  MR_CHECK(S.fence.wait());
   MR_CHECK(S.h_desc.reserve(nc));
   MR_CHECK(S.d_desc.reserve(nc));
   long long total = 0;
@@ -148,6 +164,7 @@ static int build_clouds(const std::vector<Cloud*>& clouds) {
     max_super_pad = std::max(max_super_pad, c->nsuper_pad);
   }
   MR_CUDA(cudaMemcpyAsync(S.d_desc.p, S.h_desc.p, sizeof(BuildDesc) * nc, cudaMemcpyHostToDevice, st));
+  MR_CHECK(S.fence.mark(st));
   size_t tot = (size_t)std::max<long long>(total, 1);
   MR_CHECK(S.keys.reserve(tot)); MR_CHECK(S.keys_alt.reserve(tot));
   MR_CHECK(S.vals.reserve(tot)); MR_CHECK(S.vals_alt.reserve(tot));
@@ -350,6 +367,7 @@ struct BatchScratch {
   DevBuf<int> d_active;
   PinBuf<PairParams> h_pairs;
   PinBuf<KnnParams> h_knn;
+  StageFence knn_fence;
   PinBuf<int> h_active;
   PinBuf<double> h_T;    // [n][12]  staging of the transforms of the next launch
   DevBuf<double> d_T;    // [n][12]
@@ -429,20 +447,25 @@ static int ensure_built(Gicp** hs, int n) {
   return build_clouds(cs);
 }
 
-static int compute_covariances(Gicp** hs, int n) {
+// which: bit 0 = source clouds, bit 1 = target clouds
+static int compute_covariances(Gicp** hs, int n, int which = 3) {
   BatchScratch& S = scratch();
-  MR_CHECK(ensure_built(hs, n));
-  std::vector<Cloud*> todo;
+  std::vector<Cloud*> todo, all;
   std::vector<int> ks, regs;
   for (int i = 0; i < n; i++)
-    for (Cloud* c : {hs[i]->src, hs[i]->tgt}) {
+    for (int side = 0; side < 2; side++) {
+      Cloud* c = side == 0 ? hs[i]->src : hs[i]->tgt;
+      if (!(which & (1 << side)) || !c) continue;
+      all.push_back(c);
       if (c->cov_valid) continue;
       if (std::find(todo.begin(), todo.end(), c) != todo.end()) continue;
       todo.push_back(c);
       ks.push_back(hs[i]->k_corr);
       regs.push_back(hs[i]->regularization);
     }
+  MR_CHECK(build_clouds(all));
   if (todo.empty()) return MRSLAM_OK;
+  MR_CHECK(S.knn_fence.wait());
   MR_CHECK(S.h_knn.reserve(todo.size()));
   MR_CHECK(S.d_knn.reserve(todo.size()));
   // group by k (normally a single group)
@@ -464,6 +487,7 @@ static int compute_covariances(Gicp** hs, int n) {
     S.h_knn.p[pos++] = p;
   }
   MR_CUDA(cudaMemcpyAsync(S.d_knn.p, S.h_knn.p, sizeof(KnnParams) * todo.size(), cudaMemcpyHostToDevice, rt().stream));
+  MR_CHECK(S.knn_fence.mark(rt().stream));
   size_t i0 = 0;
   while (i0 < order.size()) {
     size_t i1 = i0;
@@ -588,7 +612,7 @@ static int reserve_scratch(int n) {
   MR_CHECK(S.h_T.reserve((size_t)n * 12));
   MR_CHECK(S.d_T.reserve((size_t)n * 12));
   MR_CHECK(S.h_out.reserve((size_t)n * NRED));
-  MR_CHECK(S.d_stat.reserve(4));
+  MR_CHECK(S.d_stat.reserve(8));
   return MRSLAM_OK;
 }
 
@@ -819,6 +843,53 @@ mrslam_cloud_t* mrslam_cloud_create_device(const float* d_xyz, int n, int stride
   }
   return reinterpret_cast<mrslam_cloud_t*>(c);
 }
+int mrslam_cloud_create_device_batch(const float* const* d_xyz, const int* n, int stride_floats, int count, mrslam_cloud_t** out) {
+  if (count < 0 || (count > 0 && (!d_xyz || !n || !out)) || stride_floats < 3) {
+    set_error("cloud_create_device_batch: bad arguments");
+    return MRSLAM_ERR_ARG;
+  }
+  MR_CHECK(ensure_init());
+  LOCK();
+  if (count == 0) return MRSLAM_OK;
+  static PinBuf<PackDesc> h_desc;
+  static DevBuf<PackDesc> d_desc;
+  static StageFence fence;
+  MR_CHECK(fence.wait());
+  MR_CHECK(h_desc.reserve(count));
+  MR_CHECK(d_desc.reserve(count));
+  int max_n = 0;
+  for (int i = 0; i < count; i++) {
+    out[i] = nullptr;
+    if (n[i] < 0 || (n[i] > 0 && !d_xyz[i])) {
+      set_error("cloud_create_device_batch: bad cloud %d", i);
+      for (int j = 0; j < i; j++) cloud_unref(reinterpret_cast<Cloud*>(out[j])), out[j] = nullptr;
+      return MRSLAM_ERR_ARG;
+    }
+    Cloud* c = acquire_cloud();
+    int st = c->set_sizes(n[i]);
+    if (st != MRSLAM_OK) {
+      c->release();
+      delete c;
+      for (int j = 0; j < i; j++) cloud_unref(reinterpret_cast<Cloud*>(out[j])), out[j] = nullptr;
+      return st;
+    }
+    out[i] = reinterpret_cast<mrslam_cloud_t*>(c);
+    PackDesc d;
+    d.raw = d_xyz[i]; d.porig = c->porig.p; d.n = n[i]; d.stride = stride_floats;
+    h_desc.p[i] = d;
+    max_n = std::max(max_n, n[i]);
+  }
+  if (max_n > 0) {
+    ProfScope ps(PROF_CLOUD_BUILD);
+    MR_CUDA(cudaMemcpyAsync(d_desc.p, h_desc.p, sizeof(PackDesc) * count, cudaMemcpyHostToDevice, rt().stream));
+    MR_CHECK(fence.mark(rt().stream));
+    int gx = std::max(1, std::min((max_n + 255) / 256, 128));
+    k_pack_points_batch<<<dim3(gx, count), 256, 0, rt().stream>>>(d_desc.p);
+    count_launch(1);
+    MR_CUDA(cudaGetLastError());
+  }
+  return MRSLAM_OK;
+}
 void mrslam_cloud_destroy(mrslam_cloud_t* h) {
   if (!h) return;
   LOCK();
@@ -1045,6 +1116,28 @@ int mrslam_gicp_align_batch(mrslam_gicp_t** handles, int n, const float* guesses
     }
   return align_batch(reinterpret_cast<Gicp**>(handles), n, guesses16);
 }
+int mrslam_gicp_prepare_batch(mrslam_gicp_t** handles, int n, int which) {
+  if (n < 0 || (n > 0 && !handles) || (which & ~3) || which == 0) {
+    set_error("prepare_batch: bad arguments");
+    return MRSLAM_ERR_ARG;
+  }
+  MR_CHECK(ensure_init());
+  LOCK();
+  std::vector<Gicp*> hs;
+  for (int i = 0; i < n; i++) {
+    REQUIRE(handles[i]);
+    Gicp* g = G(handles[i]);
+    if (((which & 1) && !g->src) || ((which & 2) && !g->tgt)) {
+      set_error("prepare_batch: registration %d has no %s cloud", i, ((which & 1) && !g->src) ? "source" : "target");
+      return MRSLAM_ERR_STATE;
+    }
+    hs.push_back(g);
+  }
+  if (hs.empty()) return MRSLAM_OK;
+  MR_CHECK(reserve_scratch((int)hs.size()));
+  return compute_covariances(hs.data(), (int)hs.size(), which);
+}
+
 int mrslam_gicp_align(mrslam_gicp_t* h, const float* guess16) { return mrslam_gicp_align_batch(&h, 1, guess16); }
 
 int mrslam_gicp_get_final_transformation_d(const mrslam_gicp_t* h, double* T) {
@@ -1215,8 +1308,8 @@ int mrslam_gicp_stats_enable(int on) {
   MR_CHECK(ensure_init());
   LOCK();
   BatchScratch& S = scratch();
-  MR_CHECK(S.d_stat.reserve(4));
-  MR_CUDA(cudaMemsetAsync(S.d_stat.p, 0, sizeof(unsigned long long) * 4, rt().stream));
+  MR_CHECK(S.d_stat.reserve(8));
+  MR_CUDA(cudaMemsetAsync(S.d_stat.p, 0, sizeof(unsigned long long) * 8, rt().stream));
   S.stats = on != 0;
   return MRSLAM_OK;
 }
@@ -1224,8 +1317,8 @@ int mrslam_gicp_stats_enable(int on) {
 unsigned long long mrslam_gicp_stats_get(int which) {
   LOCK();
   BatchScratch& S = scratch();
-  unsigned long long v[4] = {0, 0, 0, 0};
-  if (!S.d_stat.p || which < 0 || which > 3) return 0;
+  unsigned long long v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (!S.d_stat.p || which < 0 || which > 7) return 0;
   cudaMemcpyAsync(v, S.d_stat.p, sizeof(v), cudaMemcpyDeviceToHost, rt().stream);
   cudaStreamSynchronize(rt().stream);
   return v[which];

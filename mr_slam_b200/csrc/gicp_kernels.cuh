@@ -48,6 +48,20 @@ __global__ void k_pack_points(const float* __restrict__ raw, int n, int stride, 
   porig[i] = make_float4(p[0], p[1], p[2], 1.0f);
 }
 
+struct PackDesc {
+  const float* raw;
+  float4* porig;
+  int n, stride;
+};
+// the same for many clouds in one launch (blockIdx.y = cloud)
+__global__ void k_pack_points_batch(const PackDesc* __restrict__ descs) {
+  const PackDesc d = descs[blockIdx.y];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < d.n; i += gridDim.x * blockDim.x) {
+    const float* p = d.raw + (size_t)i * d.stride;
+    d.porig[i] = make_float4(p[0], p[1], p[2], 1.0f);
+  }
+}
+
 // ---- batched cloud build: every kernel handles all clouds of a batch (blockIdx.y = cloud) ----
 struct BuildDesc {
   const float4* porig;
@@ -514,25 +528,139 @@ __device__ __forceinline__ void knn_write_warp_list(const KnnParams& P, u64 my_k
   }
 }
 
-// one warp per query tile, queries served one by one by warp_query_knn
+// One warp per query tile; its 32 queries are served one after the other, each by the whole warp (k-best list one key
+// per lane).  The candidate tiles are found ONCE per query tile: every query's k-th neighbour lies within
+// B = max pairwise distance of the tile's own 32 points (they are k <= 32 candidates already), so only tiles whose box is
+// within B of the query tile's box can contribute to any of its queries.  Their ids and boxes stay in registers (2 per
+// lane).  A query then (1) sorts its own tile, (2) computes its point-to-box distance to every candidate -- one per lane --
+// and (3) visits candidates nearest-first (warp redux-min over (box distance | slot) keys) until the nearest unvisited box
+// is farther than its current k-th neighbour.  Exact: a skipped tile t has box distance > d_k >= every later d_k.
+// Tiles with padding points or more than KCAND candidates take the per-query two-level culling path (warp_query_knn).
+constexpr int KCAND = 64;
+#ifndef MR_KNN_SHARED
+#define MR_KNN_SHARED 1
+#endif
+
 __global__ void __launch_bounds__(128, 8) k_knn_search(const KnnParams* __restrict__ plist) {
+  __shared__ int s_list[4][KCAND];
   const KnnParams P = plist[blockIdx.y];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int qt = blockIdx.x * 4 + wib;
   if (qt >= P.ntiles) return;  // warp-uniform; no block-level barrier in this kernel
   const float4 qmine = P.psort[(size_t)qt * TILE + lane];
+  const int k = P.k;
   unsigned long long tiles_done = 0, inserts = 0;
+  bool shared_ok = MR_KNN_SHARED && (qt + 1) * TILE <= P.n;
+  int ncand = 0;
+  if (shared_ok) {
+    const int ntp = P.ntiles_pad, nsp = P.nsuper_pad;
+    float B = 0.0f;
+#pragma unroll 4
+    for (int j = 0; j < TILE; j++) {
+      const float px = __shfl_sync(FULL, qmine.x, j), py = __shfl_sync(FULL, qmine.y, j), pz = __shfl_sync(FULL, qmine.z, j);
+      B = fmaxf(B, dist2(qmine.x, qmine.y, qmine.z, px, py, pz));
+    }
+    B = warp_max(B);
+    float a[6];
+#pragma unroll
+    for (int c = 0; c < 6; c++) a[c] = P.tb[(size_t)c * ntp + qt];
 #pragma unroll 1
-  for (int qi = 0; qi < TILE; qi++) {
-    const float qx = __shfl_sync(FULL, qmine.x, qi), qy = __shfl_sync(FULL, qmine.y, qi), qz = __shfl_sync(FULL, qmine.z, qi);
-    const int qidx = __shfl_sync(FULL, __float_as_int(qmine.w), qi);
-    if (qidx == PAD_IDX) continue;
-    const u64 my_key = warp_query_knn(P, qx, qy, qz, qt, P.k, lane, tiles_done, inserts);
-    knn_write_warp_list(P, my_key, (size_t)qt * TILE + qi, qidx, P.k, lane);
+    for (int s0 = 0; s0 < P.nsuper && shared_ok; s0 += 32) {
+      const int s = s0 + lane;
+      const float bs = (s < P.nsuper) ? box_box_dist2(a, P.sb, nsp, s) : INFINITY;
+      unsigned ms = __ballot_sync(FULL, bs * CULL_SAFETY <= B);
+      while (ms) {
+        const int js = __ffs(ms) - 1;
+        ms &= ms - 1;
+        const int t = (s0 + js) * 32 + lane;
+        const bool pass = t < P.ntiles && t != qt && box_box_dist2(a, P.tb, ntp, t) * CULL_SAFETY <= B;
+        const unsigned mt = __ballot_sync(FULL, pass);
+        const int pos = ncand + __popc(mt & ((1u << lane) - 1u));
+        if (pass && pos < KCAND) s_list[wib][pos] = t;
+        ncand += __popc(mt);
+        if (ncand > KCAND) {
+          shared_ok = false;
+          break;
+        }
+      }
+    }
+    __syncwarp();
+  }
+  if (shared_ok) {
+    const int ntp = P.ntiles_pad;
+    const int t0 = (lane < ncand) ? s_list[wib][lane] : -1;
+    const int t1 = (lane + 32 < ncand) ? s_list[wib][lane + 32] : -1;
+    float b0[6], b1[6];
+#pragma unroll
+    for (int c = 0; c < 6; c++) {
+      b0[c] = (t0 >= 0) ? P.tb[(size_t)c * ntp + t0] : 0.0f;
+      b1[c] = (t1 >= 0) ? P.tb[(size_t)c * ntp + t1] : 0.0f;
+    }
+    constexpr unsigned NONE = 0xffffffffu;
+#pragma unroll 1
+    for (int qi = 0; qi < TILE; qi++) {
+      const float qx = __shfl_sync(FULL, qmine.x, qi), qy = __shfl_sync(FULL, qmine.y, qi), qz = __shfl_sync(FULL, qmine.z, qi);
+      const int qidx = __shfl_sync(FULL, __float_as_int(qmine.w), qi);
+      // own tile: all 32 candidates enter the (empty) list -> one bitonic sort instead of 32 insertions
+      u64 my_key = warp_sort_keys(make_key(dist2(qx, qy, qz, qmine.x, qmine.y, qmine.z), __float_as_int(qmine.w)), lane);
+      u64 wkey = __shfl_sync(FULL, my_key, k - 1);
+      tiles_done++;
+      // per-query distance to the candidate boxes; the low 6 bits of the (non-negative) float carry the slot, which rounds
+      // the box distance DOWN by < 2^-17 relative: conservative for the cull test
+      unsigned k0 = NONE, k1 = NONE;
+      if (t0 >= 0) {
+        const float gx = fmaxf(0.0f, fmaxf(b0[0] - qx, qx - b0[3])), gy = fmaxf(0.0f, fmaxf(b0[1] - qy, qy - b0[4])),
+                    gz = fmaxf(0.0f, fmaxf(b0[2] - qz, qz - b0[5]));
+        k0 = (__float_as_uint(gx * gx + gy * gy + gz * gz) & ~63u) | (unsigned)lane;
+      }
+      if (t1 >= 0) {
+        const float gx = fmaxf(0.0f, fmaxf(b1[0] - qx, qx - b1[3])), gy = fmaxf(0.0f, fmaxf(b1[1] - qy, qy - b1[4])),
+                    gz = fmaxf(0.0f, fmaxf(b1[2] - qz, qz - b1[5]));
+        k1 = (__float_as_uint(gx * gx + gy * gy + gz * gz) & ~63u) | (unsigned)(32 + lane);
+      }
+      while (true) {
+        const unsigned m = __reduce_min_sync(FULL, min(k0, k1));
+        if (m == NONE || __uint_as_float(m & ~63u) * CULL_SAFETY > key_dist(wkey)) break;
+        const int slot = (int)(m & 63u), owner = slot & 31;
+        const int ta = __shfl_sync(FULL, t0, owner), tb2 = __shfl_sync(FULL, t1, owner);
+        const int t = (slot < 32) ? ta : tb2;
+        if (lane == owner) {
+          if (slot < 32) k0 = NONE;
+          else k1 = NONE;
+        }
+        const float4 c = P.psort[(size_t)t * TILE + lane];
+        const u64 ckey = make_key(dist2(qx, qy, qz, c.x, c.y, c.z), __float_as_int(c.w));
+        unsigned mm = __ballot_sync(FULL, ckey < wkey);
+        if (mm) {
+          while (mm) {
+            const int j = __ffs(mm) - 1;
+            mm &= mm - 1;
+            const u64 ck = __shfl_sync(FULL, ckey, j);
+            const u64 up = __shfl_up_sync(FULL, my_key, 1);
+            if (ck < my_key) my_key = (lane > 0 && ck < up) ? up : ck;
+            inserts++;
+          }
+          wkey = __shfl_sync(FULL, my_key, k - 1);
+        }
+        tiles_done++;
+      }
+      knn_write_warp_list(P, my_key, (size_t)qt * TILE + qi, qidx, k, lane);
+    }
+  } else {
+#pragma unroll 1
+    for (int qi = 0; qi < TILE; qi++) {
+      const float qx = __shfl_sync(FULL, qmine.x, qi), qy = __shfl_sync(FULL, qmine.y, qi), qz = __shfl_sync(FULL, qmine.z, qi);
+      const int qidx = __shfl_sync(FULL, __float_as_int(qmine.w), qi);
+      if (qidx == PAD_IDX) continue;
+      const u64 my_key = warp_query_knn(P, qx, qy, qz, qt, k, lane, tiles_done, inserts);
+      knn_write_warp_list(P, my_key, (size_t)qt * TILE + qi, qidx, k, lane);
+    }
   }
   if (P.stat_pairs && lane == 0) {
     atomicAdd(P.stat_pairs, tiles_done * 32ull);
     atomicAdd(P.stat_pairs + 2, inserts);
+    atomicAdd(P.stat_pairs + 4, shared_ok ? 0ull : 1ull);
+    atomicAdd(P.stat_pairs + 5, (unsigned long long)ncand);
   }
 }
 

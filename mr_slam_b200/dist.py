@@ -30,15 +30,21 @@ def requested_targets(pairs, world_size):
     return [sorted(s) for s in need]
 
 
-def allgather_slots(local_slots):
+def allgather_slots(local_slots, async_op=False):
     """local_slots: tensor [S, N, 3] (same S, N on every rank; pad with NaN rows if a robot contributes fewer clouds).
-    Returns [world, S, N, 3] on every rank.  One collective per loop-closure batch."""
+    Returns [world, S, N, 3] on every rank.  One collective per loop-closure batch.
+    async_op=True returns (out, work): the collective runs on the backend's own stream while the caller prepares the clouds
+    it already holds; `work.wait()` orders the current stream after it (work is None when there is nothing to wait for)."""
     if not dist.is_initialized() or dist.get_world_size() == 1:
-        return local_slots.unsqueeze(0)
+        out = local_slots.unsqueeze(0)
+        return (out, None) if async_op else out
     world = dist.get_world_size()
     out = torch.empty((world,) + tuple(local_slots.shape), dtype=local_slots.dtype, device=local_slots.device)
-    dist.all_gather(list(out.unbind(0)), local_slots.contiguous())  # views into `out`; works for gloo and nccl
-    return out
+    if local_slots.is_cuda:
+        work = dist.all_gather_into_tensor(out, local_slots.contiguous(), async_op=async_op)  # one ncclAllGather, no staging copy
+    else:
+        work = dist.all_gather(list(out.unbind(0)), local_slots.contiguous(), async_op=async_op)  # gloo: views into `out`
+    return (out, work) if async_op else out
 
 
 def gather_results(local_T, local_ids, n_total):

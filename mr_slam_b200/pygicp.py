@@ -42,6 +42,21 @@ class Cloud:
         if not self._h:
             raise _lib.MrSlamError(L.mrslam_last_error().decode())
 
+    @classmethod
+    def from_device_batch(cls, device_ptrs, n, stride=3):
+        """One launch packs `len(device_ptrs)` clouds of n points each (mrslam_cloud_create_device_batch)."""
+        cnt = len(device_ptrs)
+        ptrs = (C.c_void_p * cnt)(*[int(p) for p in device_ptrs])
+        ns = (C.c_int * cnt)(*([int(n)] * cnt if np.isscalar(n) else [int(v) for v in n]))
+        out = (C.c_void_p * cnt)()
+        check(lib().mrslam_cloud_create_device_batch(ptrs, ns, int(stride), cnt, out))
+        clouds = []
+        for h in out:
+            c = cls.__new__(cls)
+            c._h = h
+            clouds.append(c)
+        return clouds
+
     def __len__(self):
         return lib().mrslam_cloud_size(self._h)
 
@@ -221,6 +236,16 @@ def align_batch(regs, initial_guesses=None):
     if s not in (0, -4):
         check(s)
     return np.stack([r.get_final_transformation() for r in regs])
+
+
+SOURCE, TARGET = 1, 2
+
+
+def prepare_batch(regs, which=SOURCE | TARGET):
+    """Build the spatial tiles and covariances of the source and/or target clouds ahead of align_batch."""
+    n = len(regs)
+    arr = (C.c_void_p * n)(*[r._h for r in regs])
+    check(lib().mrslam_gicp_prepare_batch(arr, n, int(which)))
 
 
 def fitness_batch(regs, max_range=DBL_MAX):

@@ -185,6 +185,44 @@ def test_gauss_newton_and_batch_equal_single(gpu):
     assert np.abs(g.align(T_guess.astype(np.float32)) - o.align(T_guess.astype(np.float32))).max() < TOL_T
 
 
+def test_device_batch_create_and_prepare_equal_plain_path(gpu):
+    """clouds packed from device pointers by one launch + covariances prepared ahead (source first, targets later, as the
+    overlapped multi-GPU step does) must give bit-identical transforms to the plain host-buffer path"""
+    import torch
+    pairs = [synth.make_pair(i, "vlp16")[:4] for i in range(3)]
+    guesses = np.stack([p[3].astype(np.float32) for p in pairs])
+    plain = pygicp.align_batch([make(pygicp.FastGICP, p[0], p[1]) for p in pairs], guesses)
+    # ragged sizes: every cloud keeps its own length
+    src_t = [torch.from_numpy(np.ascontiguousarray(p[0], np.float32)).cuda() for p in pairs]
+    tgt_t = [torch.from_numpy(np.ascontiguousarray(p[1], np.float32)).cuda() for p in pairs]
+    torch.cuda.synchronize()
+    regs = []
+    for _ in pairs:
+        g = pygicp.FastGICP()
+        g.set_correspondence_randomness(15)
+        g.set_max_correspondence_distance(100.0)
+        g.set_maximum_iterations(50)
+        g.set_transformation_epsilon(1e-3)
+        regs.append(g)
+    with pytest.raises(Exception):
+        pygicp.prepare_batch(regs, pygicp.SOURCE)     # no source set yet
+    sc = pygicp.Cloud.from_device_batch([t.data_ptr() for t in src_t], [t.shape[0] for t in src_t], 3)
+    assert [len(c) for c in sc] == [t.shape[0] for t in src_t]
+    for g, c in zip(regs, sc):
+        g.set_input_source(c)
+    pygicp.prepare_batch(regs, pygicp.SOURCE)
+    tc = pygicp.Cloud.from_device_batch([t.data_ptr() for t in tgt_t], [t.shape[0] for t in tgt_t], 3)
+    for g, c in zip(regs, tc):
+        g.set_input_target(c)
+    pygicp.prepare_batch(regs, pygicp.TARGET)
+    Ts = pygicp.align_batch(regs, guesses)
+    assert np.array_equal(Ts, plain)
+    covs = regs[0].get_source_covariances(len(sc[0]))
+    ref = make(pygicp.FastGICP, pairs[0][0], pairs[0][1]).get_source_covariances(len(sc[0]))
+    assert np.array_equal(covs, ref)
+    assert pygicp.Cloud.from_device_batch([], 0) == []
+
+
 def test_edge_cases(gpu):
     src, tgt = synth.make_pair(0, "vlp16")[:2]
     g = pygicp.FastGICP()
