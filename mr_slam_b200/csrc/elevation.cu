@@ -79,18 +79,24 @@ __global__ void k_elev_fill(float* elevation, float* variance, float* intensity,
   B[i] = 0;
 }
 
-// G_Clear_map(start, shift, row_flag): gpu_process.cu:254-276
-__global__ void k_elev_clear_region(float* elevation, float* variance, float* intensity, int* R, int* G, int* B, int L, int start,
-                                    int shift, int row_flag) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= L * shift) return;
-  size_t c = row_flag ? (size_t)start * L + i : (size_t)(i / shift) * L + i % shift + start;
-  intensity[c] = 0;
-  elevation[c] = -10;
-  variance[c] = -10;
-  R[c] = 0;
-  G[c] = 0;
-  B[c] = 0;
+// G_Clear_map(start, shift, row_flag): gpu_process.cu:254-276.  A Move clears up to four strips (two axes, each possibly
+// wrapping around the ring buffer): they are handled by ONE launch, blockIdx.y = strip.
+struct ClearRegions {
+  int start[4], shift[4], row_flag[4];
+  int count;
+};
+__global__ void k_elev_clear_region(float* elevation, float* variance, float* intensity, int* R, int* G, int* B, int L, ClearRegions cr) {
+  const int r = blockIdx.y;
+  const int start = cr.start[r], shift = cr.shift[r], row_flag = cr.row_flag[r];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < L * shift; i += gridDim.x * blockDim.x) {
+    size_t c = row_flag ? (size_t)start * L + i : (size_t)(i / shift) * L + i % shift + start;
+    intensity[c] = 0;
+    elevation[c] = -10;
+    variance[c] = -10;
+    R[c] = 0;
+    G[c] = 0;
+    B[c] = 0;
+  }
 }
 
 // G_pointsprocess.  Outputs -1 everywhere for dropped points.  keys[i] = map_index or `cells` (sorts last).
@@ -177,6 +183,19 @@ __global__ void k_elev_gather(const int* __restrict__ order, int n, const float*
 
 // One thread per run of equal cell keys (points inside a run are in ascending point index because the radix sort is
 // stable): the sequential recurrence of G_fuse, gpu_process.cu:477-535, over the gathered (height, variance) stream.
+// The recurrence is a loop-carried dependency, so the kernel's duration is the longest run times the latency of one
+// update.  Two things keep that latency short: (1) the end of the run is found up front (galloping + binary search on the
+// sorted keys), so the loads of the next points do not sit behind the loop-exit test and are issued four at a time;
+// (2) the Mahalanobis test |h-e|/sqrt(v) > 5 is decided from |h-e|*rsqrt(v) (relative error < 2^-20) unless that lands
+// within 1e-4 of the threshold -- only then the IEEE sqrt and division of the reference expression are evaluated.  The
+// decision, and with it every stored value, is identical to the reference's.
+__device__ __forceinline__ bool elev_mahal_gt5(float h, float e, float v) {
+  const float d = fabsf(h - e);
+  const float approx = d * rsqrtf(v);
+  if (fabsf(approx - 5.f) > 1e-4f) return approx > 5.f;  // (NaN / inf-inf fall through to the exact expression)
+  return d / sqrtf(v) > 5.f;
+}
+
 __global__ void k_elev_fuse_segments(const int* __restrict__ keys, int n, int cells, const float2* __restrict__ hv,
                                      const int4* __restrict__ col, float* __restrict__ elevation, float* __restrict__ variance,
                                      float* __restrict__ intensity, int* __restrict__ R, int* __restrict__ G, int* __restrict__ B,
@@ -186,29 +205,48 @@ __global__ void k_elev_fuse_segments(const int* __restrict__ keys, int n, int ce
   const int c = keys[i];
   if (c >= cells) return;
   if (i > 0 && keys[i - 1] == c) return;  // not the head of a run
+  // end of the run: first position whose key differs
+  int lo = i, step = 1;
+  while (lo + step < n && keys[lo + step] == c) {
+    lo += step;
+    step <<= 1;
+  }
+  int hi = min(lo + step, n);  // keys[lo] == c, keys[hi] != c (or hi == n)
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (keys[mid] == c) lo = mid;
+    else hi = mid;
+  }
+  const int end = hi;
   float e = elevation[c], v = variance[c];
   float ci = 0.f;
   int cr = 0, cg = 0, cb = 0;
   bool colour_written = false;
-  int cnt = 0;
-  for (int j = i; j < n && keys[j] == c; j++) {
-    const float2 m = hv[j];
-    const float h = m.x, hvv = m.y;
-    cnt++;
-    bool colour = false;
-    int4 cc = make_int4(0, 0, 0, 0);
-    if (col) {
-      cc = col[j];
-      colour = cc.x != 0 && cc.y != 0 && cc.z != 0 && __int_as_float(cc.w) != 0.f;
+  for (int j0 = i; j0 < end; j0 += 4) {
+    float2 m4[4];
+    int4 c4[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int j = min(j0 + u, end - 1);
+      m4[u] = hv[j];
+      if (col) c4[u] = col[j];
     }
-    bool wc = false;
-    if (e == -10.f) {
-      e = h;
-      v = hvv;
-      wc = colour;
-    } else {
-      const float md = fabsf(h - e) / sqrtf(v);
-      if (md > 5.f) {
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      if (j0 + u >= end) break;
+      const float h = m4[u].x, hvv = m4[u].y;
+      bool colour = false;
+      int4 cc = make_int4(0, 0, 0, 0);
+      if (col) {
+        cc = c4[u];
+        colour = cc.x != 0 && cc.y != 0 && cc.z != 0 && __int_as_float(cc.w) != 0.f;
+      }
+      bool wc = false;
+      if (e == -10.f) {
+        e = h;
+        v = hvv;
+        wc = colour;
+      } else if (elev_mahal_gt5(h, e, v)) {
         if (e < h) {
           e = h;
           v = hvv;
@@ -221,13 +259,13 @@ __global__ void k_elev_fuse_segments(const int* __restrict__ keys, int n, int ce
         v = nv;
         wc = colour;
       }
-    }
-    if (wc) {
-      ci = __int_as_float(cc.w);
-      cr = cc.x;
-      cg = cc.y;
-      cb = cc.z;
-      colour_written = true;
+      if (wc) {
+        ci = __int_as_float(cc.w);
+        cr = cc.x;
+        cg = cc.y;
+        cb = cc.z;
+        colour_written = true;
+      }
     }
   }
   elevation[c] = e;
@@ -238,7 +276,7 @@ __global__ void k_elev_fuse_segments(const int* __restrict__ keys, int n, int ce
     G[c] = cg;
     B[c] = cb;
   }
-  if (n_fused) atomicAdd(n_fused, (unsigned long long)cnt);
+  if (n_fused) atomicAdd(n_fused, (unsigned long long)(end - i));
 }
 
 // tail of G_fuse (gpu_process.cu:531-532): every cell, including empty ones
@@ -438,12 +476,26 @@ int mrslam_elev_move(mrslam_elev_t* h, const float* pos, float resolution, int l
   index_shift(ishift, pshift, resolution);
   float ashift[2];
   for (int i = 0; i < 2; i++) ashift[i] = (float)ishift[i] * resolution;
+  ClearRegions cr;
+  cr.count = 0;
+  int max_cnt = 0;
+  auto flush_clears = [&]() {
+    if (cr.count == 0) return;
+    k_elev_clear_region<<<dim3((max_cnt + 255) / 256, cr.count), 256, 0, st>>>(m->elevation.p, m->variance.p, m->intensity.p, m->R.p,
+                                                                                m->G.p, m->B.p, length, cr);
+    count_launch(1);
+    cr.count = 0;
+    max_cnt = 0;
+  };
+  // strips of one axis never overlap each other; a row strip and a column strip may, but both write the same constants
   auto clear = [&](int start, int ncell, int row) {
     int cnt = ncell * length;
     if (cnt <= 0) return;
-    k_elev_clear_region<<<(cnt + 255) / 256, 256, 0, st>>>(m->elevation.p, m->variance.p, m->intensity.p, m->R.p, m->G.p, m->B.p, length,
-                                                          start, ncell, row);
-    count_launch(1);
+    cr.start[cr.count] = start;
+    cr.shift[cr.count] = ncell;
+    cr.row_flag[cr.count] = row;
+    cr.count++;
+    max_cnt = std::max(max_cnt, cnt);
   };
   for (int i = 0; i < 2; i++) {
     if (ishift[i] != 0) {
@@ -472,6 +524,7 @@ int mrslam_elev_move(mrslam_elev_t* h, const float* pos, float resolution, int l
     hs[i] = index_to_range(hs[i], length);
     hc[i] = position_to_range(hc[i], ashift[i], resolution);
   }
+  flush_clears();
   MR_CUDA(cudaGetLastError());
   m->g.cx = hc[0]; m->g.cy = hc[1];
   m->g.sx = hs[0]; m->g.sy = hs[1];

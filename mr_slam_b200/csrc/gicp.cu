@@ -182,9 +182,9 @@ static int build_clouds(const std::vector<Cloud*>& clouds) {
     cub::DoubleBuffer<unsigned long long> dk(S.keys.p, S.keys_alt.p);
     cub::DoubleBuffer<int> dv(S.vals.p, S.vals_alt.p);
     size_t tmp = 0;
-    MR_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp, dk, dv, (int)total, 0, bits, st));
+    MR_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp, dk, dv, (int)total, KEY_DROP_BITS, bits, st));
     MR_CHECK(S.cubtmp.reserve(tmp));
-    MR_CUDA(cub::DeviceRadixSort::SortPairs(S.cubtmp.p, tmp, dk, dv, (int)total, 0, bits, st));
+    MR_CUDA(cub::DeviceRadixSort::SortPairs(S.cubtmp.p, tmp, dk, dv, (int)total, KEY_DROP_BITS, bits, st));
     order = dv.Current();
     keys_sorted = dk.Current();
   }
@@ -196,6 +196,7 @@ static int build_clouds(const std::vector<Cloud*>& clouds) {
   return MRSLAM_OK;
 }
 
+static bool scratch_stats_enabled();
 static int dispatch_knn(int k, const KnnParams* d_params, int nproblems, int max_tiles, bool with_cov) {
   if (k < 1 || k > 32) {
     set_error("k_correspondences must be in 1..32 (got %d)", k);
@@ -205,7 +206,8 @@ static int dispatch_knn(int k, const KnnParams* d_params, int nproblems, int max
   dim3 grid((max_tiles + 3) / 4, nproblems);
   {
     ProfScope ps(PROF_KNN_SEARCH);
-    k_knn_search<<<grid, 128, 0, rt().stream>>>(d_params);
+    if (scratch_stats_enabled()) k_knn_search<true><<<grid, 128, 0, rt().stream>>>(d_params);
+    else k_knn_search<false><<<grid, 128, 0, rt().stream>>>(d_params);
   }
   count_launch(1);
   if (with_cov) {
@@ -380,6 +382,7 @@ static BatchScratch& scratch() {
   return s;
 }
 
+static bool scratch_stats_enabled() { return scratch().stats; }
 static std::vector<Gicp::PairBufs*>& pair_pool() {
   static std::vector<Gicp::PairBufs*> p;
   return p;

@@ -130,6 +130,11 @@ __device__ __forceinline__ unsigned long long spread16(unsigned v) {  // 16 bits
 #ifndef MR_HILBERT
 #define MR_HILBERT 1
 #endif
+// The batched radix sort skips the lowest KEY_DROP_BITS bits of the curve key (2 per axis: cells of extent/2^14, ~1 cm for
+// a 200 m scan) so that (cloud id | key) fits six 8-bit passes instead of seven; ties keep input order (stable sort).  Any
+// order is correct for the exact searches -- the curve only makes tiles compact.
+constexpr int KEY_DROP_BITS = 6;
+constexpr unsigned long long KEY48_SORTED_MASK = 0xffffffffffffull & ~((1ull << KEY_DROP_BITS) - 1ull);
 // 48-bit space-filling-curve key of a point in the cloud's bounding cube (16 bits per axis): Hilbert order (Skilling's
 // axes-to-transpose transform + bit interleave) keeps 32 consecutive points in tighter boxes than Morton order does.
 __device__ __forceinline__ unsigned long long morton48(float x, float y, float z, float mnx, float mny, float mnz, float s) {
@@ -195,7 +200,7 @@ __global__ void k_gather_tiles(const BuildDesc* __restrict__ descs, const int* _
       int o = order[s];
       v = D.porig[o];
       v.w = __int_as_float(o);
-      D.skeys[s] = keys_sorted[D.offset + s] & 0xffffffffffffull;
+      D.skeys[s] = keys_sorted[D.offset + s] & KEY48_SORTED_MASK;
       mn[0] = mx[0] = v.x; mn[1] = mx[1] = v.y; mn[2] = mx[2] = v.z;
     } else {
       v = make_float4(PAD_COORD, PAD_COORD, PAD_COORD, __int_as_float(PAD_IDX));
@@ -541,6 +546,7 @@ constexpr int KCAND = 64;
 #define MR_KNN_SHARED 1
 #endif
 
+template <bool STATS>
 __global__ void __launch_bounds__(128, 8) k_knn_search(const KnnParams* __restrict__ plist) {
   __shared__ int s_list[4][KCAND];
   const KnnParams P = plist[blockIdx.y];
@@ -604,7 +610,7 @@ __global__ void __launch_bounds__(128, 8) k_knn_search(const KnnParams* __restri
       // own tile: all 32 candidates enter the (empty) list -> one bitonic sort instead of 32 insertions
       u64 my_key = warp_sort_keys(make_key(dist2(qx, qy, qz, qmine.x, qmine.y, qmine.z), __float_as_int(qmine.w)), lane);
       u64 wkey = __shfl_sync(FULL, my_key, k - 1);
-      tiles_done++;
+      if (STATS) tiles_done++;
       // per-query distance to the candidate boxes; the low 6 bits of the (non-negative) float carry the slot, which rounds
       // the box distance DOWN by < 2^-17 relative: conservative for the cull test
       unsigned k0 = NONE, k1 = NONE;
@@ -638,11 +644,11 @@ __global__ void __launch_bounds__(128, 8) k_knn_search(const KnnParams* __restri
             const u64 ck = __shfl_sync(FULL, ckey, j);
             const u64 up = __shfl_up_sync(FULL, my_key, 1);
             if (ck < my_key) my_key = (lane > 0 && ck < up) ? up : ck;
-            inserts++;
+            if (STATS) inserts++;
           }
           wkey = __shfl_sync(FULL, my_key, k - 1);
         }
-        tiles_done++;
+        if (STATS) tiles_done++;
       }
       knn_write_warp_list(P, my_key, (size_t)qt * TILE + qi, qidx, k, lane);
     }
@@ -656,7 +662,7 @@ __global__ void __launch_bounds__(128, 8) k_knn_search(const KnnParams* __restri
       knn_write_warp_list(P, my_key, (size_t)qt * TILE + qi, qidx, k, lane);
     }
   }
-  if (P.stat_pairs && lane == 0) {
+  if (STATS && P.stat_pairs && lane == 0) {
     atomicAdd(P.stat_pairs, tiles_done * 32ull);
     atomicAdd(P.stat_pairs + 2, inserts);
     atomicAdd(P.stat_pairs + 4, shared_ok ? 0ull : 1ull);
@@ -957,7 +963,7 @@ __global__ void __launch_bounds__(128) k_nn1_search(const PairParams* __restrict
       // first pass: the target is sorted by Morton key, so a binary search for the query's key lands next to points that
       // are (usually) spatially close -- a seed that costs ~17 probes per lane instead of a full per-query search
       const float mnx = P.tgt_qp[0], mny = P.tgt_qp[1], mnz = P.tgt_qp[2], sc = P.tgt_qp[3];
-      const unsigned long long kq = morton48(qx, qy, qz, mnx, mny, mnz, sc);
+      const unsigned long long kq = morton48(qx, qy, qz, mnx, mny, mnz, sc) & KEY48_SORTED_MASK;
       int lo = 0, hi = P.tgt_n;  // first position whose key is >= kq
       while (lo < hi) {
         const int mid = (lo + hi) >> 1;
