@@ -194,6 +194,9 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # NCCL_DEBUG=VERSION (the image default on some boxes) prints a banner on stdout, which must carry the JSON line only
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     _lib.init(local_rank)
     L = _lib.lib()
@@ -310,7 +313,10 @@ def main():
             print("[debug] host ms: " + ", ".join("%s %.2f" % (n_, 1e3 * (tm[i + 1] - tm[i])) for i, n_ in enumerate(names)) +
                   "; events: src prepare %.2f elev %.2f targets+LM %.2f ms; iters %s" %
                   (e0.elapsed_time(e1), t_elev, e2.elapsed_time(e3), [r.num_iterations() for r in regs]), file=sys.stderr)
-        return t_gicp, t_elev, fused, Ts, regs
+        counts = [r.eval_counts() for r in regs]
+        # the registrations (and their clouds) are released here, like ICPCheck's locals: the library recycles their device
+        # buffers for the next batch -- holding them across steps would make every other step allocate 64 fresh clouds
+        return t_gicp, t_elev, fused, Ts, (sum(c[0] for c in counts), sum(c[1] for c in counts))
 
     def step_e2e():
         """same step through the C-ABI with HOST buffers (pinned): H2D of every cloud, D2H of the results"""
@@ -355,9 +361,8 @@ def main():
         return float(t.item())
 
     # ---- warm-up (also grows the memory pools) ----
-    # The clock sampler is started and exercised here too: the FIRST NVML query of a process was measured to stall the CUDA
-    # calls of the following step by 50-200 ms on some boxes (lazy NVML/driver initialisation); the samples taken during the
-    # warm-up are discarded, the ones reported are taken between the timed steps.
+    # The clock sampler is started and exercised here too, so that NVML's lazy initialisation happens outside the timed
+    # region; the samples taken during the warm-up are discarded, the ones reported are taken between the timed steps.
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -375,14 +380,12 @@ def main():
     exch_ms[0] = 0.0
     wall0 = time.perf_counter()
     for _ in range(args.steps):
-        tg, te, fused, Ts, regs = step_device()
+        tg, te, fused, Ts, (a, b) = step_device()
         t_g += tg
         t_e += te
         fused_tot += fused
-        for r in regs:
-            a, b = r.eval_counts()
-            n_lin += a
-            n_err += b
+        n_lin += a
+        n_err += b
         if rank == 0:
             sampler.sample()  # the GPU has been busy for the whole step that just ended
     barrier()
@@ -399,12 +402,10 @@ def main():
     p_lin = p_err = 0
     tgp = 0.0
     for _ in range(PROF_STEPS):
-        tg_, _te, _f, _Ts, regs_ = step_device()
+        tg_, _te, _f, _Ts, (a, b) = step_device()
         tgp += tg_
-        for r in regs_:
-            a, b = r.eval_counts()
-            p_lin += a
-            p_err += b
+        p_lin += a
+        p_err += b
     prof = _lib.prof_get()
     _lib.prof_enable(False)
     barrier()

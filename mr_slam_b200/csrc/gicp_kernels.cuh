@@ -427,8 +427,8 @@ __device__ __forceinline__ u64 warp_sort_keys(u64 key, int lane) {
     for (int stride = size >> 1; stride > 0; stride >>= 1) {
       const u64 other = __shfl_xor_sync(FULL, key, stride);
       const bool take_min = ((lane & size) == 0) == ((lane & stride) == 0);
-      const u64 lo = key < other ? key : other, hi = key < other ? other : key;
-      key = take_min ? lo : hi;
+      // keep `key` when it already is the wanted one of the pair (keys are distinct or identical: ties are harmless)
+      key = ((key < other) == take_min) ? key : other;
     }
   }
   return key;
@@ -627,13 +627,10 @@ __global__ void __launch_bounds__(128, 8) k_knn_search(const KnnParams* __restri
       while (true) {
         const unsigned m = __reduce_min_sync(FULL, min(k0, k1));
         if (m == NONE || __uint_as_float(m & ~63u) * CULL_SAFETY > key_dist(wkey)) break;
-        const int slot = (int)(m & 63u), owner = slot & 31;
-        const int ta = __shfl_sync(FULL, t0, owner), tb2 = __shfl_sync(FULL, t1, owner);
-        const int t = (slot < 32) ? ta : tb2;
-        if (lane == owner) {
-          if (slot < 32) k0 = NONE;
-          else k1 = NONE;
-        }
+        const int slot = (int)(m & 63u);
+        const int t = s_list[wib][slot];
+        if (slot == lane) k0 = NONE;
+        if (slot == lane + 32) k1 = NONE;
         const float4 c = P.psort[(size_t)t * TILE + lane];
         const u64 ckey = make_key(dist2(qx, qy, qz, c.x, c.y, c.z), __float_as_int(c.w));
         unsigned mm = __ballot_sync(FULL, ckey < wkey);
