@@ -34,6 +34,7 @@ N_PAIRS = 32
 N_POINTS = 120000
 K_CORR, MAX_CORR, MAX_ITER, TRANS_EPS = 15, 100.0, 50, 1e-3
 ELEV_L, ELEV_RES = 1200, 0.1
+KNN_DRAM_BYTES_PER_CLOUD = (16.160256e6 + 5.948416e6) / 8  # ncu --set full, profiles/r1_knn_search_v3.ncu-rep (8 clouds of 120k pts)
 
 
 def env_int(name, default):
@@ -242,6 +243,8 @@ def main():
         return (e["T"], z0 - 5.0, z0 + 5.0, e["min_r"], e["beam_a"], e["beam_c"], e["sensorJacobian"], e["rotationVariance"],
                 e["C_SB_transpose"], e["P_mul_C_BM_transpose"], e["B_r_BS_skew"])
 
+    elev_frames = [elevation.ElevationMap.make_frame(soa_dev[i][0], soa_dev[i][1], soa_dev[i][2], N_POINTS, *elev_args(i), near_filter=True,
+                                                     position=pairs[i]["pose"][:3, 3].astype(np.float32)) for i in range(n_pairs)]
     ev = lambda: torch.cuda.Event(enable_timing=True)
     exch_ms = [0.0]
     step_trace = []
@@ -278,9 +281,12 @@ def main():
         mark()
         with torch.cuda.stream(lib_stream):
             e1.record()
-        for i in range(n_pairs):
-            emap.Move(pairs[i]["pose"][:3, 3].astype(np.float32), ELEV_RES, ELEV_L)
-            emap.process_fuse_device(soa_dev[i][0], soa_dev[i][1], soa_dev[i][2], N_POINTS, *elev_args(i), near_filter=True, want_count=False)
+        if "perframe" in flow:
+            for i in range(n_pairs):
+                emap.Move(pairs[i]["pose"][:3, 3].astype(np.float32), ELEV_RES, ELEV_L)
+                emap.process_fuse_device(soa_dev[i][0], soa_dev[i][1], soa_dev[i][2], N_POINTS, *elev_args(i), near_filter=True, want_count=False)
+        else:  # the robot's 32 scans replayed into its map by one call (frames pipelined over two streams inside the library)
+            emap.process_fuse_device_batch(elev_frames, ELEV_RES, ELEV_L)
         with torch.cuda.stream(lib_stream):
             e2.record()
         mark()
@@ -465,7 +471,10 @@ def main():
         gd = groups[dom]
         achieved = gd["bytes"] / (gd["ms"] * 1e-3) / 1e9 if gd["ms"] > 0 else 0.0
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                    "traffic": None, "peak_source": peak_src,
+                    "traffic": (KNN_DRAM_BYTES_PER_CLOUD * clouds_per_step * PROF_STEPS / max(gd["launches"], 1)) if dom == "knn_search+cov" else None,
+                    "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of k_knn_search in profiles/r1_knn_search_v3.ncu-rep "
+                                      "(22.1 MB for 8 clouds; neighbour lists stay in the 126 MB L2), scaled to the clouds of one launch",
+                    "peak_source": peak_src,
                     "ms_per_launch": gd["ms"] / max(gd["launches"], 1), "launches": gd["launches"],
                     "share_of_gicp_time": gd["ms"] / tgp if tgp > 0 else None,
                     "timed_over": "%d extra steps of the same workload with per-kernel CUDA events on the launch stream" % PROF_STEPS,
@@ -475,7 +484,7 @@ def main():
             "metric": "gicp_aligns_per_s", "value": value, "unit": "aligns/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": t_total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64",
             "data": "synthetic",
-            "config": {"workload": "cfg2: 32 pairwise GICP refines of 120k-pt synthetic 64-beam scans + elevation fuse @0.1 m (1200x1200)",
+            "config": {"workload": "cfg2: 32 pairwise GICP refines of 120k-pt synthetic 64-beam scans + elevation fuse @0.1 m (1200x1200) of the 32 source scans (one batched replay call, frames in order)",
                        "pairs_per_rank": n_pairs, "points_per_scan": N_POINTS, "k": K_CORR, "max_iter": MAX_ITER,
                        "parallelism": "robot-per-gpu x%d" % world,
                        "exchange": ("nccl all_gather of candidate clouds per step, %d MB received per rank, overlapped with the local source-cloud "

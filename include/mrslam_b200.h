@@ -160,6 +160,23 @@ int mrslam_elev_process_fuse_device(mrslam_elev_t*, const float* d_x, const floa
                                     const float* sensorJacobian3, const float* rotationVariance9, const float* C_SB_transpose9,
                                     const float* P_mul_C_BM_transpose3, const float* B_r_BS_skew9, int near_filter,
                                     long long* n_fused);
+/* One frame of the batched entry point below: Move(position) when do_move != 0, then Process_points + Fuse of the device
+ * arrays with the same arguments as the per-frame call. */
+typedef struct mrslam_elev_frame {
+  const float *d_x, *d_y, *d_z;
+  int n;
+  int do_move;
+  float position[3];
+  float T16[16];
+  double lower, upper;
+  float min_r, beam_a, beam_c;
+  float sJ[3], rotVar[9], CSBT[9], PCBM[3], BrBS[9];
+  int near_filter;
+} mrslam_elev_frame_t;
+/* nframes frames in call order (map replay, or the frames queued while a loop closure was processed): same results as
+ * nframes x (Move, process_fuse_device); internally the map-independent half of frame f+1 (transform, sensor variance, sort by
+ * cell) overlaps the per-cell recurrence of frame f on a second stream.  No host synchronisation; counts go to fused_total. */
+int mrslam_elev_process_fuse_device_batch(mrslam_elev_t*, const mrslam_elev_frame_t* frames, int nframes, float resolution, int length);
 /* cell fuses accumulated on the device by process_fuse_device calls that passed n_fused == NULL (no per-frame host sync) */
 int mrslam_elev_fused_total(mrslam_elev_t*, int reset, long long* total);
 int mrslam_elev_mapvar_update(mrslam_elev_t*, int length, float var_update);          /* Mapvar_update  :1144 */

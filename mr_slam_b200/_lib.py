@@ -40,6 +40,14 @@ def check(status):
     return status
 
 
+class ElevFrame(C.Structure):
+    """mrslam_elev_frame_t (include/mrslam_b200.h)"""
+    _fields_ = [("d_x", C.c_void_p), ("d_y", C.c_void_p), ("d_z", C.c_void_p), ("n", C.c_int), ("do_move", C.c_int),
+                ("position", C.c_float * 3), ("T16", C.c_float * 16), ("lower", C.c_double), ("upper", C.c_double),
+                ("min_r", C.c_float), ("beam_a", C.c_float), ("beam_c", C.c_float), ("sJ", C.c_float * 3), ("rotVar", C.c_float * 9),
+                ("CSBT", C.c_float * 9), ("PCBM", C.c_float * 3), ("BrBS", C.c_float * 9), ("near_filter", C.c_int)]
+
+
 def _declare(L):
     vp, i, f, d, ll = C.c_void_p, C.c_int, C.c_float, C.c_double, C.c_longlong
     fp, ip, dp = C.c_void_p, C.c_void_p, C.c_void_p  # raw pointers (host or device) passed as integers
@@ -106,6 +114,7 @@ def _declare(L):
         L.mrslam_elev_fuse.argtypes = [vp, i, i, ip, ip, ip, ip, fp, fp, fp, C.POINTER(ll)]
         L.mrslam_elev_process_fuse_device.argtypes = [vp, fp, fp, fp, i, fp, d, d, f, f, f] + [fp] * 5 + [i, C.POINTER(ll)]
         L.mrslam_elev_mapvar_update.argtypes = [vp, i, f]
+        L.mrslam_elev_process_fuse_device_batch.argtypes = [vp, C.POINTER(ElevFrame), i, f, i]
         L.mrslam_elev_fused_total.argtypes = [vp, i, C.POINTER(ll)]
         L.mrslam_elev_map_optmove.argtypes = [vp, fp, f, f, i, fp]
         L.mrslam_elev_map_closeloop.argtypes = [vp, fp, f, i, f]

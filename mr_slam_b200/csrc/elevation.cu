@@ -320,6 +320,12 @@ struct Elev {
   DevBuf<int4> gcol;
   DevBuf<unsigned char> cubtmp;
   DevBuf<unsigned long long> counter;
+  // second set of sorted-stream buffers + an auxiliary stream: the batched entry point overlaps process+sort+gather of frame
+  // f+1 (aux stream) with the run walk of frame f (library stream)
+  DevBuf<int> keys2, keys_alt2, vals2, vals_alt2;
+  DevBuf<float2> ghv2;
+  cudaStream_t aux = nullptr;
+  cudaEvent_t ev_start = nullptr, ev_a[2] = {nullptr, nullptr}, ev_b[2] = {nullptr, nullptr};
   std::mutex mu;  // Fuse and Mapvar_update may be called from two threads (ElevationMapping.cpp:393-394)
 
   int cells() const { return g.L * g.L; }
@@ -338,10 +344,27 @@ struct Elev {
   void release() {
     for (DevBuf<float>* b : {&elevation, &variance, &intensity, &lowest, &traver, &px, &py, &pz, &pvar, &pxt, &pyt, &pzt, &pint, &ph}) b->release();
     for (DevBuf<int>* b : {&R, &G, &B, &pidx, &pR, &pG, &pB, &keys, &keys_alt, &vals, &vals_alt}) b->release();
+    for (DevBuf<int>* b : {&keys2, &keys_alt2, &vals2, &vals_alt2}) b->release();
+    ghv2.release();
     cubtmp.release();
     counter.release();
     ghv.release();
     gcol.release();
+    if (aux) cudaStreamDestroy(aux);
+    for (cudaEvent_t e : {ev_start, ev_a[0], ev_a[1], ev_b[0], ev_b[1]})
+      if (e) cudaEventDestroy(e);
+    aux = nullptr;
+    ev_start = ev_a[0] = ev_a[1] = ev_b[0] = ev_b[1] = nullptr;
+  }
+  int ensure_pipeline(int n) {
+    size_t m = std::max(n, 1);
+    MR_CHECK(keys2.reserve(m)); MR_CHECK(keys_alt2.reserve(m)); MR_CHECK(vals2.reserve(m)); MR_CHECK(vals_alt2.reserve(m));
+    MR_CHECK(ghv2.reserve(m));
+    if (!aux) {
+      MR_CUDA(cudaStreamCreateWithFlags(&aux, cudaStreamNonBlocking));
+      for (cudaEvent_t* e : {&ev_start, &ev_a[0], &ev_a[1], &ev_b[0], &ev_b[1]}) MR_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    }
+    return MRSLAM_OK;
   }
 };
 
@@ -458,6 +481,8 @@ int mrslam_elev_init(mrslam_elev_t* h, int length, float resolution, float mahal
   return MRSLAM_OK;
 }
 
+static int move_locked(Elev* m, const float* pos, float resolution, int length, float* central_out, int* start_out, float* shift_out);
+
 int mrslam_elev_move(mrslam_elev_t* h, const float* pos, float resolution, int length, float* central_out, int* start_out,
                      float* shift_out) {
   REQ(h);
@@ -465,6 +490,10 @@ int mrslam_elev_move(mrslam_elev_t* h, const float* pos, float resolution, int l
   REQ_INIT(m);
   std::lock_guard<std::mutex> lk2(m->mu);
   std::lock_guard<std::mutex> lk(rt().mu);
+  return move_locked(m, pos, resolution, length, central_out, start_out, shift_out);
+}
+
+static int move_locked(Elev* m, const float* pos, float resolution, int length, float* central_out, int* start_out, float* shift_out) {
   cudaStream_t st = rt().stream;
   int ishift[2];
   float pshift[2];
@@ -625,6 +654,84 @@ int mrslam_elev_process_fuse_device(mrslam_elev_t* h, const float* d_x, const fl
     count_launch(1);
   }
   return fuse_sorted(m, n, m->pzt.p, m->pvar.p, nullptr, nullptr, nullptr, nullptr, n_fused);
+}
+
+// Many frames in one call (map replay / catching up after a loop closure): Move + Process_points + Fuse per frame, exactly
+// the per-frame sequence, with the map-independent half of frame f+1 (process, sort by cell, gather; aux stream) running
+// under the run walk of frame f (library stream).  `lowest` is only touched by the process kernels (aux stream, in frame
+// order); elevation / variance / colour only by clear, fuse and clamp (library stream, in frame order).
+int mrslam_elev_process_fuse_device_batch(mrslam_elev_t* h, const mrslam_elev_frame_t* frames, int nframes, float resolution, int length) {
+  REQ(h);
+  Elev* m = E(h);
+  REQ_INIT(m);
+  if (nframes < 0 || (nframes > 0 && !frames)) {
+    set_error("process_fuse_device_batch: bad arguments");
+    return MRSLAM_ERR_ARG;
+  }
+  std::lock_guard<std::mutex> lk2(m->mu);
+  std::lock_guard<std::mutex> lk(rt().mu);
+  if (nframes == 0) return MRSLAM_OK;
+  int max_n = 0;
+  for (int f = 0; f < nframes; f++) {
+    if (frames[f].n < 0 || (frames[f].n > 0 && (!frames[f].d_x || !frames[f].d_y || !frames[f].d_z))) {
+      set_error("process_fuse_device_batch: bad frame %d", f);
+      return MRSLAM_ERR_ARG;
+    }
+    max_n = std::max(max_n, frames[f].n);
+  }
+  MR_CHECK(m->reserve_points(max_n));
+  MR_CHECK(m->ensure_pipeline(max_n));
+  cudaStream_t st = rt().stream, aux = m->aux;
+  const int cells = m->cells();
+  int bits = 1;
+  while ((1ll << bits) <= cells) bits++;
+  size_t tmp = 0;
+  {
+    cub::DoubleBuffer<int> dk(m->keys.p, m->keys_alt.p), dv(m->vals.p, m->vals_alt.p);
+    MR_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp, dk, dv, std::max(max_n, 1), 0, bits, aux));
+  }
+  MR_CHECK(m->cubtmp.reserve(tmp));
+  ProfScope ps(PROF_ELEV_FUSE);
+  MR_CUDA(cudaEventRecord(m->ev_start, st));  // inputs and the map state are ordered on the library stream
+  MR_CUDA(cudaStreamWaitEvent(aux, m->ev_start, 0));
+  for (int f = 0; f < nframes; f++) {
+    const mrslam_elev_frame_t& F = frames[f];
+    const int s = f & 1, n = F.n;
+    if (F.do_move) MR_CHECK(move_locked(m, F.position, resolution, length, nullptr, nullptr, nullptr));  // clears -> library stream
+    int* keys = s ? m->keys2.p : m->keys.p;
+    int* keys_alt = s ? m->keys_alt2.p : m->keys_alt.p;
+    int* vals = s ? m->vals2.p : m->vals.p;
+    int* vals_alt = s ? m->vals_alt2.p : m->vals_alt.p;
+    float2* ghv = s ? m->ghv2.p : m->ghv.p;
+    const int* keys_sorted = keys;
+    // ---- aux stream: everything of frame f that does not read the map
+    if (f >= 2) MR_CUDA(cudaStreamWaitEvent(aux, m->ev_b[s], 0));  // set s is free again once frame f-2 has been fused
+    if (n > 0) {
+      ProcParams P;
+      fill_proc(P, F.T16, F.lower, F.upper, F.min_r, F.beam_a, F.beam_c, F.sJ, F.rotVar, F.CSBT, F.PCBM, F.BrBS, F.near_filter);
+      k_elev_process<<<(n + 255) / 256, 256, 0, aux>>>(F.d_x, F.d_y, F.d_z, n, P, m->g, m->lowest.p, nullptr, m->pvar.p, nullptr, nullptr,
+                                                      m->pzt.p, keys, vals);
+      cub::DoubleBuffer<int> dk(keys, keys_alt), dv(vals, vals_alt);
+      size_t t2 = tmp;
+      MR_CUDA(cub::DeviceRadixSort::SortPairs(m->cubtmp.p, t2, dk, dv, n, 0, bits, aux));
+      keys_sorted = dk.Current();
+      k_elev_gather<<<(n + 255) / 256, 256, 0, aux>>>(dv.Current(), n, m->pzt.p, m->pvar.p, nullptr, nullptr, nullptr, nullptr, ghv, nullptr);
+      count_launch(2);
+    }
+    MR_CUDA(cudaEventRecord(m->ev_a[s], aux));
+    // ---- library stream: the run walk and the clamp, in frame order
+    MR_CUDA(cudaStreamWaitEvent(st, m->ev_a[s], 0));
+    if (n > 0) {
+      k_elev_fuse_segments<<<(n + 127) / 128, 128, 0, st>>>(keys_sorted, n, cells, ghv, nullptr, m->elevation.p, m->variance.p,
+                                                           m->intensity.p, m->R.p, m->G.p, m->B.p, m->counter.p + 1);
+      count_launch(1);
+    }
+    k_elev_clamp_var<<<((cells + 3) / 4 + 255) / 256, 256, 0, st>>>(m->variance.p, cells);
+    count_launch(1);
+    MR_CUDA(cudaEventRecord(m->ev_b[s], st));
+  }
+  MR_CUDA(cudaGetLastError());
+  return MRSLAM_OK;
 }
 
 // cell fuses accumulated by calls that passed n_fused == NULL (no host sync per frame); optionally reset

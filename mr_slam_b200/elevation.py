@@ -10,6 +10,7 @@ import ctypes as C
 
 import numpy as np
 
+from . import _lib
 from ._lib import MrSlamError, check, lib, ptr
 
 
@@ -85,6 +86,32 @@ class ElevationMap:
                                                       *[ptr(a) for a in args[1:]], int(bool(near_filter)),
                                                       C.byref(nf) if want_count else None))
         return nf.value if want_count else None
+
+    @staticmethod
+    def make_frame(d_x, d_y, d_z, n, T, lower, upper, min_r, beam_a, beam_c, sensorJacobian, rotationVariance, C_SB_transpose,
+                   P_mul_C_BM_transpose, B_r_BS_skew, near_filter=True, position=None):
+        """One mrslam_elev_frame_t for process_fuse_device_batch (position != None: Move(position) first)."""
+        dp = lambda a: a if isinstance(a, int) else a.data_ptr() if hasattr(a, "data_ptr") else ptr(a)
+        F = _lib.ElevFrame()
+        F.d_x, F.d_y, F.d_z, F.n = dp(d_x), dp(d_y), dp(d_z), int(n)
+        F.do_move = 0 if position is None else 1
+        if position is not None:
+            F.position[:] = [float(v) for v in np.asarray(position).reshape(3)]
+        F.T16[:] = _f32(T).reshape(16).tolist()
+        F.lower, F.upper = float(lower), float(upper)
+        F.min_r, F.beam_a, F.beam_c = float(min_r), float(beam_a), float(beam_c)
+        F.sJ[:] = _f32(sensorJacobian).reshape(3).tolist()
+        F.rotVar[:] = _f32(rotationVariance).reshape(9).tolist()
+        F.CSBT[:] = _f32(C_SB_transpose).reshape(9).tolist()
+        F.PCBM[:] = _f32(P_mul_C_BM_transpose).reshape(3).tolist()
+        F.BrBS[:] = _f32(B_r_BS_skew).reshape(9).tolist()
+        F.near_filter = int(bool(near_filter))
+        return F
+
+    def process_fuse_device_batch(self, frames, resolution, length):
+        """frames: list of make_frame(...) results, fused in order (mrslam_elev_process_fuse_device_batch); no host sync."""
+        arr = (_lib.ElevFrame * len(frames))(*frames)
+        check(self._L.mrslam_elev_process_fuse_device_batch(self._h, arr, len(frames), float(resolution), int(length)))
 
     def fused_total(self, reset=True):
         """cell fuses accumulated on the device by process_fuse_device(..., want_count=False) calls"""

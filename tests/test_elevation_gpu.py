@@ -119,6 +119,42 @@ def test_device_fused_path_equals_host_path(gpu):
     assert nf_off > nf_b
 
 
+def test_pipelined_batch_equals_per_frame_sequence(gpu):
+    """mrslam_elev_process_fuse_device_batch (two-stream pipeline over frames) == Move + process_fuse_device per frame, bit for bit
+    for elevation / variance and the fused-point count; `lowest` (process kernels, auxiliary stream) touches the same cells"""
+    import torch
+    L, res = 1200, 0.1
+    a = elevation.ElevationMap()
+    a.Init_GPU_elevationmap(L, res, 2.5, 0.2)
+    b = elevation.ElevationMap()
+    b.Init_GPU_elevationmap(L, res, 2.5, 0.2)
+    o = oracle.ElevationMap(L, res, 2.5, 0.2)
+    frames, keep, total = [], [], 0
+    for f in range(5):
+        pose, x, y, z, args = frame(f, "hdl64")
+        n = len(x) if f != 3 else 0                     # one empty frame in the middle
+        pos = pose[:3, 3].astype(np.float32)
+        d = [torch.from_numpy(t).cuda() for t in (x, y, z)]
+        keep.append(d)
+        a.Move(pos, res, L)
+        total += a.process_fuse_device(d[0], d[1], d[2], n, *args, near_filter=True)
+        frames.append(elevation.ElevationMap.make_frame(d[0], d[1], d[2], n, *args, near_filter=True, position=pos))
+        o.move(pos)
+        r = o.process_points(x[:n], y[:n], z[:n], *args)
+        zi = np.zeros(n, np.int32)
+        o.fuse(r[0], zi, zi, zi, np.zeros(n, np.float32), r[4], r[1])
+    torch.cuda.synchronize()
+    b.fused_total(reset=True)
+    b.process_fuse_device_batch(frames, res, L)
+    assert b.fused_total(reset=True) == total
+    ma, mb, mo = a.get_map(), b.get_map(), o.get_map()
+    for key in ("elevation", "variance", "lowest"):
+        assert np.array_equal(ma[key], mb[key]), key
+    assert np.array_equal(mb["elevation"] != -10, mo["elevation"] != -10)
+    assert np.abs(mb["elevation"] - mo["elevation"]).max() <= 1e-5
+    b.process_fuse_device_batch([], res, L)             # empty batch is a no-op
+
+
 def test_empty_and_invalid_inputs(gpu):
     g = elevation.ElevationMap()
     with pytest.raises(Exception):
