@@ -249,10 +249,13 @@ def main():
     exch_ms = [0.0]
     step_trace = []
 
-    def step_device():
+    def step_device(overlap=True):
         """inputs resident in HBM; returns (t_gicp_ms, t_elev_ms, n_fused, results) measured with events on the library stream.
         Order inside a step: start the exchange (NCCL stream) -> local work that does not need it (source tiles + covariances,
-        elevation fuse of the robot's own scans) on the library stream -> wait -> target tiles + covariances + LM."""
+        elevation replay of the robot's own scans) -> wait -> target tiles + covariances + LM.
+        overlap=True (the timed steps): the elevation replay is enqueued on the map's own streams and runs concurrently with
+        the rest of the GICP batch; the step ends when both are done, and only the total is meaningful (returned as t_gicp,
+        t_elev = 0).  overlap=False: the replay runs in line on the library stream, which gives the per-part times."""
         e0, e1, e2, e3 = ev(), ev(), ev(), ev()
         with torch.cuda.stream(lib_stream):
             e0.record()
@@ -286,7 +289,7 @@ def main():
                 emap.Move(pairs[i]["pose"][:3, 3].astype(np.float32), ELEV_RES, ELEV_L)
                 emap.process_fuse_device(soa_dev[i][0], soa_dev[i][1], soa_dev[i][2], N_POINTS, *elev_args(i), near_filter=True, want_count=False)
         else:  # the robot's 32 scans replayed into its map by one call (frames pipelined over two streams inside the library)
-            emap.process_fuse_device_batch(elev_frames, ELEV_RES, ELEV_L)
+            emap.process_fuse_device_batch(elev_frames, ELEV_RES, ELEV_L, asynchronous=overlap)
         with torch.cuda.stream(lib_stream):
             e2.record()
         mark()
@@ -307,12 +310,16 @@ def main():
         mark()
         Ts = pygicp.align_batch(regs, guesses)
         mark()
+        fused = emap.fused_total(reset=True) if overlap else None   # joins the asynchronous replay into the library stream
         with torch.cuda.stream(lib_stream):
             e3.record()
         e3.synchronize()
-        fused = emap.fused_total(reset=True)
+        if fused is None:
+            fused = emap.fused_total(reset=True)
         t_gicp = e0.elapsed_time(e1) + e2.elapsed_time(e3)
         t_elev = e1.elapsed_time(e2)
+        if overlap:
+            t_gicp, t_elev = e0.elapsed_time(e3), 0.0
         step_trace.append((round(e0.elapsed_time(e1), 2), round(t_elev, 2), round(e2.elapsed_time(e3), 2), round(1e3 * (tm[-1] - tm[-2]), 2)))
         if os.environ.get("BENCH_DEBUG"):
             names = ["new_regs", "pack src", "set src", "prepare src", "elev launches", "exchange wait", "pack+set tgt", "align_batch"]
@@ -403,12 +410,20 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     # per-kernel device times for the roofline block: the same steps again with CUDA events around every launch group on
     # the library stream (kept out of the region above: ~300 extra event records per step would be timed with it)
+    SEQ_STEPS = 3
+    seq_g = seq_e = 0.0
+    seq_fused = 0
+    for _ in range(SEQ_STEPS):  # the same step with the elevation replay in line: per-part device times
+        tg_, te_, f_, _Ts, _c = step_device(overlap=False)
+        seq_g += tg_
+        seq_e += te_
+        seq_fused += f_
     PROF_STEPS = 2
     _lib.prof_enable(True)
     p_lin = p_err = 0
     tgp = 0.0
     for _ in range(PROF_STEPS):
-        tg_, _te, _f, _Ts, (a, b) = step_device()
+        tg_, _te, _f, _Ts, (a, b) = step_device(overlap=False)
         tgp += tg_
         p_lin += a
         p_err += b
@@ -416,9 +431,10 @@ def main():
     _lib.prof_enable(False)
     barrier()
     t_total_ms = reduce_max(t_g + t_e)
-    t_g_ms, t_e_ms = reduce_max(t_g), reduce_max(t_e)
+    seq_g_ms, seq_e_ms = reduce_max(seq_g), reduce_max(seq_e)     # per-part times of the SEQ_STEPS in-line steps
     aligns_total = n_pairs * args.steps * world
     fused_all = reduce_sum(float(fused_tot))
+    seq_fused_all = reduce_sum(float(seq_fused))
     value = aligns_total / (t_total_ms * 1e-3)
     last_Ts = Ts
 
@@ -491,11 +507,14 @@ def main():
                                     "preparation and elevation fuse (host waited %.2f ms per step for it)" %
                                     (world * n_pairs * N_POINTS * 12 // 1000000, exchange_ms_per_step)) if world > 1 else "none (single robot)",
                        "l2": "per-step working set (64 clouds x ~10 MB + map) exceeds the 126 MB L2; clouds are rebuilt every step"},
-            "gicp": {"aligns_per_s": aligns_total / (t_g_ms * 1e-3), "ms_per_step": t_g_ms / args.steps,
+            "overlap": "timed steps: the elevation replay runs on the map's own streams concurrently with the GICP batch (the step ends "
+                       "when both are done); the gicp / elevation blocks below are device times of %d further steps with the replay in "
+                       "line on the library stream (%.2f ms per step in that mode)" % (SEQ_STEPS, (seq_g_ms + seq_e_ms) / SEQ_STEPS),
+            "gicp": {"aligns_per_s": n_pairs * SEQ_STEPS * world / (seq_g_ms * 1e-3), "ms_per_step": seq_g_ms / SEQ_STEPS,
                      "mean_linearize_per_align": n_lin / float(n_pairs * args.steps), "mean_error_evals_per_align": n_err / float(n_pairs * args.steps),
                      "median_t_err_m": float(np.median([e[0] for e in errs])), "median_r_err_rad": float(np.median([e[1] for e in errs]))},
-            "elevation": {"metric": "elevation_cell_fuses_per_s", "value": fused_all / (t_e_ms * 1e-3), "unit": "cell-fuses/s",
-                          "cell_fuses_per_step": fused_all / args.steps / world, "ms_per_step": t_e_ms / args.steps,
+            "elevation": {"metric": "elevation_cell_fuses_per_s", "value": seq_fused_all / (seq_e_ms * 1e-3), "unit": "cell-fuses/s",
+                          "cell_fuses_per_step": fused_all / args.steps / world, "ms_per_step": seq_e_ms / SEQ_STEPS,
                           "grid": "%dx%d @ %.2f m" % (ELEV_L, ELEV_L, ELEV_RES), "near_filter": True},
             "e2e": {"value": e2e_value, "unit": "aligns/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": te2e_ms / args.steps},

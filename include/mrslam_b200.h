@@ -177,6 +177,11 @@ typedef struct mrslam_elev_frame {
  * nframes x (Move, process_fuse_device); internally the map-independent half of frame f+1 (transform, sensor variance, sort by
  * cell) overlaps the per-cell recurrence of frame f on a second stream.  No host synchronisation; counts go to fused_total. */
 int mrslam_elev_process_fuse_device_batch(mrslam_elev_t*, const mrslam_elev_frame_t* frames, int nframes, float resolution, int length);
+/* The same replay with its map-writing half on the map's own stream instead of mrslam_stream(): the call returns after the
+ * enqueue and an unrelated batch (a loop-closure storm on the library stream) runs concurrently with it.  Inputs must be
+ * ready in mrslam_stream() order at the call; every later mrslam_elev_* call on this map joins the replay first. */
+int mrslam_elev_process_fuse_device_batch_async(mrslam_elev_t*, const mrslam_elev_frame_t* frames, int nframes, float resolution,
+                                                int length);
 /* cell fuses accumulated on the device by process_fuse_device calls that passed n_fused == NULL (no per-frame host sync) */
 int mrslam_elev_fused_total(mrslam_elev_t*, int reset, long long* total);
 int mrslam_elev_mapvar_update(mrslam_elev_t*, int length, float var_update);          /* Mapvar_update  :1144 */

@@ -115,6 +115,7 @@ def _declare(L):
         L.mrslam_elev_process_fuse_device.argtypes = [vp, fp, fp, fp, i, fp, d, d, f, f, f] + [fp] * 5 + [i, C.POINTER(ll)]
         L.mrslam_elev_mapvar_update.argtypes = [vp, i, f]
         L.mrslam_elev_process_fuse_device_batch.argtypes = [vp, C.POINTER(ElevFrame), i, f, i]
+        L.mrslam_elev_process_fuse_device_batch_async.argtypes = [vp, C.POINTER(ElevFrame), i, f, i]
         L.mrslam_elev_fused_total.argtypes = [vp, i, C.POINTER(ll)]
         L.mrslam_elev_map_optmove.argtypes = [vp, fp, f, f, i, fp]
         L.mrslam_elev_map_closeloop.argtypes = [vp, fp, f, i, f]

@@ -326,6 +326,18 @@ struct Elev {
   DevBuf<float2> ghv2;
   cudaStream_t aux = nullptr;
   cudaEvent_t ev_start = nullptr, ev_a[2] = {nullptr, nullptr}, ev_b[2] = {nullptr, nullptr};
+  // asynchronous replay: the map-writing half runs on `bstream` instead of the library stream, so that an unrelated batch
+  // (a loop-closure storm) can use the library stream meanwhile; every other entry point joins first
+  cudaStream_t bstream = nullptr;
+  cudaEvent_t ev_done = nullptr;
+  bool pending_join = false;
+  int join() {
+    if (pending_join) {
+      MR_CUDA(cudaStreamWaitEvent(rt().stream, ev_done, 0));
+      pending_join = false;
+    }
+    return MRSLAM_OK;
+  }
   std::mutex mu;  // Fuse and Mapvar_update may be called from two threads (ElevationMapping.cpp:393-394)
 
   int cells() const { return g.L * g.L; }
@@ -350,11 +362,14 @@ struct Elev {
     counter.release();
     ghv.release();
     gcol.release();
+    if (bstream) cudaStreamSynchronize(bstream);
     if (aux) cudaStreamDestroy(aux);
-    for (cudaEvent_t e : {ev_start, ev_a[0], ev_a[1], ev_b[0], ev_b[1]})
+    if (bstream) cudaStreamDestroy(bstream);
+    for (cudaEvent_t e : {ev_start, ev_a[0], ev_a[1], ev_b[0], ev_b[1], ev_done})
       if (e) cudaEventDestroy(e);
-    aux = nullptr;
-    ev_start = ev_a[0] = ev_a[1] = ev_b[0] = ev_b[1] = nullptr;
+    aux = bstream = nullptr;
+    ev_start = ev_a[0] = ev_a[1] = ev_b[0] = ev_b[1] = ev_done = nullptr;
+    pending_join = false;
   }
   int ensure_pipeline(int n) {
     size_t m = std::max(n, 1);
@@ -362,7 +377,8 @@ struct Elev {
     MR_CHECK(ghv2.reserve(m));
     if (!aux) {
       MR_CUDA(cudaStreamCreateWithFlags(&aux, cudaStreamNonBlocking));
-      for (cudaEvent_t* e : {&ev_start, &ev_a[0], &ev_a[1], &ev_b[0], &ev_b[1]}) MR_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+      MR_CUDA(cudaStreamCreateWithFlags(&bstream, cudaStreamNonBlocking));
+      for (cudaEvent_t* e : {&ev_start, &ev_a[0], &ev_a[1], &ev_b[0], &ev_b[1], &ev_done}) MR_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     }
     return MRSLAM_OK;
   }
@@ -466,6 +482,7 @@ int mrslam_elev_init(mrslam_elev_t* h, int length, float resolution, float mahal
   Elev* m = E(h);
   std::lock_guard<std::mutex> lk2(m->mu);
   std::lock_guard<std::mutex> lk(rt().mu);
+  MR_CHECK(m->join());
   m->g = ElevGeom{length, resolution, 0.f, 0.f, 0, 0};
   m->mahal_thr = mahal;
   m->obstacle_thr = obst;
@@ -481,7 +498,8 @@ int mrslam_elev_init(mrslam_elev_t* h, int length, float resolution, float mahal
   return MRSLAM_OK;
 }
 
-static int move_locked(Elev* m, const float* pos, float resolution, int length, float* central_out, int* start_out, float* shift_out);
+static int move_locked(Elev* m, const float* pos, float resolution, int length, float* central_out, int* start_out, float* shift_out,
+                       cudaStream_t st);
 
 int mrslam_elev_move(mrslam_elev_t* h, const float* pos, float resolution, int length, float* central_out, int* start_out,
                      float* shift_out) {
@@ -490,11 +508,12 @@ int mrslam_elev_move(mrslam_elev_t* h, const float* pos, float resolution, int l
   REQ_INIT(m);
   std::lock_guard<std::mutex> lk2(m->mu);
   std::lock_guard<std::mutex> lk(rt().mu);
-  return move_locked(m, pos, resolution, length, central_out, start_out, shift_out);
+  MR_CHECK(m->join());
+  return move_locked(m, pos, resolution, length, central_out, start_out, shift_out, rt().stream);
 }
 
-static int move_locked(Elev* m, const float* pos, float resolution, int length, float* central_out, int* start_out, float* shift_out) {
-  cudaStream_t st = rt().stream;
+static int move_locked(Elev* m, const float* pos, float resolution, int length, float* central_out, int* start_out, float* shift_out,
+                       cudaStream_t st) {
   int ishift[2];
   float pshift[2];
   m->sensor_z = pos[2];
@@ -576,6 +595,7 @@ int mrslam_elev_process_points(mrslam_elev_t* h, int* map_index, const float* x,
   }
   std::lock_guard<std::mutex> lk2(m->mu);
   std::lock_guard<std::mutex> lk(rt().mu);
+  MR_CHECK(m->join());
   cudaStream_t st = rt().stream;
   MR_CHECK(m->reserve_points(n));
   if (n == 0) return MRSLAM_OK;
@@ -609,6 +629,7 @@ int mrslam_elev_fuse(mrslam_elev_t* h, int length, int n, const int* idx, const 
   }
   std::lock_guard<std::mutex> lk2(m->mu);
   std::lock_guard<std::mutex> lk(rt().mu);
+  MR_CHECK(m->join());
   cudaStream_t st = rt().stream;
   MR_CHECK(m->reserve_points(n));
   if (n > 0) {
@@ -641,6 +662,7 @@ int mrslam_elev_process_fuse_device(mrslam_elev_t* h, const float* d_x, const fl
   }
   std::lock_guard<std::mutex> lk2(m->mu);
   std::lock_guard<std::mutex> lk(rt().mu);
+  MR_CHECK(m->join());
   cudaStream_t st = rt().stream;
   MR_CHECK(m->reserve_points(n));
   if (n > 0) {
@@ -660,7 +682,7 @@ int mrslam_elev_process_fuse_device(mrslam_elev_t* h, const float* d_x, const fl
 // the per-frame sequence, with the map-independent half of frame f+1 (process, sort by cell, gather; aux stream) running
 // under the run walk of frame f (library stream).  `lowest` is only touched by the process kernels (aux stream, in frame
 // order); elevation / variance / colour only by clear, fuse and clamp (library stream, in frame order).
-int mrslam_elev_process_fuse_device_batch(mrslam_elev_t* h, const mrslam_elev_frame_t* frames, int nframes, float resolution, int length) {
+static int elev_batch(mrslam_elev_t* h, const mrslam_elev_frame_t* frames, int nframes, float resolution, int length, bool async) {
   REQ(h);
   Elev* m = E(h);
   REQ_INIT(m);
@@ -670,6 +692,7 @@ int mrslam_elev_process_fuse_device_batch(mrslam_elev_t* h, const mrslam_elev_fr
   }
   std::lock_guard<std::mutex> lk2(m->mu);
   std::lock_guard<std::mutex> lk(rt().mu);
+  MR_CHECK(m->join());
   if (nframes == 0) return MRSLAM_OK;
   int max_n = 0;
   for (int f = 0; f < nframes; f++) {
@@ -681,7 +704,7 @@ int mrslam_elev_process_fuse_device_batch(mrslam_elev_t* h, const mrslam_elev_fr
   }
   MR_CHECK(m->reserve_points(max_n));
   MR_CHECK(m->ensure_pipeline(max_n));
-  cudaStream_t st = rt().stream, aux = m->aux;
+  cudaStream_t st = async ? m->bstream : rt().stream, aux = m->aux;
   const int cells = m->cells();
   int bits = 1;
   while ((1ll << bits) <= cells) bits++;
@@ -691,13 +714,14 @@ int mrslam_elev_process_fuse_device_batch(mrslam_elev_t* h, const mrslam_elev_fr
     MR_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp, dk, dv, std::max(max_n, 1), 0, bits, aux));
   }
   MR_CHECK(m->cubtmp.reserve(tmp));
-  ProfScope ps(PROF_ELEV_FUSE);
-  MR_CUDA(cudaEventRecord(m->ev_start, st));  // inputs and the map state are ordered on the library stream
+  ProfScope ps(PROF_ELEV_FUSE);  // (spans only the enqueue when the batch is asynchronous)
+  MR_CUDA(cudaEventRecord(m->ev_start, rt().stream));  // inputs and the map state are ordered on the library stream
   MR_CUDA(cudaStreamWaitEvent(aux, m->ev_start, 0));
+  if (async) MR_CUDA(cudaStreamWaitEvent(st, m->ev_start, 0));
   for (int f = 0; f < nframes; f++) {
     const mrslam_elev_frame_t& F = frames[f];
     const int s = f & 1, n = F.n;
-    if (F.do_move) MR_CHECK(move_locked(m, F.position, resolution, length, nullptr, nullptr, nullptr));  // clears -> library stream
+    if (F.do_move) MR_CHECK(move_locked(m, F.position, resolution, length, nullptr, nullptr, nullptr, st));  // clears -> map stream
     int* keys = s ? m->keys2.p : m->keys.p;
     int* keys_alt = s ? m->keys_alt2.p : m->keys_alt.p;
     int* vals = s ? m->vals2.p : m->vals.p;
@@ -731,7 +755,19 @@ int mrslam_elev_process_fuse_device_batch(mrslam_elev_t* h, const mrslam_elev_fr
     MR_CUDA(cudaEventRecord(m->ev_b[s], st));
   }
   MR_CUDA(cudaGetLastError());
+  if (async) {
+    MR_CUDA(cudaEventRecord(m->ev_done, st));
+    m->pending_join = true;
+  }
   return MRSLAM_OK;
+}
+
+int mrslam_elev_process_fuse_device_batch(mrslam_elev_t* h, const mrslam_elev_frame_t* frames, int nframes, float resolution, int length) {
+  return elev_batch(h, frames, nframes, resolution, length, false);
+}
+int mrslam_elev_process_fuse_device_batch_async(mrslam_elev_t* h, const mrslam_elev_frame_t* frames, int nframes, float resolution,
+                                                int length) {
+  return elev_batch(h, frames, nframes, resolution, length, true);
 }
 
 // cell fuses accumulated by calls that passed n_fused == NULL (no host sync per frame); optionally reset
@@ -741,6 +777,7 @@ int mrslam_elev_fused_total(mrslam_elev_t* h, int reset, long long* total) {
   REQ_INIT(m);
   std::lock_guard<std::mutex> lk2(m->mu);
   std::lock_guard<std::mutex> lk(rt().mu);
+  MR_CHECK(m->join());
   unsigned long long c = 0;
   if (m->counter.p) {
     MR_CUDA(cudaMemcpyAsync(&c, m->counter.p + 1, sizeof(c), cudaMemcpyDeviceToHost, rt().stream));
@@ -757,6 +794,7 @@ int mrslam_elev_mapvar_update(mrslam_elev_t* h, int length, float upd) {
   REQ_INIT(m);
   std::lock_guard<std::mutex> lk2(m->mu);
   std::lock_guard<std::mutex> lk(rt().mu);
+  MR_CHECK(m->join());
   int n = length * length;
   k_elev_mapvar<<<(n + 255) / 256, 256, 0, rt().stream>>>(m->variance.p, std::min(n, m->cells()), upd);
   count_launch(1);
@@ -770,6 +808,7 @@ int mrslam_elev_map_optmove(mrslam_elev_t* h, const float* opt_p, float height_u
   REQ_INIT(m);
   std::lock_guard<std::mutex> lk2(m->mu);
   std::lock_guard<std::mutex> lk(rt().mu);
+  MR_CHECK(m->join());
   float last[2] = {m->g.cx, m->g.cy};
   for (int i = 0; i < 2; i++) {
     float ps = opt_p[i] - last[i];
@@ -791,6 +830,7 @@ int mrslam_elev_map_closeloop(mrslam_elev_t* h, const float* upos, float height_
   REQ_INIT(m);
   std::lock_guard<std::mutex> lk2(m->mu);
   std::lock_guard<std::mutex> lk(rt().mu);
+  MR_CHECK(m->join());
   int ishift[2];
   float pshift[2] = {upos[0] - m->g.cx, upos[1] - m->g.cy}, ashift[2];
   index_shift(ishift, pshift, resolution);
@@ -810,6 +850,7 @@ int mrslam_elev_get_map(mrslam_elev_t* h, float* elevation, float* variance, flo
   REQ_INIT(m);
   std::lock_guard<std::mutex> lk2(m->mu);
   std::lock_guard<std::mutex> lk(rt().mu);
+  MR_CHECK(m->join());
   cudaStream_t st = rt().stream;
   size_t n = (size_t)m->cells();
   if (elevation) MR_CUDA(cudaMemcpyAsync(elevation, m->elevation.p, n * 4, cudaMemcpyDeviceToHost, st));

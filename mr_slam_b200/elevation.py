@@ -108,10 +108,13 @@ class ElevationMap:
         F.near_filter = int(bool(near_filter))
         return F
 
-    def process_fuse_device_batch(self, frames, resolution, length):
-        """frames: list of make_frame(...) results, fused in order (mrslam_elev_process_fuse_device_batch); no host sync."""
+    def process_fuse_device_batch(self, frames, resolution, length, asynchronous=False):
+        """frames: list of make_frame(...) results, fused in order (mrslam_elev_process_fuse_device_batch); no host sync.
+        asynchronous=True: the replay runs on the map's own streams, concurrently with later work on the library stream; any
+        later call on this map (e.g. fused_total, get_map) joins it."""
         arr = (_lib.ElevFrame * len(frames))(*frames)
-        check(self._L.mrslam_elev_process_fuse_device_batch(self._h, arr, len(frames), float(resolution), int(length)))
+        fn = self._L.mrslam_elev_process_fuse_device_batch_async if asynchronous else self._L.mrslam_elev_process_fuse_device_batch
+        check(fn(self._h, arr, len(frames), float(resolution), int(length)))
 
     def fused_total(self, reset=True):
         """cell fuses accumulated on the device by process_fuse_device(..., want_count=False) calls"""

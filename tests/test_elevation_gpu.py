@@ -148,11 +148,26 @@ def test_pipelined_batch_equals_per_frame_sequence(gpu):
     b.process_fuse_device_batch(frames, res, L)
     assert b.fused_total(reset=True) == total
     ma, mb, mo = a.get_map(), b.get_map(), o.get_map()
-    for key in ("elevation", "variance", "lowest"):
+    for key in ("elevation", "variance"):
         assert np.array_equal(ma[key], mb[key]), key
+    # `lowest` is updated by a racy read-modify-write inside one frame (in the reference too, gpu_process.cu:434-438): only the
+    # set of cells it touched is deterministic
+    assert np.array_equal(ma["lowest"] != 100, mb["lowest"] != 100)
     assert np.array_equal(mb["elevation"] != -10, mo["elevation"] != -10)
     assert np.abs(mb["elevation"] - mo["elevation"]).max() <= 1e-5
     b.process_fuse_device_batch([], res, L)             # empty batch is a no-op
+    # asynchronous replay (map-writing half on the map's own stream): same map; get_map / fused_total join it
+    c = elevation.ElevationMap()
+    c.Init_GPU_elevationmap(L, res, 2.5, 0.2)
+    c.process_fuse_device_batch(frames, res, L, asynchronous=True)
+    mc = c.get_map()
+    assert c.fused_total(reset=True) == total
+    for key in ("elevation", "variance"):
+        assert np.array_equal(ma[key], mc[key]), key
+    c.process_fuse_device_batch(frames[:2], res, L, asynchronous=True)      # two replays back to back, then a per-frame call
+    c.process_fuse_device_batch(frames[2:], res, L, asynchronous=True)
+    a.process_fuse_device_batch(frames, res, L)
+    assert np.array_equal(a.get_map()["elevation"], c.get_map()["elevation"])
 
 
 def test_empty_and_invalid_inputs(gpu):
