@@ -5,8 +5,8 @@
 // unit named libgpu and the ROS node links unchanged.  One hidden map per process, as in the reference.
 //
 // The Eigen-typed overload of Process_points is provided when <Eigen/Core> is found; a POD overload (row-major float
-// arrays) always exists and is what tests/cpp uses.  Map_feature / Raytracing are "next" rows of SURVEY.md 8f and are
-// declared but report "not provided" on stderr (the reference's convention: print and continue).
+// arrays) always exists and is what tests/cpp uses.  Map_feature / Raytracing run
+// the traversability and ray-tracing kernels of csrc/elev_post.cu.
 #pragma once
 #include <cstdio>
 
@@ -78,15 +78,9 @@ inline void Map_optmove(float* opt_p, float height_update, float resolution, int
 inline void Map_closeloop(float* update_position, float height_update, int length, float resolution) {
   elevation_b200::report(mrslam_elev_map_closeloop(elevation_b200::map(), update_position, height_update, length, resolution), "Map_closeloop");
 }
-// SURVEY.md 8f "next" rows -- declared so the node links; they only read back what exists today.
 inline void Map_feature(int length, float* elevation, float* var, int* colorR, int* colorG, int* colorB, float* rough, float* slope,
                         float* traver, float* intensity) {
-  (void)rough; (void)slope; (void)traver;
-  (void)length;
-  std::fprintf(stderr, "Map_feature: traversability features are not provided by mrslam_b200 yet (elevation/variance/colour only)\n");
-  elevation_b200::report(mrslam_elev_get_map(elevation_b200::map(), elevation, var, intensity, colorR, colorG, colorB, nullptr), "Map_feature");
+  elevation_b200::report(mrslam_elev_map_feature(elevation_b200::map(), length, elevation, var, colorR, colorG, colorB, rough, slope, traver,
+                                                 intensity), "Map_feature");
 }
-inline void Raytracing(int length) {
-  (void)length;
-  std::fprintf(stderr, "Raytracing: not provided by mrslam_b200 yet\n");
-}
+inline void Raytracing(int length) { elevation_b200::report(mrslam_elev_raytracing(elevation_b200::map(), length), "Raytracing"); }

@@ -189,6 +189,12 @@ int mrslam_elev_map_optmove(mrslam_elev_t*, const float* opt_p, float height_upd
                             float* opt_aligned_position2);                             /* Map_optmove    :1213 */
 int mrslam_elev_map_closeloop(mrslam_elev_t*, const float* update_position, float height_update, int length,
                               float resolution);                                       /* Map_closeloop  :1233 */
+/* Map_feature(length, elevation, var, R, G, B, rough, slope, traver, intensity)   :1254  (host arrays, any may be NULL):
+ * 5x5 plane-fit traversability (G_Mapfeature :547-668) + read-out of the map; cells without elevation get 0 / 0 / -10. */
+int mrslam_elev_map_feature(mrslam_elev_t*, int length, float* elevation, float* var, int* colorR, int* colorG, int* colorB,
+                            float* rough, float* slope, float* traver, float* intensity);
+/* Raytracing(length)   :1301   obstacle clean-up along the sensor rays (G_Raytracing :706-889) + reset of map_lowest */
+int mrslam_elev_raytracing(mrslam_elev_t*, int length);
 /* read back the hidden map (any pointer may be NULL); length*length entries each, storage (ring-buffer) order */
 int mrslam_elev_get_map(mrslam_elev_t*, float* elevation, float* variance, float* intensity, int* R, int* G, int* B,
                         float* lowest);

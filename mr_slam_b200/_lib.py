@@ -119,6 +119,8 @@ def _declare(L):
         L.mrslam_elev_fused_total.argtypes = [vp, i, C.POINTER(ll)]
         L.mrslam_elev_map_optmove.argtypes = [vp, fp, f, f, i, fp]
         L.mrslam_elev_map_closeloop.argtypes = [vp, fp, f, i, f]
+        L.mrslam_elev_map_feature.argtypes = [vp, i] + [fp] * 9
+        L.mrslam_elev_raytracing.argtypes = [vp, i]
         L.mrslam_elev_get_map.argtypes = [vp] + [C.c_void_p] * 7
         L.mrslam_elev_get_state.argtypes = [vp, fp, ip]
     if hasattr(L, "mrslam_voxelocc_transform"):

@@ -26,6 +26,13 @@
 
 namespace mrslam {
 
+// csrc/elev_post.cu
+void launch_mapfeature(const float* elevation, const float* variance, const float* intensity, const int* R, const int* G, const int* B,
+                       float* traver_map, int L, float res, int sx, int sy, float* o_elev, float* o_var, int* o_R, int* o_G, int* o_B,
+                       float* o_rough, float* o_slope, float* o_traver, float* o_int, cudaStream_t st);
+void launch_raytracing(float* elevation, const float* variance, const float* traver, float* lowest, int L, int sx, int sy, float sensor_z,
+                       float obstacle_thr, cudaStream_t st);
+
 struct ElevGeom {
   int L;
   float res;
@@ -320,6 +327,8 @@ struct Elev {
   DevBuf<int4> gcol;
   DevBuf<unsigned char> cubtmp;
   DevBuf<unsigned long long> counter;
+  DevBuf<float> feat;   // Map_feature staging: 6 float planes
+  DevBuf<int> feat_i;   // ... and 3 int planes
   // second set of sorted-stream buffers + an auxiliary stream: the batched entry point overlaps process+sort+gather of frame
   // f+1 (aux stream) with the run walk of frame f (library stream)
   DevBuf<int> keys2, keys_alt2, vals2, vals_alt2;
@@ -362,6 +371,8 @@ struct Elev {
     counter.release();
     ghv.release();
     gcol.release();
+    feat.release();
+    feat_i.release();
     if (bstream) cudaStreamSynchronize(bstream);
     if (aux) cudaStreamDestroy(aux);
     if (bstream) cudaStreamDestroy(bstream);
@@ -863,6 +874,60 @@ int mrslam_elev_get_map(mrslam_elev_t* h, float* elevation, float* variance, flo
   MR_CUDA(cudaStreamSynchronize(st));
   return MRSLAM_OK;
 }
+// Map_feature (gpu_process.cu:1254-1298): traversability features of every cell + the read-out of the map.  Host arrays of
+// length*length; any of them may be NULL (not copied).  Updates the resident traversability plane like the reference.
+int mrslam_elev_map_feature(mrslam_elev_t* h, int length, float* elevation, float* var, int* colorR, int* colorG, int* colorB, float* rough,
+                            float* slope, float* traver, float* intensity) {
+  REQ(h);
+  Elev* m = E(h);
+  REQ_INIT(m);
+  if (length != m->g.L) {
+    set_error("Map_feature: length %d does not match the map (%d)", length, m->g.L);
+    return MRSLAM_ERR_ARG;
+  }
+  std::lock_guard<std::mutex> lk2(m->mu);
+  std::lock_guard<std::mutex> lk(rt().mu);
+  MR_CHECK(m->join());
+  cudaStream_t st = rt().stream;
+  const size_t n = (size_t)m->cells();
+  MR_CHECK(m->feat.reserve(6 * n));
+  MR_CHECK(m->feat_i.reserve(3 * n));
+  float* f = m->feat.p;
+  int* fi = m->feat_i.p;
+  launch_mapfeature(m->elevation.p, m->variance.p, m->intensity.p, m->R.p, m->G.p, m->B.p, m->traver.p, m->g.L, m->g.res, m->g.sx, m->g.sy,
+                    f, f + n, fi, fi + n, fi + 2 * n, f + 2 * n, f + 3 * n, f + 4 * n, f + 5 * n, st);
+  MR_CUDA(cudaGetLastError());
+  auto back = [&](void* dst, const void* src) -> int {
+    if (dst) MR_CUDA(cudaMemcpyAsync(dst, src, n * 4, cudaMemcpyDeviceToHost, st));
+    return MRSLAM_OK;
+  };
+  MR_CHECK(back(elevation, f)); MR_CHECK(back(var, f + n)); MR_CHECK(back(rough, f + 2 * n)); MR_CHECK(back(slope, f + 3 * n));
+  MR_CHECK(back(traver, f + 4 * n)); MR_CHECK(back(intensity, f + 5 * n));
+  MR_CHECK(back(colorR, fi)); MR_CHECK(back(colorG, fi + n)); MR_CHECK(back(colorB, fi + 2 * n));
+  MR_CUDA(cudaStreamSynchronize(st));
+  return MRSLAM_OK;
+}
+
+// Raytracing (gpu_process.cu:1301-1316): obstacle cells (traversability below the obstacle threshold) that lie above the
+// sensor-to-lowest-point rays are removed; map_lowest is reset to 10 afterwards.
+int mrslam_elev_raytracing(mrslam_elev_t* h, int length) {
+  REQ(h);
+  Elev* m = E(h);
+  REQ_INIT(m);
+  if (length != m->g.L) {
+    set_error("Raytracing: length %d does not match the map (%d)", length, m->g.L);
+    return MRSLAM_ERR_ARG;
+  }
+  std::lock_guard<std::mutex> lk2(m->mu);
+  std::lock_guard<std::mutex> lk(rt().mu);
+  MR_CHECK(m->join());
+  launch_raytracing(m->elevation.p, m->variance.p, m->traver.p, m->lowest.p, m->g.L, m->g.sx, m->g.sy, m->sensor_z, m->obstacle_thr,
+                    rt().stream);
+  MR_CUDA(cudaGetLastError());
+  MR_CUDA(cudaStreamSynchronize(rt().stream));  // the reference synchronises here as well
+  return MRSLAM_OK;
+}
+
 int mrslam_elev_get_state(mrslam_elev_t* h, float* central2, int* start2) {
   REQ(h);
   Elev* m = E(h);

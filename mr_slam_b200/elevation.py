@@ -133,6 +133,20 @@ class ElevationMap:
     def Map_closeloop(self, update_position, height_update, length, resolution):
         check(self._L.mrslam_elev_map_closeloop(self._h, ptr(_f32(update_position)), float(height_update), int(length), float(resolution)))
 
+    def Map_feature(self, length):
+        """Map_feature (gpu_process.cu:1254): returns dict(elevation, var, colorR, colorG, colorB, rough, slope, traver, intensity),
+        each of length*length in storage order."""
+        n = int(length) * int(length)
+        out = dict(elevation=np.zeros(n, np.float32), var=np.zeros(n, np.float32), colorR=np.zeros(n, np.int32), colorG=np.zeros(n, np.int32),
+                   colorB=np.zeros(n, np.int32), rough=np.zeros(n, np.float32), slope=np.zeros(n, np.float32), traver=np.zeros(n, np.float32),
+                   intensity=np.zeros(n, np.float32))
+        check(self._L.mrslam_elev_map_feature(self._h, int(length), *[ptr(out[k]) for k in ("elevation", "var", "colorR", "colorG", "colorB", "rough",
+                                                                                         "slope", "traver", "intensity")]))
+        return out
+
+    def Raytracing(self, length):
+        check(self._L.mrslam_elev_raytracing(self._h, int(length)))
+
     def get_map(self):
         n = self.length * self.length
         out = dict(elevation=np.zeros(n, np.float32), variance=np.zeros(n, np.float32), intensity=np.zeros(n, np.float32),
@@ -171,6 +185,14 @@ def Process_points(*args, **kw):
 
 def Fuse(*args, **kw):
     return _map().Fuse(*args, **kw)
+
+
+def Map_feature(length):
+    return _map().Map_feature(length)
+
+
+def Raytracing(length):
+    return _map().Raytracing(length)
 
 
 def Mapvar_update(length, var_update):

@@ -73,6 +73,8 @@ def _decl(L):
     L.orc_elev_map_optmove.argtypes = [vp, _p(np.float32), f, f, i, _p(np.float32)]
     L.orc_elev_map_closeloop.argtypes = [vp, _p(np.float32), f, i, f]
     L.orc_elev_get_map.argtypes = [vp] + [C.c_void_p] * 7
+    L.orc_elev_map_feature.argtypes = [vp] + [C.c_void_p] * 9
+    L.orc_elev_raytracing.argtypes = [vp]
     L.orc_elev_get_state.argtypes = [vp, _p(np.float32), _p(np.int32)]
 
     L.orc_voxelocc.argtypes = [_p(np.float32), i, i, i, i, i, i, i, _p(np.float32), C.c_void_p, C.POINTER(i)]
@@ -256,6 +258,18 @@ class ElevationMap:
 
     def map_closeloop(self, update_position, height_update):
         self._L.orc_elev_map_closeloop(self._h, _f32(update_position), float(height_update), self.length, self.resolution)
+
+    def map_feature(self):
+        n = self.length * self.length
+        out = dict(elevation=np.zeros(n, np.float32), var=np.zeros(n, np.float32), colorR=np.zeros(n, np.int32), colorG=np.zeros(n, np.int32),
+                   colorB=np.zeros(n, np.int32), rough=np.zeros(n, np.float32), slope=np.zeros(n, np.float32), traver=np.zeros(n, np.float32),
+                   intensity=np.zeros(n, np.float32))
+        self._L.orc_elev_map_feature(self._h, *[out[k].ctypes.data for k in ("elevation", "var", "colorR", "colorG", "colorB", "rough", "slope",
+                                                                              "traver", "intensity")])
+        return out
+
+    def raytracing(self):
+        self._L.orc_elev_raytracing(self._h)
 
     def get_map(self):
         n = self.length * self.length

@@ -24,6 +24,7 @@
 //     index -- here: one ascending pass over points, which yields the same per-cell order.
 //   * map_lowest update in G_pointsprocess is racy in the reference (gpu_process.cu:434-438);
 //     the oracle keeps the plain minimum (+3*var when the point is the minimum, in index order).
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -300,6 +301,157 @@ void orc_elev_map_closeloop(void* h, const float* update_position, float height_
   for (int i = 0; i < 2; i++) m->central[i] = position_to_range(m->central[i], ashift[i], resolution);
   for (int i = 0; i < length * length; i++)
     if (m->elevation[i] != -10) m->elevation[i] += height_update;
+}
+
+// ---- post-passes.  The CPU libm (sinf/cosf/atan2f/acosf) is not CUDA's, so these twins agree with the
+// GPU to ~1e-6, not bit for bit; the bit-level pin for them is the reference kernel itself run on the GPU box (oracle/_ref).
+// computerEigenvalue, gpu_process.cu:66-185: Jacobi rotations on the largest off-diagonal entry, eigenvector of the smallest
+// eigenvalue.  The pivot scan starts from the SIGNED a[1] like the reference.
+static void orc_min_eigvec3(float* a, float* vec, float eps, int max_rot) {
+  float V[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  int rot = 0;
+  for (;;) {
+    float big = a[1];
+    int p = 0, q = 1;
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) {
+        float d = std::fabs(a[i * 3 + j]);
+        if (i != j && d > big) { big = d; p = i; q = j; }
+      }
+    if (big < eps || rot > max_rot) break;
+    rot++;
+    float app = a[p * 3 + p], apq = a[p * 3 + q], aqq = a[q * 3 + q];
+    float ang = (float)(0.5 * (double)atan2f(-2 * apq, aqq - app));
+    float sn = sinf(ang), cs = cosf(ang), s2 = sinf(2 * ang), c2 = cosf(2 * ang);
+    a[p * 3 + p] = app * cs * cs + aqq * sn * sn + 2 * apq * cs * sn;
+    a[q * 3 + q] = app * sn * sn + aqq * cs * cs - 2 * apq * cs * sn;
+    a[p * 3 + q] = (float)(0.5 * (double)(aqq - app) * (double)s2 + (double)(apq * c2));
+    a[q * 3 + p] = a[p * 3 + q];
+    for (int i = 0; i < 3; i++)
+      if (i != q && i != p) {
+        float t = a[i * 3 + p];
+        a[i * 3 + p] = a[i * 3 + q] * sn + t * cs;
+        a[i * 3 + q] = a[i * 3 + q] * cs - t * sn;
+      }
+    for (int j = 0; j < 3; j++)
+      if (j != q && j != p) {
+        float t = a[p * 3 + j];
+        a[p * 3 + j] = a[q * 3 + j] * sn + t * cs;
+        a[q * 3 + j] = a[q * 3 + j] * cs - t * sn;
+      }
+    for (int i = 0; i < 3; i++) {
+      float t = V[i * 3 + p];
+      V[i * 3 + p] = V[i * 3 + q] * sn + t * cs;
+      V[i * 3 + q] = V[i * 3 + q] * cs - t * sn;
+    }
+  }
+  int best = 0;
+  float least = a[0];
+  for (int i = 1; i < 3; i++)
+    if (least > a[i * 3 + i]) { least = a[i * 3 + i]; best = i; }
+  for (int i = 0; i < 3; i++) vec[i] = V[best + 3 * i];
+}
+
+// G_Mapfeature, gpu_process.cu:547-668 (+ host wrapper :1254-1298).  Cells without elevation: 0 / 0 / -10 (the reference leaves
+// them unwritten).  Outputs may be NULL.
+void orc_elev_map_feature(void* h, float* elevation, float* var, int* R, int* G, int* B, float* rough, float* slope, float* traver,
+                          float* intensity) {
+  ElevMap* m = (ElevMap*)h;
+  const int L = m->L;
+  for (int idx = 0; idx < L * L; idx++) {
+    if (elevation) elevation[idx] = m->elevation[idx];
+    if (var) var[idx] = m->variance[idx];
+    if (R) R[idx] = m->R[idx];
+    if (G) G[idx] = m->G[idx];
+    if (B) B[idx] = m->B[idx];
+    if (intensity) intensity[idx] = m->intensity[idx];
+    float sl = 0, ro = 0, tr = -10;
+    if (m->elevation[idx] != -10) {
+      float X[25], Y[25], Z[25], mx = 0, my = 0, mz = 0;
+      int n = 0;
+      const int cx = idx / L, cy = idx % L;
+      for (int i = -2; i < 3; i++)
+        for (int j = -2; j < 3; j++) {
+          int gx = (cx + L - m->start[0]) % L + i, gy = (cy + L - m->start[1]) % L + j;
+          if (gx >= 0 && gx < L && gy >= 0 && gy < L) {
+            int px = (cx + i + L) % L, py = (cy + j + L) % L;
+            float z = m->elevation[(size_t)px * L + py];
+            if (z != -10) {
+              X[n] = px * m->res; Y[n] = py * m->res; Z[n] = z;
+              mx += X[n]; my += Y[n]; mz += Z[n];
+              n++;
+            }
+          }
+        }
+      if (n > 7) {
+        mx /= n; my /= n; mz /= n;
+        float M[9] = {0};
+        for (int i = 0; i < n; i++) {
+          M[0] = fmaf(X[i] - mx, X[i] - mx, M[0]);
+          M[4] = fmaf(Y[i] - my, Y[i] - my, M[4]);
+          M[8] = fmaf(Z[i] - mz, Z[i] - mz, M[8]);
+          M[1] = fmaf(X[i] - mx, Y[i] - my, M[1]);
+          M[2] = fmaf(X[i] - mx, Z[i] - mz, M[2]);
+          M[5] = fmaf(Y[i] - my, Z[i] - mz, M[5]);
+        }
+        M[3] = M[1]; M[6] = M[2]; M[7] = M[5];
+        float nv[3];
+        orc_min_eigvec3(M, nv, 0.01f, 30);
+        sl = nv[2] > 0 ? acosf(nv[2]) : acosf(-nv[2]);
+        ro = std::fabs(m->elevation[idx] - mz);
+        tr = (float)(0.5 * (1.0 - (double)sl / 0.6) + 0.5 * (1.0 - ((double)ro / 0.2)));
+      }
+      m->traver[idx] = tr;
+    }
+    if (slope) slope[idx] = sl;
+    if (rough) rough[idx] = ro;
+    if (traver) traver[idx] = tr;
+  }
+}
+
+// G_Raytracing + G_Clear_maplowest, gpu_process.cu:706-889, :232-239, with the reference's quirks (see csrc/elev_post.cu header)
+void orc_elev_raytracing(void* h) {
+  ElevMap* m = (ElevMap*)h;
+  const int L = m->L;
+  std::vector<float> out(m->elevation);
+  auto bound = [&](int cxx, int cyy, int obx, float robot) {
+    float x1 = (float)(cxx - obx), x2 = (float)cxx - robot;
+    float lo = m->lowest[(size_t)cxx * L + cyy];
+    float h2 = m->sensor_z - lo;
+    return fmaf(h2 / x2, x1, lo);
+  };
+  for (int i = 0; i < L * L; i++) {
+    if (!(m->traver[i] < m->obstacle_thr && m->elevation[i] != -10)) continue;
+    const int cx = i / L, cy = i % L;
+    const int ob[2] = {(cx + L - m->start[0]) % L, (cy + L - m->start[1]) % L};
+    int cur[2] = {ob[0], ob[1]};
+    int robot = (L % 2 == 0) ? (int)(float)(L / 2 - 0.5) : (int)(float)(L / 2);
+    float inc[2] = {(float)(ob[0] - robot), (float)(ob[1] - robot)};
+    int stepx = inc[0] > 0 ? 1 : (inc[0] == 0 ? 0 : -1), stepy = inc[1] > 0 ? 1 : (inc[1] == 0 ? 0 : -1);
+    if (stepx == 0 || stepy == 0) continue;
+    float limit = m->elevation[i];
+    float dis = sqrtf(fmaf(inc[0], inc[0], inc[1] * inc[1]));
+    float dir[2] = {inc[0] / dis, inc[1] / dis};
+    float thr = std::fabs(inc[0]) > std::fabs(inc[1]) ? (float)std::sqrt(0.25 + std::pow(0.5 / inc[0] * inc[1], 2))
+                                                       : (float)std::sqrt(0.25 + std::pow(0.5 / inc[1] * inc[0], 2));
+    float bx = (float)stepx / 2, by = (float)stepy / 2, tx = bx / dir[0], ty = by / dir[1], tprev = 0;
+    while (cur[0] >= 0 && cur[0] < L && cur[1] >= 0 && cur[1] < L) {
+      bool probe = cur[0] != ob[0] && cur[1] != ob[1] && !(m->lowest[(size_t)cur[0] * L + cur[1]] == 10);
+      if (tx > ty) {
+        if (ty - tprev > thr && probe) limit = std::min(limit, bound(cur[0], cur[1], ob[0], (float)robot));
+        cur[1] += stepy; by += (float)stepy; tprev = ty; ty = by / dir[1];
+      } else if (tx < ty) {
+        if (tx - tprev > thr && probe) limit = std::min(limit, bound(cur[0], cur[1], ob[0], (float)robot));
+        cur[0] += stepx; bx += (float)stepx; tprev = tx; tx = bx / dir[0];
+      } else {
+        if (tx - tprev > thr && probe) limit = std::min(limit, bound(cur[0], cur[1], ob[0], (float)robot));
+        cur[0] += stepx; cur[1] += stepy; bx += (float)stepx; by += (float)stepy; tprev = tx; tx = bx / dir[0]; ty = by / dir[1];
+      }
+    }
+    if (m->elevation[i] - 3 * sqrtf(m->variance[i]) > limit) out[i] = -10;
+  }
+  m->elevation.swap(out);
+  std::fill(m->lowest.begin(), m->lowest.end(), 10.f);
 }
 
 void orc_elev_get_map(void* h, float* elevation, float* variance, float* intensity, int* R, int* G, int* B, float* lowest) {

@@ -128,6 +128,8 @@ class ElevationRef:
         L.ref_elev_fuse.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 7
         L.ref_elev_mapvar_update.argtypes = [C.c_int, C.c_float]
         L.ref_elev_get_map.argtypes = [C.c_int] + [C.c_void_p] * 6
+        L.ref_elev_map_feature.argtypes = [C.c_int] + [C.c_void_p] * 9
+        L.ref_elev_raytracing.argtypes = [C.c_int]
         self.length, self.res = int(length), float(resolution)
         L.ref_elev_init(self.length, self.res, mahal, obst)
 
@@ -158,6 +160,20 @@ class ElevationRef:
 
     def mapvar_update(self, upd):
         self.L.ref_elev_mapvar_update(self.length, float(upd))
+
+    def map_feature(self):
+        """the reference's Map_feature: NOTE rough / slope / traver are only defined where elevation != -10, and the call updates
+        the resident traversability plane (which Raytracing reads)"""
+        n = self.length * self.length
+        out = dict(elevation=np.zeros(n, np.float32), var=np.zeros(n, np.float32), colorR=np.zeros(n, np.int32), colorG=np.zeros(n, np.int32),
+                   colorB=np.zeros(n, np.int32), rough=np.zeros(n, np.float32), slope=np.zeros(n, np.float32), traver=np.zeros(n, np.float32),
+                   intensity=np.zeros(n, np.float32))
+        self.L.ref_elev_map_feature(self.length, *[out[k].ctypes.data for k in ("elevation", "var", "colorR", "colorG", "colorB", "rough", "slope",
+                                                                              "traver", "intensity")])
+        return out
+
+    def raytracing(self):
+        self.L.ref_elev_raytracing(self.length)
 
     def get_map(self):
         n = self.length * self.length

@@ -14,6 +14,7 @@ void Fuse(int length, int point_num, int* point_index, int* point_colorR, int* p
 void Mapvar_update(int length, float var_update);
 void Map_feature(int length, float* elevation, float* var, int* colorR, int* colorG, int* colorB, float* rough, float* slope, float* traver,
                  float* intensity);
+void Raytracing(int length);
 
 template <typename M>
 static M fill(const float* p, int n) {
@@ -53,4 +54,12 @@ void ref_elev_get_map(int length, float* elevation, float* var, int* R, int* G, 
   cudaDeviceSynchronize();
   delete[] scratch;
 }
+// the full Map_feature output (rough / slope / traver are only defined where elevation != -10: the reference leaves the rest
+// of its freshly cudaMalloc'ed output planes unwritten)
+void ref_elev_map_feature(int length, float* elevation, float* var, int* R, int* G, int* B, float* rough, float* slope, float* traver,
+                          float* intensity) {
+  Map_feature(length, elevation, var, R, G, B, rough, slope, traver, intensity);
+  cudaDeviceSynchronize();
+}
+void ref_elev_raytracing(int length) { Raytracing(length); }
 }

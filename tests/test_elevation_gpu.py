@@ -214,3 +214,87 @@ def test_against_reference_kernels(gpu):
             assert np.array_equal(mg[k], mr[k])
         g.Mapvar_update(L, 0.002)
         rk.mapvar_update(0.002)
+
+
+def test_map_feature_and_raytracing_vs_reference_kernels(gpu):
+    """the traversability read-out (Map_feature) and the ray-tracing clean-up (Raytracing) that the node runs after
+    every Fuse, next to the reference's own kernels (oracle/_ref) over a sequence of frames.  The reference leaves rough / slope /
+    traver unwritten where elevation == -10, so those planes are compared on cells with elevation only."""
+    from oracle import ref
+    if not ref.available("elev"):
+        pytest.skip("oracle/_ref/libelev_ref.so not present")
+    L, res = 100, 0.2
+    rk = ref.ElevationRef(L, res)
+    g = elevation.ElevationMap()
+    g.Init_GPU_elevationmap(L, res, 2.5, 0.2)
+    removed_total, obstacles_total = 0, 0
+    for f in range(4):
+        pose, x, y, z, args = frame(f, "vlp16")
+        n = len(x)
+        pos = pose[:3, 3].astype(np.float32)
+        g.Move(pos, res, L)
+        rk.move(pos)
+        rg = g.Process_points(x, y, z, args[0], n, *args[1:])
+        rr = rk.process_points(x, y, z, *args)
+        assert np.array_equal(rg[0], rr[0])
+        R, G, B, I = colours(n, f)
+        g.Fuse(L, n, rg[0], R, G, B, I, rg[4], rg[1])
+        rk.fuse(rr[0], R, G, B, I, rr[4], rr[1])
+        fg, fr = g.Map_feature(L), rk.map_feature()
+        has = fr["elevation"] != -10
+        assert np.array_equal(fg["elevation"] != -10, has)
+        assert np.abs(fg["elevation"] - fr["elevation"]).max() <= 1e-5 and np.abs(fg["var"] - fr["var"]).max() <= 1e-6
+        for k in ("colorR", "colorG", "colorB"):
+            assert np.array_equal(fg[k], fr[k]), k
+        assert np.array_equal(fg["intensity"], fr["intensity"])
+        # cells whose heights are bit-identical must give bit-identical features (same arithmetic, same contraction)
+        same = has & (fg["elevation"] == fr["elevation"])
+        assert same.sum() > 0.9 * has.sum()
+        for k in ("rough", "slope", "traver"):
+            d = np.abs(fg[k][has] - fr[k][has])
+            assert d.max() <= 2e-4, (k, float(d.max()))
+            assert (d == 0).mean() > 0.99, (k, float((d == 0).mean()))
+        assert (fg["traver"][~has] == -10).all() and (fg["slope"][~has] == 0).all()       # our convention for empty cells
+        obstacles_total += int(((fr["traver"] < 0.2) & has).sum())
+        g.Raytracing(L)
+        rk.raytracing()
+        ag, ar = g.Map_feature(L), rk.map_feature()
+        assert np.array_equal(ag["elevation"] != -10, ar["elevation"] != -10)             # the same cells were cleaned up
+        assert np.abs(ag["elevation"] - ar["elevation"]).max() <= 1e-5
+        removed_total += int((has & (ar["elevation"] == -10)).sum())
+        assert (g.get_map()["lowest"] == 10).all()                                        # G_Clear_maplowest
+    assert obstacles_total > 0            # the ray walk was exercised
+    print("raytracing removed %d cells of %d obstacle cells over the sequence" % (removed_total, obstacles_total))
+
+
+def test_map_feature_and_raytracing_vs_oracle_full_size(gpu):
+    """the same post-passes at the benchmark's map size against the CPU twin (CPU libm: agreement to ~1e-6, with a few cells where a
+    Jacobi pivot / eigenvalue ordering flips on a rounding difference)"""
+    L, res = 1200, 0.1
+    g = elevation.ElevationMap()
+    g.Init_GPU_elevationmap(L, res, 2.5, 0.2)
+    o = oracle.ElevationMap(L, res, 2.5, 0.2)
+    for f in range(2):
+        pose, x, y, z, args = frame(f, "hdl64")
+        n = len(x)
+        pos = pose[:3, 3].astype(np.float32)
+        g.Move(pos, res, L)
+        o.move(pos)
+        rg = g.Process_points(x, y, z, args[0], n, *args[1:])
+        ro = o.process_points(x, y, z, *args)
+        zi = np.zeros(n, np.int32)
+        g.Fuse(L, n, rg[0], zi, zi, zi, np.zeros(n, np.float32), rg[4], rg[1])
+        o.fuse(ro[0], zi, zi, zi, np.zeros(n, np.float32), ro[4], ro[1])
+        fg, fo = g.Map_feature(L), o.map_feature()
+        assert np.array_equal(fg["elevation"], fo["elevation"]) and np.array_equal(fg["var"], fo["var"])
+        has = fo["elevation"] != -10
+        assert np.array_equal(fg["traver"] == -10, fo["traver"] == -10)
+        for k in ("rough", "slope", "traver"):
+            d = np.abs(fg[k] - fo[k])
+            assert (d <= 1e-4).mean() > 0.999, (k, float((d <= 1e-4).mean()), float(d.max()))
+        g.Raytracing(L)
+        o.raytracing()
+        eg, eo = g.get_map()["elevation"], o.get_map()["elevation"]
+        assert ((eg != -10) != (eo != -10)).sum() <= max(3, int(1e-4 * has.sum()))       # borderline cells of the height test only
+        assert (g.get_map()["lowest"] == 10).all()
+
