@@ -236,6 +236,11 @@ int mrslam_ring_tiring(const float* d_sino, int items, int channels, int n_angle
 /* fast_corr of query q against `n_db` database descriptors: dist[n_db], angle[n_db] (device) */
 int mrslam_ring_fast_corr(const float* d_query, const float* d_db, int n_db, int channels, int n_angles, int det_count,
                           float* d_dist, int* d_angle, float* d_corr_opt);
+/* solve_translation(query, positive, rot_angle) (RING/util.py:388-423) with the row roll of main_RING.py:171-172 folded in:
+ * per sinogram row the circular cross-correlation shift along the detector axis (b[n_angles], optional device output), then the
+ * least-squares x, y and the residual norm -> xy_err3 (HOST, 3 floats).  d_query / d_positive: float [channels, n_angles, det]. */
+int mrslam_ring_solve_translation(const float* d_query, const float* d_positive, int channels, int n_angles, int det_count,
+                                  float rot_angle, int row_shift, float* d_row_shift_opt, float* xy_err3);
 /* fused generate_RING for a batch of BEV images: Radon -> normalise -> FFT (one kernel per image) */
 int mrslam_ring_generate(const float* d_bev, int batch, int size, const float* d_angles, int n_angles, int interp,
                          int fast_trig, float* d_sino_opt, float* d_tiring);

@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(256) k_ring_fast_corr(const float* __restrict_
 }
 
 struct RadonScratch {
-  DevBuf<float> stats, sino;
+  DevBuf<float> stats, sino, shifts;
 };
 static RadonScratch& rs() {
   static RadonScratch s;
@@ -304,6 +304,79 @@ static int tiring_launch(const float* d_sino, int items, int C, int A, int D, fl
 
 using namespace mrslam;
 
+// solve_translation (src/RING_ros/util.py:388-423).  For every sinogram row i: circular cross-correlation of the query row with
+// the (row-rolled) matched row along the detector axis, magnitude, summed over the channels, fftshift, first argmax ->
+// b[i] = W/2 - argmax.  corr[k] = 1/sqrt(W) * sum_n q[n] p[(n - k) mod W] (what ifft(fft(q) conj(fft(p))) with "ortho" norms gives
+// for real rows), evaluated directly: W = 120 makes the FFT pointless.  One block per row, one thread per lag.
+__global__ void __launch_bounds__(128) k_ring_row_shift(const float* __restrict__ q, const float* __restrict__ p, int C, int H, int W,
+                                                       int row_shift, float* __restrict__ b_out) {
+  extern __shared__ float sm[];
+  float* sq = sm;            // W
+  float* sp = sm + W;        // W
+  float* corr = sm + 2 * W;  // W (fftshift-ed order)
+  const int i = blockIdx.x;
+  int ip = (i - row_shift) % H;  // torch.roll(RING_matched, row_shift, dims=1)[i] = RING_matched[(i - row_shift) mod H]
+  if (ip < 0) ip += H;
+  const float scale = (float)(1.0 / sqrt((double)W));
+  for (int k = threadIdx.x; k < W; k += blockDim.x) corr[k] = 0.f;
+  for (int c = 0; c < C; c++) {
+    __syncthreads();
+    for (int n = threadIdx.x; n < W; n += blockDim.x) {
+      sq[n] = q[((size_t)c * H + i) * W + n];
+      sp[n] = p[((size_t)c * H + ip) * W + n];
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < W; k += blockDim.x) {
+      float acc = 0.f;
+      int m = (W - k) % W;  // (n - k) mod W for n = 0
+      for (int n = 0; n < W; n++) {
+        acc = fmaf(sq[n], sp[m], acc);
+        if (++m == W) m = 0;
+      }
+      // torch.fft.fftshift: out[j] = in[(j - W/2) mod W]  <=>  in[k] lands at j = (k + W/2) mod W
+      corr[(k + W / 2) % W] += fabsf(acc * scale);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int am = 0;
+    float best = corr[0];
+    for (int j = 1; j < W; j++)
+      if (corr[j] > best) {
+        best = corr[j];
+        am = j;
+      }
+    b_out[i] = (float)(W / 2 - am);
+  }
+}
+
+// least squares of A [x y]^T = b with A = [cos(a_i) sin(a_i)], a_i = linspace(0, 2 pi, H)_i (float32, as numpy) + rot_angle
+// (util.py:391-399, :488-506 `svd` pseudo-inverse == the normal equations for this full-rank 2-column system); double sums.
+// out[0..2] = x, y, ||A [x y]^T - b||.
+__global__ void k_ring_translation_lsq(const float* __restrict__ b, int H, float rot_angle, float* __restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double scc = 0, sss = 0, scs = 0, scb = 0, ssb = 0;
+  for (int i = 0; i < H; i++) {
+    // np.linspace(0, 2*pi, H).astype(float32): i * step in double (last element = stop exactly), then the cast
+    const float lin = (i == H - 1) ? (float)(2.0 * M_PI) : (float)((double)i * (2.0 * M_PI / (double)(H - 1)));
+    const float a = lin + rot_angle;
+    const double c = (double)cosf(a), s = (double)sinf(a);
+    scc += c * c; sss += s * s; scs += c * s; scb += c * (double)b[i]; ssb += s * (double)b[i];
+  }
+  const double det = scc * sss - scs * scs;
+  const double x = (sss * scb - scs * ssb) / det, y = (scc * ssb - scs * scb) / det;
+  double err = 0;
+  for (int i = 0; i < H; i++) {
+    const float lin = (i == H - 1) ? (float)(2.0 * M_PI) : (float)((double)i * (2.0 * M_PI / (double)(H - 1)));
+    const float a = lin + rot_angle;
+    const double r = (double)cosf(a) * x + (double)sinf(a) * y - (double)b[i];
+    err += r * r;
+  }
+  out[0] = (float)x;
+  out[1] = (float)y;
+  out[2] = (float)sqrt(err);
+}
+
 extern "C" {
 
 int mrslam_radon_forward(const float* d_img, int batch, int height, int width, const float* d_angles, int n_angles, int det_count,
@@ -348,5 +421,25 @@ int mrslam_ring_generate(const float* d_bev, int batch, int size, const float* d
   // generate_RING: ParallelBeam(num_sector, angles).forward(bev[1, ring, sector]) -> [1, n_angles, det = size]
   MR_CHECK(radon_launch(d_bev, batch, size, size, d_angles, n_angles, size, 1.0f, interp, fast_trig, sino));
   return tiring_launch(sino, batch, 1, n_angles, size, d_tiring);
+}
+int mrslam_ring_solve_translation(const float* d_query, const float* d_positive, int channels, int n_angles, int det_count, float rot_angle,
+                                  int row_shift, float* d_row_shift_opt, float* xy_err3) {
+  MR_CHECK(ensure_init());
+  if (channels <= 0 || n_angles < 2 || det_count <= 0 || !d_query || !d_positive || !xy_err3) {
+    set_error("ring_solve_translation: bad arguments");
+    return MRSLAM_ERR_ARG;
+  }
+  std::lock_guard<std::mutex> lk(rt().mu);
+  MR_CHECK(rs().shifts.reserve((size_t)n_angles + 4));
+  float* b = d_row_shift_opt ? d_row_shift_opt : rs().shifts.p;
+  float* out = rs().shifts.p + n_angles;
+  k_ring_row_shift<<<n_angles, 128, 3 * (size_t)det_count * sizeof(float), rt().stream>>>(d_query, d_positive, channels, n_angles, det_count,
+                                                                                         row_shift, b);
+  k_ring_translation_lsq<<<1, 32, 0, rt().stream>>>(b, n_angles, rot_angle, out);
+  count_launch(2);
+  MR_CUDA(cudaGetLastError());
+  MR_CUDA(cudaMemcpyAsync(xy_err3, out, 3 * sizeof(float), cudaMemcpyDeviceToHost, rt().stream));
+  MR_CUDA(cudaStreamSynchronize(rt().stream));
+  return MRSLAM_OK;
 }
 }

@@ -82,3 +82,23 @@ def fast_corr_batch(query, database, want_corr=False):
     check(lib().mrslam_ring_fast_corr(ptr(q), ptr(db), N, C, A, D, ptr(dist), ptr(ang), ptr(corr) if want_corr else None))
     _sync()
     return (dist, ang, corr) if want_corr else (dist, ang)
+
+
+def calculate_row_shift(shift, num_ring=120):
+    """util.py:377-383: circular row shift that compensates the matched yaw (in grid units)"""
+    return -shift if shift < num_ring // 2 else shift - num_ring
+
+
+def solve_translation(query, positive, rot_angle, device=None, row_shift=0, want_shifts=False):
+    """solve_translation(query, positive, rot_angle, device) of RING/util.py:388-423: query / positive are CUDA float32 sinograms
+    [B, H, W] (B = channels).  row_shift folds main_RING.py's torch.roll(RING_matched, row_shift, dims=1) into the call (pass the
+    unrolled RING_matched).  Returns (x, y, error) as numpy scalars like the reference (and the per-row shifts b[H] on request)."""
+    q, p = query.contiguous().float(), positive.contiguous().float()
+    B, H, W = q.shape
+    out = np.zeros(3, np.float32)
+    b = torch.empty(H, dtype=torch.float32, device=q.device) if want_shifts else None
+    torch.cuda.current_stream(q.device).synchronize()
+    check(lib().mrslam_ring_solve_translation(ptr(q), ptr(p), B, H, W, float(rot_angle), int(row_shift), ptr(b) if want_shifts else None,
+                                              out.ctypes.data))
+    x, y, err = np.float32(out[0]), np.float32(out[1]), np.float32(out[2])
+    return (x, y, err, b) if want_shifts else (x, y, err)

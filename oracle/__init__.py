@@ -84,6 +84,7 @@ def _decl(L):
     L.orc_radon_forward.argtypes = [_p(np.float32), i, i, i, _p(np.float32), i, i, f, i, _p(np.float32)]
     L.orc_ring_tiring.argtypes = [_p(np.float32), i, i, i, C.c_void_p, _p(np.float32)]
     L.orc_ring_fast_corr.argtypes = [_p(np.float32), _p(np.float32), i, i, i, _p(np.float32), C.POINTER(f), C.POINTER(i)]
+    L.orc_ring_solve_translation.argtypes = [_p(np.float32), _p(np.float32), i, i, i, f, i, _p(np.float32), _p(np.float32)]
 
 
 def num_procs():
@@ -346,3 +347,13 @@ def ring_fast_corr(a, b):
     dist, ang = C.c_float(), C.c_int()
     lib().orc_ring_fast_corr(il(a), il(b), Cc, A, D, corr, C.byref(dist), C.byref(ang))
     return dist.value, ang.value, corr
+
+
+def ring_solve_translation(query, positive, rot_angle, row_shift=0):
+    """solve_translation (RING/util.py:388-423) on float32 [C,H,W] arrays; returns (x, y, error, b[H])."""
+    q, p = _f32(query), _f32(positive)
+    Cc, H, W = q.shape
+    b = np.zeros(H, np.float32)
+    out = np.zeros(3, np.float32)
+    lib().orc_ring_solve_translation(q.reshape(-1), p.reshape(-1), Cc, H, W, float(rot_angle), int(row_shift), b, out)
+    return float(out[0]), float(out[1]), float(out[2]), b

@@ -183,4 +183,48 @@ void orc_ring_fast_corr(const float* a, const float* b, int C, int A, int D, flo
   *dist = 1.0f - (float)sh[am] / (float)(0.15 * A * D);
   *angle = -am + A / 2;
 }
+
+// solve_translation (util.py:388-423) with the row roll of main_RING.py:171-172: q, p float [C,H,W].
+// corr_i[k] = 1/sqrt(W) sum_n q[i][n] p[i'][(n-k) mod W] in double (the reference: float FFTs), |.|, channel sum, fftshift, first
+// argmax -> b[i] = W/2 - argmax; then least squares on A = [cos sin](linspace(0,2pi,H) + rot).  out3 = x, y, ||A[x y]-b||.
+void orc_ring_solve_translation(const float* q, const float* p, int C, int H, int W, float rot_angle, int row_shift, float* b_out,
+                                float* out3) {
+  std::vector<double> corr(W);
+  std::vector<float> b(H);
+  const double scale = 1.0 / std::sqrt((double)W);
+  for (int i = 0; i < H; i++) {
+    int ip = ((i - row_shift) % H + H) % H;
+    std::fill(corr.begin(), corr.end(), 0.0);
+    for (int c = 0; c < C; c++) {
+      const float* qr = q + ((size_t)c * H + i) * W;
+      const float* pr = p + ((size_t)c * H + ip) * W;
+      for (int k = 0; k < W; k++) {
+        double acc = 0;
+        for (int n = 0; n < W; n++) acc += (double)qr[n] * (double)pr[((n - k) % W + W) % W];
+        corr[(k + W / 2) % W] += std::fabs(acc * scale);
+      }
+    }
+    int am = 0;
+    for (int j = 1; j < W; j++)
+      if ((float)corr[j] > (float)corr[am]) am = j;
+    b[i] = (float)(W / 2 - am);
+    if (b_out) b_out[i] = b[i];
+  }
+  double scc = 0, sss = 0, scs = 0, scb = 0, ssb = 0;
+  std::vector<double> cs(H), sn(H);
+  for (int i = 0; i < H; i++) {
+    float lin = (i == H - 1) ? (float)(2.0 * M_PI) : (float)((double)i * (2.0 * M_PI / (double)(H - 1)));
+    float a = lin + rot_angle;
+    cs[i] = (double)cosf(a);
+    sn[i] = (double)sinf(a);
+    scc += cs[i] * cs[i]; sss += sn[i] * sn[i]; scs += cs[i] * sn[i]; scb += cs[i] * b[i]; ssb += sn[i] * b[i];
+  }
+  double det = scc * sss - scs * scs;
+  double x = (sss * scb - scs * ssb) / det, y = (scc * ssb - scs * scb) / det, err = 0;
+  for (int i = 0; i < H; i++) {
+    double r = cs[i] * x + sn[i] * y - b[i];
+    err += r * r;
+  }
+  out3[0] = (float)x; out3[1] = (float)y; out3[2] = (float)std::sqrt(err);
+}
 }

@@ -83,6 +83,37 @@ def ring():
     pc = (rng.random((5000, 4)).astype(np.float32) - 0.5) * np.array([200, 200, 80, 1], np.float32)
     out["pc"] = pc
     out["pc_infer"] = util.load_pc_infer(pc)
+    # solve_translation (util.py:388-423) after the row roll of main_RING.py:171-172, run by the reference itself; the per-row
+    # shifts b are captured by wrapping util.solve_overdetermined_linear_system (its second argument)
+    captured = {}
+    orig_lsq = util.solve_overdetermined_linear_system
+
+    def spy(A, b, method="pinv"):
+        captured["b"] = b.clone().numpy()
+        return orig_lsq(A, b, method=method)
+    util.solve_overdetermined_linear_system = spy
+    H = W = 120
+    cases = []
+    for ci, (tx, ty, rot, rs, nch) in enumerate([(7.0, -4.0, 0.0, 0, 1), (-11.0, 5.5, 0.6, 13, 1), (3.0, 9.0, -1.1, -29, 2)]):
+        base = (rng.random((nch, H, W)) * (rng.random((nch, H, W)) < 0.15)).astype(np.float32) * 20
+        ker = np.array([0.25, 0.5, 0.25], np.float32)
+        base = sum(np.roll(base, d - 1, axis=2) * ker[d] for d in range(3))          # a little smoothing along the detector axis
+        ang = np.linspace(0, 2 * np.pi, H).astype(np.float32) + np.float32(rot)
+        pos = np.stack([np.stack([np.roll(base[c, i], -int(round(tx * np.cos(ang[i]) + ty * np.sin(ang[i])))) for i in range(H)])
+                        for c in range(nch)]).astype(np.float32)
+        pos += (rng.random(pos.shape).astype(np.float32) - 0.5) * 0.05
+        pos_unrolled = np.roll(pos, -rs, axis=1)                                      # what the database holds (RING_matched)
+        q_t = torch.from_numpy(base)
+        p_t = torch.roll(torch.from_numpy(pos_unrolled), rs, dims=1)                  # main_RING.py:171
+        x, y, err = util.solve_translation(q_t, p_t, float(rot), util.device)
+        out["st%d_query" % ci] = base
+        out["st%d_positive" % ci] = pos_unrolled
+        out["st%d_params" % ci] = np.array([rot, rs], np.float32)
+        out["st%d_b" % ci] = captured["b"].astype(np.float32)
+        out["st%d_xye" % ci] = np.array([float(x), float(y), float(err)], np.float32)
+        cases.append((float(x), float(y), float(err)))
+    util.solve_overdetermined_linear_system = orig_lsq
+    print("solve_translation goldens (x, y, err):", cases)
     np.savez_compressed(os.path.join(HERE, "ring_fixture.npz"), **out)
     print("ring fixture: fast_corr dist", out["fast_corr_dist"].tolist(), "angle", out["fast_corr_angle"].tolist(), "rolled ->", int(angle))
 

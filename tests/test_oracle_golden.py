@@ -211,3 +211,21 @@ def test_ring_tail_oracle_vs_reference_python():
     # load_pc_infer restatement used by the bench
     got = synth.ring_preprocess(z["pc"])
     assert np.array_equal(got, z["pc_infer"])  # the reference keeps all columns of the surviving rows
+
+
+def test_solve_translation_oracle_vs_reference_python():
+    """solve_translation (util.py:388-423) goldens produced by the reference's own function.  The per-row shifts b are bit-equal in
+    all cases.  x, y: the reference multiplies by v.t() where torch.svd's V itself is needed (util.py:506); that is harmless only
+    when V happens to be symmetric (cases 0 and 2) -- in case 1 LAPACK returned a rotation and the reference's own answer has a
+    residual of 108 against 3.0 for the least-squares solution.  The oracle (and the CUDA path) return the least-squares solution."""
+    z = np.load(os.path.join(GOLDEN, "ring_fixture.npz"))
+    for ci in range(3):
+        rot, rs = z["st%d_params" % ci]
+        x, y, e, b = oracle.ring_solve_translation(z["st%d_query" % ci], z["st%d_positive" % ci], float(rot), int(rs))
+        assert np.array_equal(b, z["st%d_b" % ci])
+        gx, gy, ge = z["st%d_xye" % ci]
+        if ci != 1:
+            assert abs(x - gx) < 1e-4 and abs(y - gy) < 1e-4 and abs(e - ge) < 1e-4
+        else:
+            assert e < 5.0 < ge and abs(x - 11.0) < 0.1 and abs(y + 5.5) < 0.1       # the shifts encode (tx, ty) = (-11, 5.5)
+

@@ -124,3 +124,26 @@ def test_generate_ring_pipeline_descriptor_tolerance(gpu):
     big = bev.repeat(64, 1, 1)
     _, tb = ring.generate_RING_batch(big, interp="exact", fast_trig=False)
     assert torch.equal(tb[:4], tir) and torch.equal(tb[252:], tir)
+
+
+def test_solve_translation_vs_reference_python_and_oracle(gpu):
+    """the python row loop of solve_translation as one kernel.  Per-row shifts bit-equal to the reference's own
+    (golden) and the oracle's; x / y / error within 1e-4 of the oracle (least-squares solution, see the CPU test for the reference's
+    v.t() slip)."""
+    z = np.load(os.path.join(GOLDEN, "ring_fixture.npz"))
+    for ci in range(3):
+        rot, rs = z["st%d_params" % ci]
+        q = torch.from_numpy(z["st%d_query" % ci]).cuda()
+        pos = torch.from_numpy(z["st%d_positive" % ci]).cuda()
+        x, y, e, b = ring.solve_translation(q, pos, float(rot), row_shift=int(rs), want_shifts=True)
+        ox, oy, oe, ob = oracle.ring_solve_translation(z["st%d_query" % ci], z["st%d_positive" % ci], float(rot), int(rs))
+        assert np.array_equal(b.cpu().numpy(), z["st%d_b" % ci]) and np.array_equal(ob, z["st%d_b" % ci])
+        assert abs(x - ox) < 1e-4 and abs(y - oy) < 1e-4 and abs(e - oe) < 1e-3
+        # the reference's calling convention: roll first, no row_shift argument
+        x2, y2, e2 = ring.solve_translation(q, torch.roll(pos, int(rs), dims=1), float(rot), q.device)
+        assert (x2, y2, e2) == (x, y, e)
+        if ci != 1:
+            gx, gy, ge = z["st%d_xye" % ci]
+            assert abs(x - gx) < 1e-4 and abs(y - gy) < 1e-4 and abs(e - ge) < 1e-3
+    assert ring.calculate_row_shift(17) == -17 and ring.calculate_row_shift(100) == -20
+
