@@ -68,6 +68,15 @@ int mrslam_cloud_create_device_batch(const float* const* d_xyz, const int* n, in
 void mrslam_cloud_destroy(mrslam_cloud_t*);
 int mrslam_cloud_size(const mrslam_cloud_t*);
 
+/* GlobalManager::mergeNearestKeyframes (Mapping/src/global_manager/src/global_manager.cpp:1894-1939), the front of ICPCheck:
+ * `count` keyframe clouds (x,y,z[,intensity] points `stride_floats` apart; host pointers, or device pointers when on_device != 0)
+ * are transformed by their row-major 4x4 T16[i] (= currPose^-1 * nearPose, computed by the caller), concatenated, cropped to
+ * |x|,|y| <= xy_limit (pcl::PassThrough, 60 m in the node) and reduced by a pcl::VoxelGrid centroid filter with cubic `leaf`
+ * (icp_filter_size).  Output: DEVICE buffer d_out_xyzi of `capacity` points (x,y,z,intensity), *n_out points written, voxels in
+ * ascending voxel index like PCL; feed it to mrslam_cloud_create_device(d_out_xyzi, *n_out, 4).  capacity = sum n is always enough. */
+int mrslam_keyframe_merge(const float* const* clouds, const int* n, int stride_floats, int count, const float* T16, float xy_limit,
+                          float leaf, int on_device, float* d_out_xyzi, int capacity, int* n_out);
+
 mrslam_gicp_t* mrslam_gicp_create(void);                              /* FastGICP() ctor: fast_gicp_impl.hpp:9-24 defaults */
 void mrslam_gicp_destroy(mrslam_gicp_t*);
 int mrslam_gicp_set_num_threads(mrslam_gicp_t*, int n);               /* setNumThreads: accepted, no effect on the GPU */

@@ -301,3 +301,35 @@ def downsample(points, downsample_resolution):
         if cnt[hh]:
             out.append(cen[hh] / np.float32(cnt[hh]))
     return np.array(out, np.float32).astype(np.float64).reshape(-1, 3)
+
+
+def merge_nearest_keyframes(keyframes, transforms, xy_limit=60.0, leaf=0.2, as_cloud=False):
+    """GlobalManager::mergeNearestKeyframes (global_manager.cpp:1894-1939) on the GPU: keyframes = list of (n_i, 3|4) float32
+    arrays (numpy -> host path) or CUDA torch tensors (device path), transforms = (k,4,4) float32 (currPose^-1 * nearPose).
+    Returns the filtered (m,4) x,y,z,intensity array (numpy), or (torch CUDA tensor [m,4], Cloud) when as_cloud=True."""
+    import torch
+    k = len(keyframes)
+    T = np.ascontiguousarray(np.asarray(transforms, np.float32).reshape(k, 16))
+    on_dev = k > 0 and hasattr(keyframes[0], "data_ptr")
+    if on_dev:
+        kfs = [t.contiguous().float() for t in keyframes]
+        ptrs = (C.c_void_p * k)(*[t.data_ptr() for t in kfs])
+        ns = [int(t.shape[0]) for t in kfs]
+        stride = int(kfs[0].shape[1]) if k else 3
+    else:
+        kfs = [np.ascontiguousarray(a, np.float32) for a in keyframes]
+        ptrs = (C.c_void_p * k)(*[a.ctypes.data for a in kfs])
+        ns = [int(a.shape[0]) for a in kfs]
+        stride = int(kfs[0].shape[1]) if k else 3
+    total = max(sum(ns), 1)
+    out = torch.empty((total, 4), dtype=torch.float32, device="cuda")
+    n_out = C.c_int(0)
+    torch.cuda.current_stream().synchronize()
+    check(lib().mrslam_keyframe_merge(ptrs, (C.c_int * k)(*ns), stride, k, ptr(T), float(xy_limit), float(leaf), 1 if on_dev else 0,
+                                      out.data_ptr(), total, C.byref(n_out)))
+    m = n_out.value
+    if as_cloud:
+        return out[:m], Cloud(device_ptr=out.data_ptr(), n=m, stride=4)
+    lib().mrslam_device_synchronize()
+    return out[:m].cpu().numpy()
+

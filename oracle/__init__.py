@@ -357,3 +357,20 @@ def ring_solve_translation(query, positive, rot_angle, row_shift=0):
     out = np.zeros(3, np.float32)
     lib().orc_ring_solve_translation(q.reshape(-1), p.reshape(-1), Cc, H, W, float(rot_angle), int(row_shift), b, out)
     return float(out[0]), float(out[1]), float(out[2]), b
+
+
+def merge_nearest_keyframes(keyframes, transforms, xy_limit=60.0, leaf=0.2):
+    """mergeNearestKeyframes (global_manager.cpp:1894-1939): list of (n_i, 3|4) float32 arrays + (k,4,4) transforms -> (m,4) xyzi."""
+    k = len(keyframes)
+    kfs = [np.ascontiguousarray(a, np.float32) for a in keyframes]
+    T = np.ascontiguousarray(np.asarray(transforms, np.float32).reshape(k, 16))
+    ptrs = (C.c_void_p * k)(*[a.ctypes.data for a in kfs])
+    ns = (C.c_int * k)(*[a.shape[0] for a in kfs])
+    total = max(sum(a.shape[0] for a in kfs), 1)
+    out = np.zeros((total, 4), np.float32)
+    fn = lib().orc_keyframe_merge
+    fn.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.c_int, C.c_int, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_int]
+    m = fn(ptrs, ns, kfs[0].shape[1] if k else 3, k, T.ctypes.data, float(xy_limit), float(leaf), out.ctypes.data, total)
+    assert m >= 0
+    return out[:m].copy()
+

@@ -858,3 +858,80 @@ int orc_num_procs() {
 #endif
 }
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// GlobalManager::mergeNearestKeyframes (Mapping/src/global_manager/src/global_manager.cpp:1894-1939): transform + concat,
+// PassThrough |x|,|y| <= limit, VoxelGrid centroid filter.  PCL 1.10 (absent third-party dependency) restated from its
+// published sources: common/impl/transforms.hpp (se3: x' = m00 x + (m01 y + (m02 z + m03)), SSE mul/add), filters/impl/
+// passthrough.hpp, filters/impl/voxel_grid.hpp (applyFilter).  PCL's std::sort leaves the summation order inside a voxel
+// unspecified; ascending input order is used here (std::stable_sort).  TEST INFRASTRUCTURE.
+// ---------------------------------------------------------------------------------------------------------------------
+extern "C" int orc_keyframe_merge(const float* const* clouds, const int* n, int stride, int count, const float* T16, float lim, float leaf,
+                                  float* out_xyzi, int capacity) {
+  struct P { float x, y, z, w; };
+  std::vector<P> pts;
+  for (int c = 0; c < count; c++) {
+    const float* T = T16 + (size_t)c * 16;
+    for (int i = 0; i < n[c]; i++) {
+      const float* p = clouds[c] + (size_t)i * stride;
+      float x = p[0], y = p[1], z = p[2], w = stride > 3 ? p[3] : 0.f;
+      P q;
+      q.x = T[0] * x + (T[1] * y + (T[2] * z + T[3]));
+      q.y = T[4] * x + (T[5] * y + (T[6] * z + T[7]));
+      q.z = T[8] * x + (T[9] * y + (T[10] * z + T[11]));
+      q.w = w;
+      if (!std::isfinite(q.x) || !std::isfinite(q.y) || !std::isfinite(q.z)) continue;
+      if (q.x > lim || q.x < -lim) continue;
+      if (q.y > lim || q.y < -lim) continue;
+      pts.push_back(q);
+    }
+  }
+  if (pts.empty()) return 0;
+  float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+  for (const P& q : pts) {
+    mn[0] = std::min(mn[0], q.x); mn[1] = std::min(mn[1], q.y); mn[2] = std::min(mn[2], q.z);
+    mx[0] = std::max(mx[0], q.x); mx[1] = std::max(mx[1], q.y); mx[2] = std::max(mx[2], q.z);
+  }
+  const float inv = 1.0f / leaf;
+  long long d[3];
+  for (int a = 0; a < 3; a++) d[a] = (long long)((mx[a] - mn[a]) * inv) + 1;
+  if (d[0] * d[1] * d[2] > (long long)INT32_MAX) {  // "Leaf size is too small": output = input
+    if ((int)pts.size() > capacity) return -1;
+    memcpy(out_xyzi, pts.data(), pts.size() * sizeof(P));
+    return (int)pts.size();
+  }
+  int min_b[3], div_b[3];
+  for (int a = 0; a < 3; a++) {
+    min_b[a] = (int)std::floor(mn[a] * inv);
+    div_b[a] = (int)std::floor(mx[a] * inv) - min_b[a] + 1;
+  }
+  const int mul[3] = {1, div_b[0], div_b[0] * div_b[1]};
+  std::vector<std::pair<int, int>> idx(pts.size());
+  for (size_t i = 0; i < pts.size(); i++) {
+    int i0 = (int)(std::floor(pts[i].x * inv) - (float)min_b[0]);
+    int i1 = (int)(std::floor(pts[i].y * inv) - (float)min_b[1]);
+    int i2 = (int)(std::floor(pts[i].z * inv) - (float)min_b[2]);
+    idx[i] = {i0 * mul[0] + i1 * mul[1] + i2 * mul[2], (int)i};
+  }
+  std::stable_sort(idx.begin(), idx.end(), [](const std::pair<int, int>& a, const std::pair<int, int>& b) { return a.first < b.first; });
+  int m = 0;
+  for (size_t i = 0; i < idx.size();) {
+    size_t j = i;
+    float sx = 0, sy = 0, sz = 0, sw = 0;
+    while (j < idx.size() && idx[j].first == idx[i].first) {
+      const P& q = pts[idx[j].second];
+      sx += q.x; sy += q.y; sz += q.z; sw += q.w;
+      j++;
+    }
+    float c = (float)(j - i);
+    if (m >= capacity) return -1;
+    out_xyzi[4 * (size_t)m + 0] = sx / c;
+    out_xyzi[4 * (size_t)m + 1] = sy / c;
+    out_xyzi[4 * (size_t)m + 2] = sz / c;
+    out_xyzi[4 * (size_t)m + 3] = sw / c;
+    m++;
+    i = j;
+  }
+  return m;
+}
+

@@ -270,3 +270,37 @@ def test_full_size_120k_properties(gpu):
     moved = (src[sel].astype(np.float64) @ Tf[:3, :3].astype(np.float64).T + Tf[:3, 3]).astype(np.float32)
     bi, bd = oracle.knn(tgt, moved, 1)
     assert (bi[:, 0] == corr[sel]).mean() > 0.995          # (rounding of the re-transformed query can flip exact near-ties)
+
+
+def test_keyframe_merge_matches_oracle(gpu):
+    """mergeNearestKeyframes (transform + concat + PassThrough + VoxelGrid centroids) as the GICP front end:
+    host-pointer and device-pointer paths bit-equal to the oracle (same voxel order, same summation order), and the merged cloud
+    feeds a registration directly on the device"""
+    import torch
+    from test_oracle_golden import _merge_case
+    for nkf, kind, leaf, lim in [(3, "vlp16", 0.4, 20.0), (5, "hdl64", 0.2, 60.0)]:
+        kfs, Ts = _merge_case(nkf, kind)
+        exp = oracle.merge_nearest_keyframes(kfs, Ts, lim, leaf)
+        got_h = pygicp.merge_nearest_keyframes(kfs, Ts, lim, leaf)
+        assert got_h.shape == exp.shape and np.array_equal(got_h, exp)
+        dev = [torch.from_numpy(k).cuda() for k in kfs]
+        got_d = pygicp.merge_nearest_keyframes(dev, Ts, lim, leaf)
+        assert np.array_equal(got_d, exp)
+        xyz_only = pygicp.merge_nearest_keyframes([k[:, :3].copy() for k in kfs], Ts, lim, leaf)       # stride 3: intensity = 0
+        assert np.array_equal(xyz_only[:, :3], exp[:, :3]) and (xyz_only[:, 3] == 0).all()
+    # leaf too small -> unfiltered (PCL warning path); empty input
+    kfs, Ts = _merge_case(1, "vlp16")
+    assert np.array_equal(pygicp.merge_nearest_keyframes(kfs, Ts, 20.0, 1e-4), oracle.merge_nearest_keyframes(kfs, Ts, 20.0, 1e-4))
+    assert len(pygicp.merge_nearest_keyframes([np.zeros((0, 4), np.float32)], np.eye(4, dtype=np.float32)[None])) == 0
+    # ICPCheck: both clouds merged on the device, then aligned without leaving it
+    kfs, Ts = _merge_case(3, "vlp16")
+    T_true = synth.pose_matrix(0.3, -0.2, 0.05, 0.04).astype(np.float32)
+    src_t, src_c = pygicp.merge_nearest_keyframes(kfs, Ts, 60.0, 0.4, as_cloud=True)
+    tgt_t, tgt_c = pygicp.merge_nearest_keyframes(kfs, np.stack([T_true @ T for T in Ts]), 60.0, 0.4, as_cloud=True)
+    g = make(pygicp.FastGICP, src_c, tgt_c, max_corr=2.0)
+    T = g.align(np.eye(4, dtype=np.float32))
+    o = make(oracle.FastGICP, src_t[:, :3].cpu().numpy(), tgt_t[:, :3].cpu().numpy(), max_corr=2.0)
+    To = o.align(np.eye(4, dtype=np.float32))
+    assert np.abs(T - To).max() < TOL_T
+    assert synth.pose_error(T, T_true)[0] < 0.05
+

@@ -229,3 +229,40 @@ def test_solve_translation_oracle_vs_reference_python():
         else:
             assert e < 5.0 < ge and abs(x - 11.0) < 0.1 and abs(y + 5.5) < 0.1       # the shifts encode (tx, ty) = (-11, 5.5)
 
+
+def _merge_case(nkf=3, kind="vlp16"):
+    kfs, Ts = [], []
+    P0 = synth.pose_matrix(0.5, -0.2, 0.0, 0.1)
+    for f in range(nkf):
+        pose = synth.pose_matrix(1.5 * f - 1.0, 0.4 * f, 0.0, 0.05 * f)
+        pts = synth.make_scan(pose, kind, scan_id=300 + f).astype(np.float32)
+        inten = np.random.default_rng(f).random((len(pts), 1)).astype(np.float32)
+        kfs.append(np.hstack([pts, inten]))
+        Ts.append((np.linalg.inv(P0) @ pose).astype(np.float32))
+    return kfs, np.stack(Ts)
+
+
+def test_keyframe_merge_oracle_properties():
+    """mergeNearestKeyframes restated from PCL 1.10's published VoxelGrid / PassThrough / transformPointCloud (PCL is absent: parity
+    unpinned by reference artefacts, see oracle/gicp_oracle.cpp).  Properties the algorithm guarantees: one output per occupied
+    voxel, each output inside its voxel and inside the crop, ascending voxel index, means of the members, idempotent count."""
+    kfs, Ts = _merge_case()
+    leaf, lim = 0.4, 20.0
+    out = oracle.merge_nearest_keyframes(kfs, Ts, lim, leaf)
+    allp = np.concatenate([(k[:, :3] @ T[:3, :3].T + T[:3, 3]).astype(np.float32) for k, T in zip(kfs, Ts)])
+    keep = (np.abs(allp[:, 0]) <= lim) & (np.abs(allp[:, 1]) <= lim)
+    assert (np.abs(out[:, 0]) <= lim).all() and (np.abs(out[:, 1]) <= lim).all()
+    inv = np.float32(1.0) / np.float32(leaf)
+    vox_in = np.unique(np.floor(allp[keep] * inv).astype(np.int64), axis=0)
+    vox_out = np.floor(out[:, :3] * inv).astype(np.int64)
+    assert abs(len(out) - len(vox_in)) <= 2                       # numpy's transform differs from the se3 form in the last bit
+    assert len(np.unique(vox_out, axis=0)) >= len(out) - 2        # one centroid per voxel, each inside its own voxel
+    again = oracle.merge_nearest_keyframes([out], np.eye(4, dtype=np.float32)[None], lim, leaf)
+    assert len(again) == len(out) and np.abs(again - out).max() < 1e-6
+    # intensity is averaged like the coordinates
+    assert 0.0 <= out[:, 3].min() and out[:, 3].max() <= 1.0
+    # leaf too small for int indices -> PCL returns the (cropped) input unchanged
+    tiny = oracle.merge_nearest_keyframes(kfs[:1], Ts[:1], lim, 1e-4)
+    assert len(tiny) == int(((np.abs((kfs[0][:, :3] @ Ts[0][:3, :3].T + Ts[0][:3, 3])[:, :2]) <= lim).all(axis=1)).sum())
+    assert len(oracle.merge_nearest_keyframes([np.zeros((0, 4), np.float32)], np.eye(4, dtype=np.float32)[None], lim, leaf)) == 0
+
