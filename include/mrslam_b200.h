@@ -77,6 +77,12 @@ int mrslam_cloud_size(const mrslam_cloud_t*);
 int mrslam_keyframe_merge(const float* const* clouds, const int* n, int stride_floats, int count, const float* T16, float xy_limit,
                           float leaf, int on_device, float* d_out_xyzi, int capacity, int* n_out);
 
+/* build_neighbors_NN(pointcloud, k) of the RING++ generator (LoopDetection/src/RING_ros/util.py:163-170, k = 30): exact kNN lists
+ * (self first, (distance, index) order), sample covariances (row-major 3x3, divisor k-1), eigen-entropy and [e0 e1 e2 | f0 f1]
+ * (3-D and x-y eigenvalues, descending) -- the inputs of voxelfeat.GPUFeatureExtractor.  HOST arrays; covs / entropy may be NULL. */
+int mrslam_ringpp_build_neighbors(const float* xyz, int n, int stride_floats, int k, int* indices_out, float* covs_out9,
+                                  float* entropy_out, float* eigens_out5);
+
 mrslam_gicp_t* mrslam_gicp_create(void);                              /* FastGICP() ctor: fast_gicp_impl.hpp:9-24 defaults */
 void mrslam_gicp_destroy(mrslam_gicp_t*);
 int mrslam_gicp_set_num_threads(mrslam_gicp_t*, int n);               /* setNumThreads: accepted, no effect on the GPU */

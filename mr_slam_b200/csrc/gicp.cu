@@ -907,6 +907,7 @@ int mrslam_cloud_knn(mrslam_cloud_t* h, int k, int* idx_out, float* sqd_out) {
   Cloud* c = reinterpret_cast<Cloud*>(h);
   BatchScratch& S = scratch();
   MR_CHECK(build_clouds(std::vector<Cloud*>(1, c)));
+  MR_CHECK(S.knn_fence.wait());
   MR_CHECK(S.h_knn.reserve(1));
   MR_CHECK(S.d_knn.reserve(1));
   DevBuf<int> di;
@@ -935,6 +936,64 @@ int mrslam_cloud_knn(mrslam_cloud_t* h, int k, int* idx_out, float* sqd_out) {
   di.release();
   dd.release();
   return MRSLAM_OK;
+}
+
+// build_neighbors_NN(pointcloud, k) of the RING++ generator (LoopDetection/src/RING_ros/util.py:163-170): kNN lists (self first),
+// sample covariances, eigen-entropy and the 3-D / 2-D eigenvalues that voxelfeat.GPUFeatureExtractor consumes.  Host arrays.
+int mrslam_ringpp_build_neighbors(const float* xyz, int n, int stride_floats, int k, int* indices_out, float* covs_out9, float* entropy_out,
+                                  float* eigens_out5) {
+  MR_CHECK(ensure_init());
+  if (n < 0 || stride_floats < 3 || (n > 0 && (!xyz || !indices_out || !eigens_out5))) {
+    set_error("ringpp_build_neighbors: bad arguments");
+    return MRSLAM_ERR_ARG;
+  }
+  if (k < 2 || k > 32) {
+    set_error("ringpp_build_neighbors: k must be in 2..32 (got %d)", k);
+    return MRSLAM_ERR_ARG;
+  }
+  if (n == 0) return MRSLAM_OK;
+  LOCK();
+  Cloud* c = acquire_cloud();
+  int st = c->set_from_host(xyz, n, stride_floats);
+  if (st == MRSLAM_OK) st = build_clouds(std::vector<Cloud*>(1, c));
+  BatchScratch& S = scratch();
+  DevBuf<int> di;
+  DevBuf<float> dout;
+  auto body = [&]() -> int {
+    MR_CHECK(st);
+    MR_CHECK(S.knn_fence.wait());
+    MR_CHECK(S.h_knn.reserve(1));
+    MR_CHECK(S.d_knn.reserve(1));
+    MR_CHECK(di.reserve((size_t)n * k));
+    MR_CHECK(dout.reserve((size_t)n * 15));
+    MR_CHECK(c->knn_ids.reserve((size_t)std::max(c->npad, 1) * k));
+    KnnParams p;
+    p.n = c->n; p.ids = c->knn_ids.p;
+    p.psort = c->psort.p; p.porig = c->porig.p; p.tb = c->tb.p; p.sb = c->sb.p;
+    p.ntiles = c->ntiles; p.ntiles_pad = c->ntiles_pad; p.nsuper = c->nsuper; p.nsuper_pad = c->nsuper_pad; p.k = k; p.reg = 0;
+    p.cov = nullptr; p.knn_idx = di.p; p.knn_sqd = nullptr; p.stat_pairs = nullptr;
+    S.h_knn.p[0] = p;
+    MR_CUDA(cudaMemcpyAsync(S.d_knn.p, S.h_knn.p, sizeof(KnnParams), cudaMemcpyHostToDevice, rt().stream));
+    MR_CHECK(S.knn_fence.mark(rt().stream));
+    MR_CHECK(dispatch_knn(k, S.d_knn.p, 1, c->ntiles, false));
+    float* cov = dout.p;
+    float* ent = dout.p + (size_t)n * 9;
+    float* eig = dout.p + (size_t)n * 10;
+    k_ringpp_eigens<<<(n + 127) / 128, 128, 0, rt().stream>>>(c->porig.p, n, k, di.p, cov, ent, eig);
+    count_launch(1);
+    MR_CUDA(cudaGetLastError());
+    MR_CUDA(cudaMemcpyAsync(indices_out, di.p, sizeof(int) * (size_t)n * k, cudaMemcpyDeviceToHost, rt().stream));
+    if (covs_out9) MR_CUDA(cudaMemcpyAsync(covs_out9, cov, sizeof(float) * (size_t)n * 9, cudaMemcpyDeviceToHost, rt().stream));
+    if (entropy_out) MR_CUDA(cudaMemcpyAsync(entropy_out, ent, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, rt().stream));
+    MR_CUDA(cudaMemcpyAsync(eigens_out5, eig, sizeof(float) * (size_t)n * 5, cudaMemcpyDeviceToHost, rt().stream));
+    MR_CUDA(cudaStreamSynchronize(rt().stream));
+    return MRSLAM_OK;
+  };
+  st = body();
+  di.release();
+  dout.release();
+  cloud_unref(c);
+  return st;
 }
 
 mrslam_gicp_t* mrslam_gicp_create(void) {

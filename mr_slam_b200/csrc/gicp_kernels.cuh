@@ -388,6 +388,64 @@ __device__ __forceinline__ void inverse3(const double a[9], double r[9]) {
   r[8] = (a[0] * a[4] - a[1] * a[3]) * id;
 }
 
+// RING++ local-descriptor front end (LoopDetection/src/RING_ros/util.py:124-170, covariation_eigenvalue after
+// build_neighbors_NN): sample covariance (divisor k-1) of the k neighbours of every point, its three eigenvalues in descending
+// order, the two of the x-y block, and the eigen-entropy (util.py:114-121).  One thread per point (ORIGINAL order); double
+// arithmetic (the reference: float32 numpy + LAPACK ssyevd, so agreement is to float32 rounding of the reference itself).
+__global__ void __launch_bounds__(128) k_ringpp_eigens(const float4* __restrict__ porig, int n, int k, const int* __restrict__ knn_idx,
+                                                       float* __restrict__ cov_out, float* __restrict__ entropy_out,
+                                                       float* __restrict__ eigens_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int* nb = knn_idx + (size_t)i * k;
+  double m[3] = {0, 0, 0};
+  int cnt = 0;
+  for (int j = 0; j < k; j++) {
+    const int id = nb[j];
+    if (id < 0) continue;
+    const float4 p = porig[id];
+    m[0] += (double)p.x; m[1] += (double)p.y; m[2] += (double)p.z;
+    cnt++;
+  }
+  double C[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  if (cnt > 1) {
+    m[0] /= cnt; m[1] /= cnt; m[2] /= cnt;
+    for (int j = 0; j < k; j++) {
+      const int id = nb[j];
+      if (id < 0) continue;
+      const float4 p = porig[id];
+      const double d[3] = {(double)p.x - m[0], (double)p.y - m[1], (double)p.z - m[2]};
+#pragma unroll
+      for (int a = 0; a < 3; a++)
+#pragma unroll
+        for (int b = a; b < 3; b++) C[3 * a + b] = fma(d[a], d[b], C[3 * a + b]);
+    }
+    const double inv = 1.0 / (double)(cnt - 1);
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+#pragma unroll
+      for (int b = a; b < 3; b++) {
+        C[3 * a + b] *= inv;
+        C[3 * b + a] = C[3 * a + b];
+      }
+  }
+  if (cov_out)
+    for (int a = 0; a < 9; a++) cov_out[(size_t)i * 9 + a] = (float)C[a];
+  double w[3], V[9];
+  sym_eig3(C, w, V);  // descending
+  // 2x2 block [a b; b c]: closed form, descending
+  const double a = C[0], b = C[1], c = C[4];
+  const double tr = 0.5 * (a + c), df = 0.5 * (a - c);
+  const double rad = sqrt(fma(df, df, b * b));
+  const double e2a = tr + rad, e2b = tr - rad;
+  float* e = eigens_out + (size_t)i * 5;
+  e[0] = (float)w[0]; e[1] = (float)w[1]; e[2] = (float)w[2]; e[3] = (float)e2a; e[4] = (float)e2b;
+  if (entropy_out) {
+    const double L = (w[0] - w[1]) / w[0], P = (w[1] - w[2]) / w[0], S = w[2] / w[0];
+    entropy_out[i] = (float)(-L * log(L) - P * log(P) - S * log(S));
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // kNN search (k <= 32), then covariance + regularisation as a separate lane-per-point kernel.
 // fast_gicp_impl.hpp:241-298 (calculate_covariances); GPU precedent brute_force_knn.cu:16-60 +

@@ -102,3 +102,17 @@ def solve_translation(query, positive, rot_angle, device=None, row_shift=0, want
                                               out.ctypes.data))
     x, y, err = np.float32(out[0]), np.float32(out[1]), np.float32(out[2])
     return (x, y, err, b) if want_shifts else (x, y, err)
+
+
+def build_neighbors_NN(pointcloud, k):
+    """build_neighbors_NN(pointcloud, k) of util.py:163-170 on the GPU (exact tiled kNN + covariance / eigenvalue kernel).
+    Returns (indices [n,k] int32, covs [n,3,3], entropy [n], eigens_ [n,5], vectors_ = []) like the reference."""
+    pc = np.ascontiguousarray(np.asarray(pointcloud)[:, :3], np.float32)
+    n = pc.shape[0]
+    idx = np.zeros((n, k), np.int32)
+    cov = np.zeros((n, 3, 3), np.float32)
+    ent = np.zeros(n, np.float32)
+    eig = np.zeros((n, 5), np.float32)
+    check(lib().mrslam_ringpp_build_neighbors(ptr(pc), n, 3, int(k), ptr(idx), ptr(cov), ptr(ent), ptr(eig)))
+    return idx, cov, ent, eig, []
+

@@ -374,3 +374,20 @@ def merge_nearest_keyframes(keyframes, transforms, xy_limit=60.0, leaf=0.2):
     assert m >= 0
     return out[:m].copy()
 
+
+def ringpp_build_neighbors(pointcloud, k):
+    """build_neighbors_NN (RING/util.py:163-170): exact kNN (this oracle's kd-tree; sklearn's kd_tree in the reference) followed by
+    covariation_eigenvalue (util.py:124-160) restated with the same numpy float32 operations and LAPACK eigvalsh."""
+    pc = np.ascontiguousarray(np.asarray(pointcloud)[:, :3], np.float32)
+    idx, _ = knn(pc, pc, k)
+    nb = pc[idx]                                             # [n, k, 3]
+    ex = np.average(nb, axis=1)
+    P = nb - ex[:, None, :]
+    cov = np.matmul(P.transpose((0, 2, 1)), P) / (nb.shape[1] - 1)
+    e3 = np.sort(np.linalg.eigvalsh(cov), axis=1)[:, ::-1]
+    L_, P_, S_ = (e3[:, 0] - e3[:, 1]) / e3[:, 0], (e3[:, 1] - e3[:, 2]) / e3[:, 0], e3[:, 2] / e3[:, 0]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        entropy = -L_ * np.log(L_) - P_ * np.log(P_) - S_ * np.log(S_)
+    e2 = np.sort(np.linalg.eigvalsh(cov[:, :2, :2]), axis=1)[:, ::-1]
+    return idx, cov, entropy, np.append(e3, e2, axis=1)
+

@@ -114,6 +114,18 @@ def ring():
         cases.append((float(x), float(y), float(err)))
     util.solve_overdetermined_linear_system = orig_lsq
     print("solve_translation goldens (x, y, err):", cases)
+    # RING++ front end: the reference's build_neighbors_NN (sklearn kd_tree kNN + covariation_eigenvalue), util.py:124-170
+    from mr_slam_b200 import synth
+    scan = synth.make_scan(synth.pose_matrix(1.0, 2.0, 0.0, 0.3), "vlp16", scan_id=77).astype(np.float32)
+    pcn = util.load_pc_infer(np.hstack([scan, np.zeros((len(scan), 1), np.float32)]))[:, :3]
+    pcn = np.ascontiguousarray(pcn[:: max(1, len(pcn) // 2500)][:2500], np.float32)
+    idx, covs, entropy, eigens, _ = util.build_neighbors_NN(pcn, 30)
+    out["nn_pc"] = pcn
+    out["nn_idx"] = idx.astype(np.int32)
+    out["nn_cov"] = covs.astype(np.float32)
+    out["nn_entropy"] = entropy.astype(np.float32)
+    out["nn_eigens"] = eigens.astype(np.float32)
+    print("build_neighbors_NN golden:", pcn.shape, idx.shape, eigens.shape, covs.dtype, eigens.dtype)
     np.savez_compressed(os.path.join(HERE, "ring_fixture.npz"), **out)
     print("ring fixture: fast_corr dist", out["fast_corr_dist"].tolist(), "angle", out["fast_corr_angle"].tolist(), "rolled ->", int(angle))
 

@@ -144,3 +144,27 @@ def test_voxelfeat_bev(gpu):
         t2 = voxelfeat.GPUTransformer(soa2, m, 1, 1, 120, 120, 1, fs)
         t2.transform()
         assert np.array_equal(t2.retreive(), ref.voxelfeat_bev(soa2, m, 1, 1, 120, 120, 1, fs))
+
+
+def test_ringpp_build_neighbors_vs_reference_python(gpu):
+    """build_neighbors_NN (CPU sklearn kNN(30) + numpy/LAPACK eigenvalues in the reference) on the GPU: neighbour lists
+    identical to the reference's, eigenvalues / covariances / entropy to float32 rounding; its output drives GPUFeatureExtractor."""
+    import os
+    from conftest import GOLDEN
+    from test_oracle_golden import _nn_close
+    from mr_slam_b200 import ring
+    z = np.load(os.path.join(GOLDEN, "ring_fixture.npz"))
+    idx, cov, ent, eig, vec = ring.build_neighbors_NN(z["nn_pc"], 30)
+    assert vec == [] and idx.dtype == np.int32
+    assert np.array_equal(idx, z["nn_idx"])
+    _nn_close(eig, ent, cov, z)
+    # chained with the feature extractor exactly like generate_RINGplusplus (util.py:211-220)
+    from mr_slam_b200 import voxelfeat
+    pc = z["nn_pc"]
+    n = len(pc)
+    feat = voxelfeat.GPUFeatureExtractor(pc.flatten(), n, 13, 30, idx.flatten().astype(np.int32), eig.flatten()).get_features()
+    exp = oracle.voxelfeat_features(pc.reshape(-1), n, 13, 30, z["nn_idx"].reshape(-1), eig.reshape(-1))
+    assert np.array_equal(np.asarray(feat).reshape(n, 13), exp.reshape(n, 13))
+    with pytest.raises(Exception):
+        ring.build_neighbors_NN(pc, 40)          # k <= 32
+

@@ -266,3 +266,20 @@ def test_keyframe_merge_oracle_properties():
     assert len(tiny) == int(((np.abs((kfs[0][:, :3] @ Ts[0][:3, :3].T + Ts[0][:3, 3])[:, :2]) <= lim).all(axis=1)).sum())
     assert len(oracle.merge_nearest_keyframes([np.zeros((0, 4), np.float32)], np.eye(4, dtype=np.float32)[None], lim, leaf)) == 0
 
+
+def _nn_close(eig, ent, cov, z):
+    e0 = z["nn_eigens"][:, :1]
+    assert (np.abs(eig - z["nn_eigens"]) <= 2e-5 * e0 + 1e-4 * np.abs(z["nn_eigens"])).all()
+    assert np.abs(cov.reshape(-1, 9) - z["nn_cov"].reshape(-1, 9)).max() <= 2e-5 * e0.max()
+    ok = np.isfinite(z["nn_entropy"])
+    assert np.abs(ent[ok] - z["nn_entropy"][ok]).max() < 2e-3
+
+
+def test_ringpp_front_end_oracle_vs_reference_python():
+    """RING++ front end: golden vectors from the reference's own build_neighbors_NN (sklearn kd_tree kNN, k = 30, +
+    covariation_eigenvalue).  Neighbour lists are identical row for row (also pins this oracle's exact kNN against sklearn)."""
+    z = np.load(os.path.join(GOLDEN, "ring_fixture.npz"))
+    idx, cov, ent, eig = oracle.ringpp_build_neighbors(z["nn_pc"], 30)
+    assert np.array_equal(idx, z["nn_idx"])
+    _nn_close(eig, ent, cov, z)
+
