@@ -256,6 +256,11 @@ int mrslam_ring_fast_corr(const float* d_query, const float* d_db, int n_db, int
  * least-squares x, y and the residual norm -> xy_err3 (HOST, 3 floats).  d_query / d_positive: float [channels, n_angles, det]. */
 int mrslam_ring_solve_translation(const float* d_query, const float* d_positive, int channels, int n_angles, int det_count,
                                   float rot_angle, int row_shift, float* d_row_shift_opt, float* xy_err3);
+/* GlobalManager::calcRelOri(newDiSCO, oldDiSCO) (Mapping/src/global_manager/src/global_manager.cpp:2719-2762) for one new
+ * signature a against n_b old ones b: real/imag planes float [height, width] (a) and [n_b, height, width] (b), DEVICE pointers.
+ * d_rel_angle[n_b] = width offset of the arg-max of Re(IDFT2(cross spectrum)) * 3 degrees; d_max_loc_opt[n_b] = the flat arg-max. */
+int mrslam_disco_rel_ori(const float* d_real_a, const float* d_imag_a, const float* d_real_b, const float* d_imag_b, int n_b,
+                         int height, int width, float* d_rel_angle, int* d_max_loc_opt);
 /* fused generate_RING for a batch of BEV images: Radon -> normalise -> FFT (one kernel per image) */
 int mrslam_ring_generate(const float* d_bev, int batch, int size, const float* d_angles, int n_angles, int interp,
                          int fast_trig, float* d_sino_opt, float* d_tiring);

@@ -137,6 +137,7 @@ def _declare(L):
         L.mrslam_ring_fast_corr.argtypes = [fp, fp, i, i, i, i, fp, ip, fp]
         L.mrslam_ring_generate.argtypes = [fp, i, i, fp, i, i, i, fp, fp]
         L.mrslam_ring_solve_translation.argtypes = [fp, fp, i, i, i, f, i, fp, fp]
+        L.mrslam_disco_rel_ori.argtypes = [fp, fp, fp, fp, i, i, i, fp, ip]
 
 
 def ptr(a):

@@ -259,6 +259,7 @@ __global__ void __launch_bounds__(256) k_ring_fast_corr(const float* __restrict_
 
 struct RadonScratch {
   DevBuf<float> stats, sino, shifts;
+  DevBuf<double> disco;
 };
 static RadonScratch& rs() {
   static RadonScratch s;
@@ -377,6 +378,92 @@ __global__ void k_ring_translation_lsq(const float* __restrict__ b, int H, float
   out[2] = (float)sqrt(err);
 }
 
+// GlobalManager::calcRelOri (Mapping/src/global_manager/src/global_manager.cpp:2719-2762): yaw between two DiSCO signatures.
+// Cross spectrum with the reference's (non-conjugate) imaginary part, un-normalised inverse 2-D DFT (FFTW_BACKWARD, double),
+// first arg-max of the real part, column offset * 3 degrees.  (The reference's r0 normalisation lines :2737-2738 have no effect.)
+// The 40 x 120 transform is evaluated directly and separably in double: stage 1 one block per (pair, row) does the width
+// transform, stage 2 one block per pair does the height transform of the real part and the arg-max.
+__global__ void __launch_bounds__(128) k_disco_rows(const float* __restrict__ ra, const float* __restrict__ ia, const float* __restrict__ rb,
+                                                   const float* __restrict__ ib, int H, int W, double* __restrict__ row_re,
+                                                   double* __restrict__ row_im) {
+  extern __shared__ double smd[];
+  double* cr = smd;
+  double* ci = smd + W;
+  double* tc = smd + 2 * W;
+  double* ts = smd + 3 * W;
+  const int pair = blockIdx.y, h = blockIdx.x;
+  const float* rbp = rb + (size_t)pair * H * W;
+  const float* ibp = ib + (size_t)pair * H * W;
+  for (int w = threadIdx.x; w < W; w += blockDim.x) {
+    const float a_r = ra[h * W + w], a_i = ia[h * W + w], b_r = rbp[h * W + w], b_i = ibp[h * W + w];
+    cr[w] = (double)(a_r * b_r + a_i * b_i);  // float products and sums, then widened: real_a[i] * real_b[i] + ... is float math
+    ci[w] = (double)(a_r * b_i + b_r * a_i);
+    double sv, cv;
+    sincospi(2.0 * (double)w / (double)W, &sv, &cv);
+    tc[w] = cv;
+    ts[w] = sv;
+  }
+  __syncthreads();
+  for (int v = threadIdx.x; v < W; v += blockDim.x) {
+    double re = 0, im = 0;
+    int ph = 0;
+    for (int w = 0; w < W; w++) {
+      re += cr[w] * tc[ph] - ci[w] * ts[ph];
+      im += cr[w] * ts[ph] + ci[w] * tc[ph];
+      ph += v;
+      if (ph >= W) ph -= W;
+    }
+    row_re[((size_t)pair * H + h) * W + v] = re;
+    row_im[((size_t)pair * H + h) * W + v] = im;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_disco_cols_argmax(const double* __restrict__ row_re, const double* __restrict__ row_im, int H, int W,
+                                                          float* __restrict__ rel_angle, int* __restrict__ max_loc) {
+  __shared__ float s_best[256];
+  __shared__ int s_loc[256];
+  const int pair = blockIdx.x;
+  const double* rr = row_re + (size_t)pair * H * W;
+  const double* ri = row_im + (size_t)pair * H * W;
+  float best = -INFINITY;
+  int loc = 0x7fffffff;
+  for (int o = threadIdx.x; o < H * W; o += blockDim.x) {
+    const int u = o / W, v = o - u * W;
+    double re = 0;
+    for (int h = 0; h < H; h++) {
+      double sv, cv;
+      sincospi(2.0 * (double)((h * u) % H) / (double)H, &sv, &cv);
+      re += rr[h * W + v] * cv - ri[h * W + v] * sv;
+    }
+    const float val = (float)re;  // Eigen::VectorXf cross_real
+    if (val > best || (val == best && o < loc)) {
+      best = val;
+      loc = o;
+    }
+  }
+  s_best[threadIdx.x] = best;
+  s_loc[threadIdx.x] = loc;
+  __syncthreads();
+  for (int st = 128; st > 0; st >>= 1) {
+    if (threadIdx.x < st) {
+      const float ob = s_best[threadIdx.x + st];
+      const int ol = s_loc[threadIdx.x + st];
+      if (ob > s_best[threadIdx.x] || (ob == s_best[threadIdx.x] && ol < s_loc[threadIdx.x])) {
+        s_best[threadIdx.x] = ob;
+        s_loc[threadIdx.x] = ol;
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const int ml = s_loc[0];
+    const int hoff = ml / W;
+    const int woff = ml - W * hoff;
+    rel_angle[pair] = (float)woff * 3.0f;
+    if (max_loc) max_loc[pair] = ml;
+  }
+}
+
 extern "C" {
 
 int mrslam_radon_forward(const float* d_img, int batch, int height, int width, const float* d_angles, int n_angles, int det_count,
@@ -440,6 +527,26 @@ int mrslam_ring_solve_translation(const float* d_query, const float* d_positive,
   MR_CUDA(cudaGetLastError());
   MR_CUDA(cudaMemcpyAsync(xy_err3, out, 3 * sizeof(float), cudaMemcpyDeviceToHost, rt().stream));
   MR_CUDA(cudaStreamSynchronize(rt().stream));
+  return MRSLAM_OK;
+}
+int mrslam_disco_rel_ori(const float* d_real_a, const float* d_imag_a, const float* d_real_b, const float* d_imag_b, int n_b, int height,
+                         int width, float* d_rel_angle, int* d_max_loc_opt) {
+  MR_CHECK(ensure_init());
+  if (n_b < 0 || height <= 0 || width <= 0 || (n_b > 0 && (!d_real_a || !d_imag_a || !d_real_b || !d_imag_b || !d_rel_angle))) {
+    set_error("disco_rel_ori: bad arguments");
+    return MRSLAM_ERR_ARG;
+  }
+  if (n_b == 0) return MRSLAM_OK;
+  std::lock_guard<std::mutex> lk(rt().mu);
+  const size_t plane = (size_t)n_b * height * width;
+  MR_CHECK(rs().disco.reserve(2 * plane));
+  double* re = rs().disco.p;
+  double* im = rs().disco.p + plane;
+  k_disco_rows<<<dim3(height, n_b), 128, 4 * (size_t)width * sizeof(double), rt().stream>>>(d_real_a, d_imag_a, d_real_b, d_imag_b, height, width,
+                                                                                         re, im);
+  k_disco_cols_argmax<<<n_b, 256, 0, rt().stream>>>(re, im, height, width, d_rel_angle, d_max_loc_opt);
+  count_launch(2);
+  MR_CUDA(cudaGetLastError());
   return MRSLAM_OK;
 }
 }

@@ -116,3 +116,17 @@ def build_neighbors_NN(pointcloud, k):
     check(lib().mrslam_ringpp_build_neighbors(ptr(pc), n, 3, int(k), ptr(idx), ptr(cov), ptr(ent), ptr(eig)))
     return idx, cov, ent, eig, []
 
+
+def calc_rel_ori(new_disco, old_discos, want_loc=False):
+    """GlobalManager::calcRelOri (global_manager.cpp:2719-2762), batched over the old signatures: new_disco = (real, imag) CUDA float32
+    [H, W], old_discos = (real, imag) CUDA float32 [N, H, W].  Returns rel_angle [N] in degrees (and the flat arg-max)."""
+    ra, ia = (t.contiguous().float() for t in new_disco)
+    rb, ib = (t.contiguous().float() for t in old_discos)
+    N, H, W = rb.shape
+    ang = torch.empty(N, dtype=torch.float32, device=rb.device)
+    loc = torch.empty(N, dtype=torch.int32, device=rb.device) if want_loc else None
+    torch.cuda.current_stream(rb.device).synchronize()
+    check(lib().mrslam_disco_rel_ori(ptr(ra), ptr(ia), ptr(rb), ptr(ib), N, H, W, ptr(ang), ptr(loc) if want_loc else None))
+    _sync()
+    return (ang, loc) if want_loc else ang
+

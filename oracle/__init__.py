@@ -391,3 +391,15 @@ def ringpp_build_neighbors(pointcloud, k):
     e2 = np.sort(np.linalg.eigvalsh(cov[:, :2, :2]), axis=1)[:, ::-1]
     return idx, cov, entropy, np.append(e3, e2, axis=1)
 
+
+def disco_rel_ori(real_a, imag_a, real_b, imag_b):
+    """GlobalManager::calcRelOri (global_manager.cpp:2719-2762) for one pair of [H, W] float32 planes -> (angle_deg, flat arg-max)."""
+    ra, ia, rb, ib = (_f32(x) for x in (real_a, imag_a, real_b, imag_b))
+    H, W = ra.shape
+    fn = lib().orc_disco_rel_ori
+    fn.restype = C.c_float
+    fn.argtypes = [C.c_void_p] * 4 + [C.c_int, C.c_int, C.POINTER(C.c_int)]
+    loc = C.c_int()
+    ang = fn(ra.ctypes.data, ia.ctypes.data, rb.ctypes.data, ib.ctypes.data, H, W, C.byref(loc))
+    return float(ang), loc.value
+

@@ -227,4 +227,45 @@ void orc_ring_solve_translation(const float* q, const float* p, int C, int H, in
   }
   out3[0] = (float)x; out3[1] = (float)y; out3[2] = (float)std::sqrt(err);
 }
+
+// GlobalManager::calcRelOri (Mapping/src/global_manager/src/global_manager.cpp:2719-2762).  FFTW (absent third-party dependency;
+// FFTW_BACKWARD = un-normalised sum with exp(+2 pi i (hu/H + wv/W))) is restated as a direct double DFT.  Returns the relative angle
+// in degrees, *max_loc = flat arg-max of the real part after the cast to float (first maximum, Eigen maxCoeff).
+float orc_disco_rel_ori(const float* ra, const float* ia, const float* rb, const float* ib, int H, int W, int* max_loc) {
+  std::vector<double> cr((size_t)H * W), ci((size_t)H * W);
+  for (int i = 0; i < H * W; i++) {
+    cr[i] = (double)(ra[i] * rb[i] + ia[i] * ib[i]);
+    ci[i] = (double)(ra[i] * ib[i] + rb[i] * ia[i]);
+  }
+  // separable: width transform per row, then height transform of each column (real part only)
+  std::vector<double> rr((size_t)H * W), ri((size_t)H * W), tcw(W), tsw(W), tch(H), tsh(H);
+  for (int w = 0; w < W; w++) { tcw[w] = std::cos(2.0 * M_PI * w / W); tsw[w] = std::sin(2.0 * M_PI * w / W); }
+  for (int h = 0; h < H; h++) { tch[h] = std::cos(2.0 * M_PI * h / H); tsh[h] = std::sin(2.0 * M_PI * h / H); }
+  for (int h = 0; h < H; h++)
+    for (int v = 0; v < W; v++) {
+      double re = 0, im = 0;
+      for (int w = 0; w < W; w++) {
+        int ph = (int)(((long)w * v) % W);
+        re += cr[h * W + w] * tcw[ph] - ci[h * W + w] * tsw[ph];
+        im += cr[h * W + w] * tsw[ph] + ci[h * W + w] * tcw[ph];
+      }
+      rr[h * W + v] = re;
+      ri[h * W + v] = im;
+    }
+  float best = -INFINITY;
+  int loc = 0;
+  for (int u = 0; u < H; u++)
+    for (int v = 0; v < W; v++) {
+      double re = 0;
+      for (int h = 0; h < H; h++) {
+        int ph = (h * u) % H;
+        re += rr[h * W + v] * tch[ph] - ri[h * W + v] * tsh[ph];
+      }
+      float val = (float)re;
+      if (val > best) { best = val; loc = u * W + v; }
+    }
+  if (max_loc) *max_loc = loc;
+  int hoff = loc / W;
+  return (float)(loc - W * hoff) * 3.0f;
+}
 }

@@ -283,3 +283,35 @@ def test_ringpp_front_end_oracle_vs_reference_python():
     assert np.array_equal(idx, z["nn_idx"])
     _nn_close(eig, ent, cov, z)
 
+
+def _disco_cases(n=6, H=40, W=120, seed=3):
+    rng = np.random.default_rng(seed)
+    img = (rng.random((H, W)) * (rng.random((H, W)) < 0.3)).astype(np.float32)
+    A = np.fft.fft2(img)
+    a = (A.real.astype(np.float32), A.imag.astype(np.float32))
+    rb, ib, shifts = [], [], []
+    for i in range(n):
+        sh = int(rng.integers(0, W))
+        other = np.roll(img, sh, axis=1) + 0.02 * rng.random((H, W)).astype(np.float32)
+        if i == n - 1:
+            other = (rng.random((H, W)) * (rng.random((H, W)) < 0.3)).astype(np.float32)     # unrelated scene
+        B = np.fft.fft2(other)
+        rb.append(B.real.astype(np.float32))
+        ib.append(B.imag.astype(np.float32))
+        shifts.append(sh)
+    return a, (np.stack(rb), np.stack(ib)), shifts
+
+
+def test_disco_rel_ori_oracle_vs_numpy_fft():
+    """calcRelOri (global_manager.cpp:2719-2762): FFTW is an absent third-party dependency; its un-normalised backward 2-D DFT is
+    restated directly and checked against numpy's FFT of the same definition; a column roll of the polar BEV comes back as 3 deg/bin."""
+    (ra, ia), (rb, ib), shifts = _disco_cases()
+    H, W = ra.shape
+    for i in range(len(shifts)):
+        ang, loc = oracle.disco_rel_ori(ra, ia, rb[i], ib[i])
+        cross = (ra * rb[i] + ia * ib[i]).astype(np.float64) + 1j * (ra * ib[i] + rb[i] * ia).astype(np.float64)
+        back = (np.fft.ifft2(cross) * H * W).real.astype(np.float32)
+        assert loc == int(np.argmax(back)) and ang == (loc % W) * 3.0
+        if i < len(shifts) - 1:
+            assert ang == shifts[i] * 3.0
+

@@ -147,3 +147,16 @@ def test_solve_translation_vs_reference_python_and_oracle(gpu):
             assert abs(x - gx) < 1e-4 and abs(y - gy) < 1e-4 and abs(e - ge) < 1e-3
     assert ring.calculate_row_shift(17) == -17 and ring.calculate_row_shift(100) == -20
 
+
+def test_disco_rel_ori_vs_oracle(gpu):
+    """calcRelOri batched over the database signatures: flat arg-max and angle identical to the oracle's double DFT"""
+    from test_oracle_golden import _disco_cases
+    (ra, ia), (rb, ib), shifts = _disco_cases(n=9, seed=8)
+    ang, loc = ring.calc_rel_ori((torch.from_numpy(ra).cuda(), torch.from_numpy(ia).cuda()),
+                                 (torch.from_numpy(rb).cuda(), torch.from_numpy(ib).cuda()), want_loc=True)
+    ang, loc = ang.cpu().numpy(), loc.cpu().numpy()
+    for i in range(len(shifts)):
+        oa, ol = oracle.disco_rel_ori(ra, ia, rb[i], ib[i])
+        assert int(loc[i]) == ol and float(ang[i]) == oa
+    assert (ang[:-1] == np.array(shifts[:-1], np.float32) * 3.0).all()
+
