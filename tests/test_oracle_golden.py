@@ -304,7 +304,7 @@ def _disco_cases(n=6, H=40, W=120, seed=3):
 
 def test_disco_rel_ori_oracle_vs_numpy_fft():
     """calcRelOri (global_manager.cpp:2719-2762): FFTW is an absent third-party dependency; its un-normalised backward 2-D DFT is
-    restated directly and checked against numpy's FFT of the same definition; a column roll of the polar BEV comes back as 3 deg/bin."""
+    restated directly and checked against numpy's FFT of the same definition."""
     (ra, ia), (rb, ib), shifts = _disco_cases()
     H, W = ra.shape
     for i in range(len(shifts)):
@@ -313,5 +313,7 @@ def test_disco_rel_ori_oracle_vs_numpy_fft():
         back = (np.fft.ifft2(cross) * H * W).real.astype(np.float32)
         assert loc == int(np.argmax(back)) and ang == (loc % W) * 3.0
         if i < len(shifts) - 1:
-            assert ang == shifts[i] * 3.0
+            # the reference's imaginary part is Im(a b), not Im(a conj(b)): the real part of the transform is then symmetric up to the
+            # noise, so the peak sits at the shift or at its mirror image
+            assert ang in (shifts[i] * 3.0, ((W - shifts[i]) % W) * 3.0)
 
