@@ -164,7 +164,7 @@ def test_ringpp_build_neighbors_vs_reference_python(gpu):
     n = len(pc)
     feat = voxelfeat.GPUFeatureExtractor(pc.flatten(), n, 13, 30, idx.flatten().astype(np.int32), eig.flatten()).get_features()
     exp = oracle.voxelfeat_features(pc.reshape(-1), n, 13, 30, z["nn_idx"].reshape(-1), eig.reshape(-1))
-    assert np.array_equal(np.asarray(feat).reshape(n, 13), exp.reshape(n, 13))
+    assert np.allclose(np.asarray(feat).reshape(n, 13), exp.reshape(n, 13), rtol=2e-5, atol=1e-6, equal_nan=True)   # logf/pow: glibc vs CUDA
     with pytest.raises(Exception):
         ring.build_neighbors_NN(pc, 40)          # k <= 32
 
