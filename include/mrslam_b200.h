@@ -83,6 +83,18 @@ int mrslam_keyframe_merge(const float* const* clouds, const int* n, int stride_f
 int mrslam_ringpp_build_neighbors(const float* xyz, int n, int stride_floats, int k, int* indices_out, float* covs_out9,
                                   float* entropy_out, float* eigens_out5);
 
+/* Wire formats at the seams.  Keys of dislam_msgs/Loop {int64 id0, id1}: ((97 + robot) << 56) + keyframe index + 1
+ * (global_manager.cpp:2587-2609 robotID2Key / Key2robotID, :1949-1951; RING/util.py:253-260). */
+unsigned long long mrslam_key_pack(int robot, long long keyframe_index);
+int mrslam_key_robot(unsigned long long key);
+long long mrslam_key_index(unsigned long long key);
+/* sensor_msgs/PointCloud2 data blob (dislam_msgs/SubMap.submap / .keyframePC; n_points = width*height records of point_step bytes,
+ * float32 fields at byte offsets off_*; off_intensity < 0 = none) -> packed x,y,z,intensity in DEVICE memory (capacity n_points),
+ * in record order, NaN records dropped when skip_nans (pc2.read_points(skip_nans=True), main_RING.py:251-254).  `data` is a host
+ * pointer (on_device = 0) or a device pointer.  The result can go to mrslam_cloud_create_device(d_out_xyzi, *n_out, 4). */
+int mrslam_pointcloud2_unpack(const unsigned char* data, int on_device, int n_points, int point_step, int off_x, int off_y, int off_z,
+                              int off_intensity, int skip_nans, float* d_out_xyzi, int* n_out);
+
 mrslam_gicp_t* mrslam_gicp_create(void);                              /* FastGICP() ctor: fast_gicp_impl.hpp:9-24 defaults */
 void mrslam_gicp_destroy(mrslam_gicp_t*);
 int mrslam_gicp_set_num_threads(mrslam_gicp_t*, int n);               /* setNumThreads: accepted, no effect on the GPU */

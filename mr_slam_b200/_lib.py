@@ -64,6 +64,12 @@ def _declare(L):
     L.mrslam_cloud_create_device.argtypes = [fp, i, i]
     L.mrslam_cloud_create_device.restype = vp
     L.mrslam_cloud_create_device_batch.argtypes = [C.POINTER(vp), C.POINTER(C.c_int), i, i, C.POINTER(vp)]
+    L.mrslam_key_pack.argtypes = [i, ll]
+    L.mrslam_key_pack.restype = C.c_ulonglong
+    L.mrslam_key_robot.argtypes = [C.c_ulonglong]
+    L.mrslam_key_index.argtypes = [C.c_ulonglong]
+    L.mrslam_key_index.restype = ll
+    L.mrslam_pointcloud2_unpack.argtypes = [fp, i, i, i, i, i, i, i, i, fp, C.POINTER(C.c_int)]
     L.mrslam_ringpp_build_neighbors.argtypes = [fp, i, i, i, ip, fp, fp, fp]
     L.mrslam_keyframe_merge.argtypes = [C.POINTER(vp), C.POINTER(C.c_int), i, i, fp, f, f, i, fp, i, C.POINTER(C.c_int)]
     L.mrslam_cloud_destroy.argtypes = [vp]

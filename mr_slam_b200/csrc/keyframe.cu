@@ -161,6 +161,26 @@ __global__ void k_kf_compact(const float4* __restrict__ cat, const int* __restri
   if (i < n && valid[i]) out[pos[i]] = cat[i];
 }
 
+// ---- wire formats at the seams ---------------------------------------------------------------------
+// sensor_msgs/PointCloud2 blob (dislam_msgs/SubMap.submap / .keyframePC) -> packed x,y,z,intensity on the device; replaces the
+// per-point python loop over pc2.read_points(..., skip_nans=True) of LoopDetection/src/RING_ros/main_RING.py:251-254.
+// Fields are little-endian float32 at arbitrary byte offsets inside a point_step-byte record (read bytewise: no alignment).
+__device__ __forceinline__ float load_f32_unaligned(const unsigned char* p) {
+  const unsigned u = (unsigned)p[0] | ((unsigned)p[1] << 8) | ((unsigned)p[2] << 16) | ((unsigned)p[3] << 24);
+  return __uint_as_float(u);
+}
+__global__ void k_pc2_decode(const unsigned char* __restrict__ data, int n, int point_step, int ox, int oy, int oz, int oi, int skip_nans,
+                             float4* __restrict__ pts, int* __restrict__ keep) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned char* r = data + (size_t)i * point_step;
+  const float x = load_f32_unaligned(r + ox), y = load_f32_unaligned(r + oy), z = load_f32_unaligned(r + oz);
+  const float w = oi >= 0 ? load_f32_unaligned(r + oi) : 0.0f;
+  pts[i] = make_float4(x, y, z, w);
+  // read_points(skip_nans=True) drops a point when ANY requested field is NaN (sensor_msgs/point_cloud2.py:82-88)
+  keep[i] = (skip_nans && (isnan(x) || isnan(y) || isnan(z) || (oi >= 0 && isnan(w)))) ? 0 : 1;
+}
+
 struct KfScratch {
   DevBuf<KfDesc> d_desc;
   PinBuf<KfDesc> h_desc;
@@ -170,6 +190,7 @@ struct KfScratch {
   DevBuf<unsigned> mm;
   DevBuf<unsigned char> tmp;
   DevBuf<float> staging;  // host inputs
+  DevBuf<unsigned char> bytes;
 };
 static KfScratch& ks() {
   static KfScratch s;
@@ -315,6 +336,50 @@ int mrslam_keyframe_merge(const float* const* clouds, const int* n, int stride_f
   count_launch(1);
   MR_CUDA(cudaGetLastError());
   *n_out = result;
+  return MRSLAM_OK;
+}
+/* gtsam-style symbol keys of the Loop / SubMap messages: ((97 + robot) << 56) + keyframe index + 1
+ * (global_manager.cpp:2587-2609 robotID2Key / Key2robotID, call sites :1949-1951; RING/util.py:253-260 robotid_to_key) */
+unsigned long long mrslam_key_pack(int robot, long long keyframe_index) {
+  return ((unsigned long long)(unsigned char)(97 + robot) << 56) + (unsigned long long)(keyframe_index + 1);
+}
+int mrslam_key_robot(unsigned long long key) { return (int)(char)(key >> 56) - 97; }
+long long mrslam_key_index(unsigned long long key) { return (long long)(key - ((key >> 56) << 56)) - 1; }
+
+int mrslam_pointcloud2_unpack(const unsigned char* data, int on_device, int n_points, int point_step, int off_x, int off_y, int off_z,
+                              int off_intensity, int skip_nans, float* d_out_xyzi, int* n_out) {
+  MR_CHECK(ensure_init());
+  if (n_points < 0 || point_step < 12 || off_x < 0 || off_y < 0 || off_z < 0 || off_x + 4 > point_step || off_y + 4 > point_step ||
+      off_z + 4 > point_step || off_intensity + 4 > point_step || !n_out || (n_points > 0 && (!data || !d_out_xyzi))) {
+    set_error("pointcloud2_unpack: bad arguments");
+    return MRSLAM_ERR_ARG;
+  }
+  *n_out = 0;
+  if (n_points == 0) return MRSLAM_OK;
+  std::lock_guard<std::mutex> lk(rt().mu);
+  cudaStream_t st = rt().stream;
+  KfScratch& S = ks();
+  const unsigned char* src = data;
+  if (!on_device) {
+    MR_CHECK(S.bytes.reserve((size_t)n_points * point_step));
+    MR_CUDA(cudaMemcpyAsync(S.bytes.p, data, (size_t)n_points * point_step, cudaMemcpyHostToDevice, st));
+    src = S.bytes.p;
+  }
+  MR_CHECK(S.cat.reserve(n_points)); MR_CHECK(S.valid.reserve(n_points)); MR_CHECK(S.pos.reserve(n_points));
+  k_pc2_decode<<<(n_points + 255) / 256, 256, 0, st>>>(src, n_points, point_step, off_x, off_y, off_z, off_intensity, skip_nans, S.cat.p,
+                                                      S.valid.p);
+  size_t tmp_bytes = 0;
+  MR_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, S.valid.p, S.pos.p, n_points, st));
+  MR_CHECK(S.tmp.reserve(tmp_bytes));
+  MR_CUDA(cub::DeviceScan::ExclusiveSum(S.tmp.p, tmp_bytes, S.valid.p, S.pos.p, n_points, st));
+  k_kf_compact<<<(n_points + 255) / 256, 256, 0, st>>>(S.cat.p, S.valid.p, S.pos.p, n_points, reinterpret_cast<float4*>(d_out_xyzi));
+  count_launch(2);
+  MR_CUDA(cudaGetLastError());
+  int tail[2] = {0, 0};
+  MR_CUDA(cudaMemcpyAsync(&tail[0], S.pos.p + (n_points - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
+  MR_CUDA(cudaMemcpyAsync(&tail[1], S.valid.p + (n_points - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
+  MR_CUDA(cudaStreamSynchronize(st));
+  *n_out = tail[0] + tail[1];
   return MRSLAM_OK;
 }
 }

@@ -304,3 +304,35 @@ def test_keyframe_merge_matches_oracle(gpu):
     assert np.abs(T - To).max() < TOL_T
     assert synth.pose_error(T, T_true)[0] < 0.05
 
+
+def test_pointcloud2_unpack(gpu):
+    """sensor_msgs/PointCloud2 blob -> device x,y,z,intensity (main_RING.py:251-254 does this with a per-point python loop): records of
+    odd size with unaligned float fields, NaN records dropped in order; host and device blobs; result usable as a cloud"""
+    import torch
+    from mr_slam_b200 import msgs
+    rng = np.random.default_rng(5)
+    n, step = 5000, 22                                           # x@1 y@5 z@9 intensity@14 (unaligned on purpose), 4 bytes of padding
+    pts = rng.normal(0, 20, (n, 4)).astype(np.float32)
+    pts[rng.random(n) < 0.05, rng.integers(0, 3)] = np.nan
+    pts[7, 3] = np.nan
+    blob = np.zeros((n, step), np.uint8)
+    for j, off in enumerate((1, 5, 9, 14)):
+        blob[:, off:off + 4] = pts[:, j:j + 1].copy().view(np.uint8)
+    offs = dict(x=1, y=5, z=9, intensity=14)
+    exp = pts[~np.isnan(pts).any(axis=1)]
+    got = msgs.pointcloud2_unpack(blob.tobytes(), n, step, offs).cpu().numpy()
+    assert np.array_equal(got, exp)
+    got_d = msgs.pointcloud2_unpack(torch.from_numpy(blob).cuda(), n, step, offs).cpu().numpy()
+    assert np.array_equal(got_d, exp)
+    keep_all = msgs.pointcloud2_unpack(blob, n, step, offs, skip_nans=False).cpu().numpy()
+    assert keep_all.shape == (n, 4) and np.array_equal(np.isnan(keep_all), np.isnan(pts))
+    xyz = msgs.pointcloud2_unpack(blob, n, step, dict(x=1, y=5, z=9)).cpu().numpy()          # no intensity field: w = 0
+    e3 = pts[~np.isnan(pts[:, :3]).any(axis=1)]
+    assert np.array_equal(xyz[:, :3], e3[:, :3]) and (xyz[:, 3] == 0).all()
+    t, cloud = msgs.pointcloud2_unpack(blob, n, step, offs, as_cloud=True)
+    assert len(cloud) == len(exp)
+    idx, _ = cloud.knn(4)
+    oi, _ = oracle.knn(exp[:, :3], exp[:, :3], 4)
+    assert np.array_equal(idx, oi)
+    assert msgs.pointcloud2_unpack(b"", 0, step, offs).shape == (0, 4)
+

@@ -103,3 +103,20 @@ def test_bench_reference_arm_prints_contract_line():
     line = json.loads(r.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
     assert line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_message_key_packing_matches_reference_formulas():
+    """dislam_msgs/Loop ids: ((97 + robot) << 56) + keyframe index + 1 (global_manager.cpp:2587-2609 robotID2Key / Key2robotID and the
+    decode in ICPCheck :1948-1951; RING/util.py:253-260 robotid_to_key).  Host-only entry points of the C-ABI."""
+    from mr_slam_b200 import msgs
+    for robot in (0, 1, 2, 7):
+        ref_key = (97 + robot) << (64 - 8)                      # util.py:253-260, robotID2Key
+        assert msgs.robotid_to_key(robot) == ref_key
+        for idx in (0, 1, 41, 10**6):
+            k = msgs.key_pack(robot, idx)
+            assert k == ref_key + idx + 1                       # main_RING.py publishes robotid_to_key(r) + idx + 1
+            total = (k >> 56) & 0xff                             # Key2robotID
+            assert total - 97 == robot
+            assert k - ref_key - 1 == idx                        # ICPCheck: id - robotID2Key(robot) - 1
+            assert msgs.key_unpack(k) == (robot, idx)
+
