@@ -270,26 +270,17 @@ def main():
         mark = lambda: tm.append(time.perf_counter())
         regs = new_regs()
         mark()
-        flow = os.environ.get("BENCH_FLOW", "")
-        if "percloud" in flow:
-            src_clouds = [pygicp.Cloud(device_ptr=src_dev[i].data_ptr(), n=N_POINTS, stride=3) for i in range(n_pairs)]
-        else:
-            src_clouds = pygicp.Cloud.from_device_batch([src_dev[i].data_ptr() for i in range(n_pairs)], N_POINTS, 3)
+        src_clouds = pygicp.Cloud.from_device_batch([src_dev[i].data_ptr() for i in range(n_pairs)], N_POINTS, 3)
         mark()
         for g, cs in zip(regs, src_clouds):
             g.set_input_source(cs)
         mark()
-        if "noprepare" not in flow:
-            pygicp.prepare_batch(regs, pygicp.SOURCE)
+        pygicp.prepare_batch(regs, pygicp.SOURCE)
         mark()
         with torch.cuda.stream(lib_stream):
             e1.record()
-        if "perframe" in flow:
-            for i in range(n_pairs):
-                emap.Move(pairs[i]["pose"][:3, 3].astype(np.float32), ELEV_RES, ELEV_L)
-                emap.process_fuse_device(soa_dev[i][0], soa_dev[i][1], soa_dev[i][2], N_POINTS, *elev_args(i), near_filter=True, want_count=False)
-        else:  # the robot's 32 scans replayed into its map by one call (frames pipelined over two streams inside the library)
-            emap.process_fuse_device_batch(elev_frames, ELEV_RES, ELEV_L, asynchronous=overlap)
+        # the robot's 32 scans replayed into its map by one call (frames pipelined over two streams inside the library)
+        emap.process_fuse_device_batch(elev_frames, ELEV_RES, ELEV_L, asynchronous=overlap)
         with torch.cuda.stream(lib_stream):
             e2.record()
         mark()
@@ -301,10 +292,7 @@ def main():
             lib_stream.wait_event(done)       # ... and the library stream after that
         exch_ms[0] += 1e3 * (time.perf_counter() - tx0)
         mark()
-        if "percloud" in flow:
-            tgt_clouds = [pygicp.Cloud(device_ptr=tgt_dev[i].data_ptr(), n=N_POINTS, stride=3) for i in range(n_pairs)]
-        else:
-            tgt_clouds = pygicp.Cloud.from_device_batch([tgt_dev[i].data_ptr() for i in range(n_pairs)], N_POINTS, 3)
+        tgt_clouds = pygicp.Cloud.from_device_batch([tgt_dev[i].data_ptr() for i in range(n_pairs)], N_POINTS, 3)
         for g, ct in zip(regs, tgt_clouds):
             g.set_input_target(ct)
         mark()

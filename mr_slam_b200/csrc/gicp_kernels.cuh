@@ -249,35 +249,6 @@ __global__ void k_super_boxes(const BuildDesc* __restrict__ descs) {
 // ---------------------------------------------------------------------------------------------
 // shared search pieces
 // ---------------------------------------------------------------------------------------------
-// ---------------------------------------------------------------------------------------------
-// shared search pieces
-// ---------------------------------------------------------------------------------------------
-// one warp per super tile: box of its (real) tiles
-__global__ void k_super_boxes(const float* __restrict__ tb, int ntiles, int ntiles_pad, int nsuper_pad, float* __restrict__ sb) {
-  int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  int lane = threadIdx.x & 31;
-  if (s >= nsuper_pad) return;
-  int t = s * 32 + lane;
-  bool real = t < ntiles;
-  float mn[3], mx[3];
-#pragma unroll
-  for (int a = 0; a < 3; a++) {
-    mn[a] = warp_min(real ? tb[(size_t)a * ntiles_pad + t] : FLT_MAX);
-    mx[a] = warp_max(real ? tb[(size_t)(3 + a) * ntiles_pad + t] : -FLT_MAX);
-  }
-  bool any = __any_sync(FULL, real);
-  if (lane == 0) {
-#pragma unroll
-    for (int a = 0; a < 3; a++) {
-      sb[(size_t)a * nsuper_pad + s] = any ? mn[a] : PAD_COORD;
-      sb[(size_t)(3 + a) * nsuper_pad + s] = any ? mx[a] : PAD_COORD;
-    }
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// shared search pieces
-// ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ bool lex_lt(float ad, int ai, float bd, int bi) { return ad < bd || (ad == bd && ai < bi); }
 
 // squared distance from a point to box t of an SoA box table (stride = padded count)
