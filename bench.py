@@ -192,6 +192,7 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a GPU: the hot path has no CPU fallback")
+    cores = mdist.bind_to_gpu_numa(local_rank) if world > 1 and not os.environ.get("BENCH_NO_BIND") else None
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -365,12 +366,10 @@ def main():
     # The clock sampler is started and exercised here too, so that NVML's lazy initialisation happens outside the timed
     # region; the samples taken during the warm-up are discarded, the ones reported are taken between the timed steps.
     sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    sampler.start()   # every rank samples its own GPU: the slowest GPU sets the pace of the lock-step exchange
     for _ in range(args.warmup):
         step_device()
-        if rank == 0:
-            sampler.sample()
+        sampler.sample()
     sampler.samples, sampler.reasons = [], set()
     barrier()
 
@@ -387,15 +386,14 @@ def main():
         fused_tot += fused
         n_lin += a
         n_err += b
-        if rank == 0:
-            sampler.sample()  # the GPU has been busy for the whole step that just ended
+        sampler.sample()  # the GPU has been busy for the whole step that just ended
     barrier()
     if os.environ.get("BENCH_TRACE") and rank == 0:
         print("[trace] per step (src prepare, elev, targets+LM events ms; align_batch host ms): %s" % step_trace, file=sys.stderr)
     wall = time.perf_counter() - wall0
     launches = _lib.kernel_launch_count() - launches0
     exchange_ms_per_step = exch_ms[0] / args.steps
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop()
     # per-kernel device times for the roofline block: the same steps again with CUDA events around every launch group on
     # the library stream (kept out of the region above: ~300 extra event records per step would be timed with it)
     SEQ_STEPS = 3
@@ -418,6 +416,19 @@ def main():
     prof = _lib.prof_get()
     _lib.prof_enable(False)
     barrier()
+    per_rank_ms = [(t_g + t_e) / args.steps]
+    if world > 1:
+        tt = torch.tensor([(t_g + t_e) / args.steps], dtype=torch.float64, device=dev)
+        allt = [torch.zeros_like(tt) for _ in range(world)]
+        dist.all_gather(allt, tt)
+        per_rank_ms = [float(x.item()) for x in allt]
+    per_rank_mhz, per_rank_knn = [clocks.get("sm_mhz")], [prof["knn_search"][0] / PROF_STEPS]
+    if world > 1:
+        tt = torch.tensor([float(clocks.get("sm_mhz") or 0.0), prof["knn_search"][0] / PROF_STEPS], dtype=torch.float64, device=dev)
+        allt = [torch.zeros_like(tt) for _ in range(world)]
+        dist.all_gather(allt, tt)
+        per_rank_mhz = [float(x[0].item()) for x in allt]
+        per_rank_knn = [float(x[1].item()) for x in allt]
     t_total_ms = reduce_max(t_g + t_e)
     seq_g_ms, seq_e_ms = reduce_max(seq_g), reduce_max(seq_e)     # per-part times of the SEQ_STEPS in-line steps
     aligns_total = n_pairs * args.steps * world
@@ -506,6 +517,10 @@ def main():
                           "grid": "%dx%d @ %.2f m" % (ELEV_L, ELEV_L, ELEV_RES), "near_filter": True},
             "e2e": {"value": e2e_value, "unit": "aligns/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": te2e_ms / args.steps},
+            "per_rank_ms_per_step": [round(x, 3) for x in per_rank_ms],
+            "per_rank_sm_mhz": per_rank_mhz,
+            "per_rank_knn_ms_per_step": [round(x, 3) for x in per_rank_knn],
+            "cpu_affinity": ("rank 0 bound to the %d cores NVML lists for its GPU" % len(cores)) if cores else "unbound",
             "gpu_launches": int(launches),
             "roofline": roofline,
             "cpu_baseline": cpu,

@@ -61,3 +61,20 @@ def ring_candidate_pairs(world_size, per_rank):
     """The benchmark's loop-closure storm (BASELINE config 4): robot r's keyframe i is matched against keyframe i of
     robot (r+1) % world.  Returns the global pair list."""
     return [(r, i, (r + 1) % world_size, i) for r in range(world_size) for i in range(per_rank)]
+
+
+def bind_to_gpu_numa(local_rank):
+    """Pin the calling process to the CPU cores NVML reports as local to GPU `local_rank` (nvmlDeviceSetCpuAffinity).  One process
+    per GPU on a two-socket box otherwise lands on either socket; the LM driver synchronises with the device a few dozen times per
+    batch and reads 28 doubles per problem out of pinned memory each time, so a remote socket costs latency on every one of them.
+    Returns the core list, or None when NVML is not available (nothing is changed then)."""
+    try:
+        import os
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(local_rank))
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return sorted(os.sched_getaffinity(0))
+    except Exception:  # noqa: BLE001
+        return None
+
