@@ -66,6 +66,13 @@ def _worker(rank, world, port, q):
         assert allc.shape == (world, S, N, 3)
         for r in range(world):
             assert torch.equal(allc[r], torch.full((S, N, 3), float(r)) + torch.arange(S).view(S, 1, 1))
+        # the overlapped form used by bench.py: start the collective, do local work, then wait
+        allc2, work = mdist.allgather_slots(local, async_op=True)
+        local_work = (local * 2).sum()
+        work.wait()
+        assert torch.equal(allc2, allc) and float(local_work) == float((local * 2).sum())
+        cores = mdist.bind_to_gpu_numa(rank)          # no NVML device here: must be a no-op that reports None
+        assert cores is None or len(cores) > 0
         pairs = mdist.ring_candidate_pairs(world, S)
         mine = mdist.shard_pairs(pairs, rank, world)
         T_local = torch.stack([torch.eye(4) * (i + 1) for i in mine])
