@@ -220,6 +220,14 @@ int mrslam_elev_map_closeloop(mrslam_elev_t*, const float* update_position, floa
  * 5x5 plane-fit traversability (G_Mapfeature :547-668) + read-out of the map; cells without elevation get 0 / 0 / -10. */
 int mrslam_elev_map_feature(mrslam_elev_t*, int length, float* elevation, float* var, int* colorR, int* colorG, int* colorB,
                             float* rough, float* slope, float* traver, float* intensity);
+/* Tile-sharded global grid (BASELINE config 5): restrict this instance to the STORAGE rows [row_lo, row_hi): points
+ * falling into other rows are treated as outside the map by Process_points / process_fuse_device (index -1).  Cells are disjoint
+ * across tiles, so the union of the tiles equals the single-GPU map bit for bit; no reduction is needed for the fuse. */
+int mrslam_elev_set_owned_rows(mrslam_elev_t*, int row_lo, int row_hi);
+/* n_rows consecutive storage rows of one plane <-> DEVICE buffer (n_rows*length 4-byte elements): halo rows of the neighbouring
+ * tiles for Map_feature's 5x5 window, or whole tile blocks when the full map is assembled.  plane: 0 elevation, 1 variance,
+ * 2 intensity, 3 lowest, 4 traversability, 5/6/7 R/G/B.  to_map != 0: buffer -> map.  Ordered on mrslam_stream(). */
+int mrslam_elev_rows_copy(mrslam_elev_t*, int plane, int storage_row, int n_rows, void* d_buf, int to_map);
 /* Raytracing(length)   :1301   obstacle clean-up along the sensor rays (G_Raytracing :706-889) + reset of map_lowest */
 int mrslam_elev_raytracing(mrslam_elev_t*, int length);
 /* read back the hidden map (any pointer may be NULL); length*length entries each, storage (ring-buffer) order */

@@ -129,6 +129,8 @@ def _declare(L):
         L.mrslam_elev_map_closeloop.argtypes = [vp, fp, f, i, f]
         L.mrslam_elev_map_feature.argtypes = [vp, i] + [fp] * 9
         L.mrslam_elev_raytracing.argtypes = [vp, i]
+        L.mrslam_elev_set_owned_rows.argtypes = [vp, i, i]
+        L.mrslam_elev_rows_copy.argtypes = [vp, i, i, i, fp, i]
         L.mrslam_elev_get_map.argtypes = [vp] + [C.c_void_p] * 7
         L.mrslam_elev_get_state.argtypes = [vp, fp, ip]
     if hasattr(L, "mrslam_voxelocc_transform"):

@@ -38,6 +38,7 @@ struct ElevGeom {
   float res;
   float cx, cy;    // central_coordinate
   int sx, sy;      // start_indice
+  int row_lo, row_hi;  // STORAGE rows this map instance owns (tile-sharded global grid); [0, L) for a whole map
 };
 
 struct ProcParams {
@@ -147,8 +148,10 @@ __global__ void k_elev_process(const float* __restrict__ px, const float* __rest
     for (int c = 0; c < 3; c++) b1[c] = P.sJ[c] * sv[c];
     hv += fmaf(b1[2], P.sJ[2], fmaf(b1[1], P.sJ[1], b1[0] * P.sJ[0]));
     int ix, iy;
-    if (cell_of(g, xt, yt, ix, iy)) {
-      mi = ((ix + g.sx) % g.L) * g.L + (iy + g.sy) % g.L;
+    const bool inside = cell_of(g, xt, yt, ix, iy);
+    const int srow = inside ? (ix + g.sx) % g.L : -1;
+    if (inside && srow >= g.row_lo && srow < g.row_hi) {  // cells of other tiles belong to another GPU's instance
+      mi = srow * g.L + (iy + g.sy) % g.L;
       const int gi = ix * g.L + iy;
       // racy in the reference as well (gpu_process.cu:434-438); map_lowest only feeds the ray-tracing clean-up
       atomic_min_float(&lowest[gi], height);
@@ -494,7 +497,7 @@ int mrslam_elev_init(mrslam_elev_t* h, int length, float resolution, float mahal
   std::lock_guard<std::mutex> lk2(m->mu);
   std::lock_guard<std::mutex> lk(rt().mu);
   MR_CHECK(m->join());
-  m->g = ElevGeom{length, resolution, 0.f, 0.f, 0, 0};
+  m->g = ElevGeom{length, resolution, 0.f, 0.f, 0, 0, 0, length};
   m->mahal_thr = mahal;
   m->obstacle_thr = obst;
   size_t n = (size_t)length * length;
@@ -925,6 +928,47 @@ int mrslam_elev_raytracing(mrslam_elev_t* h, int length) {
                     rt().stream);
   MR_CUDA(cudaGetLastError());
   MR_CUDA(cudaStreamSynchronize(rt().stream));  // the reference synchronises here as well
+  return MRSLAM_OK;
+}
+
+// Tile-sharded global grid (BASELINE config 5): this instance fuses only the points that fall into STORAGE rows
+// [row_lo, row_hi) -- cells are disjoint across tiles, so the union of the tiles equals the single-GPU map bit for bit.
+int mrslam_elev_set_owned_rows(mrslam_elev_t* h, int row_lo, int row_hi) {
+  REQ(h);
+  Elev* m = E(h);
+  REQ_INIT(m);
+  if (row_lo < 0 || row_hi > m->g.L || row_lo > row_hi) {
+    set_error("set_owned_rows: [%d, %d) outside [0, %d]", row_lo, row_hi, m->g.L);
+    return MRSLAM_ERR_ARG;
+  }
+  std::lock_guard<std::mutex> lk2(m->mu);
+  std::lock_guard<std::mutex> lk(rt().mu);
+  MR_CHECK(m->join());
+  m->g.row_lo = row_lo;
+  m->g.row_hi = row_hi;
+  return MRSLAM_OK;
+}
+
+// n_rows consecutive STORAGE rows of one plane <-> a DEVICE buffer of n_rows * length 4-byte elements (halo rows of a neighbouring
+// tile before Map_feature, tile blocks for assembling the whole map).  plane: 0 elevation, 1 variance, 2 intensity, 3 lowest,
+// 4 traversability, 5/6/7 colour R/G/B (int).  to_map != 0 writes the buffer into the map.  Stream-ordered on mrslam_stream().
+int mrslam_elev_rows_copy(mrslam_elev_t* h, int plane, int storage_row, int n_rows, void* d_buf, int to_map) {
+  REQ(h);
+  Elev* m = E(h);
+  REQ_INIT(m);
+  if (plane < 0 || plane > 7 || storage_row < 0 || n_rows < 0 || storage_row + n_rows > m->g.L || (n_rows > 0 && !d_buf)) {
+    set_error("rows_copy: bad arguments (plane %d rows %d+%d)", plane, storage_row, n_rows);
+    return MRSLAM_ERR_ARG;
+  }
+  std::lock_guard<std::mutex> lk2(m->mu);
+  std::lock_guard<std::mutex> lk(rt().mu);
+  MR_CHECK(m->join());
+  if (n_rows == 0) return MRSLAM_OK;
+  void* planes[8] = {m->elevation.p, m->variance.p, m->intensity.p, m->lowest.p, m->traver.p, m->R.p, m->G.p, m->B.p};
+  char* mp = (char*)planes[plane] + (size_t)storage_row * m->g.L * 4;
+  const size_t bytes = (size_t)n_rows * m->g.L * 4;
+  if (to_map) MR_CUDA(cudaMemcpyAsync(mp, d_buf, bytes, cudaMemcpyDeviceToDevice, rt().stream));
+  else MR_CUDA(cudaMemcpyAsync(d_buf, mp, bytes, cudaMemcpyDeviceToDevice, rt().stream));
   return MRSLAM_OK;
 }
 

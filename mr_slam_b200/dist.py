@@ -78,3 +78,79 @@ def bind_to_gpu_numa(local_rank):
     except Exception:  # noqa: BLE001
         return None
 
+
+class TiledElevationMap:
+    """Tile-sharded global elevation grid (BASELINE config 5): rank r owns a block of STORAGE rows of one L x L grid and
+    fuses only the points that fall into it (`set_owned_rows`); every rank scans all points, cells are disjoint across tiles, so the
+    union of the tiles equals the single-GPU map bit for bit and the fuse needs no reduction.  Only neighbourhood operations need
+    data of other tiles: before Map_feature the `halo` (= 2, the 5 x 5 window) storage rows on either side of the block are fetched
+    from the neighbouring ranks (one small all_gather of the border rows).  Raytracing walks rays across the whole grid and is not
+    tiled.
+
+    `emap` is an initialised map object with the product interface (mr_slam_b200.elevation.ElevationMap; the CPU oracle twin in the
+    gloo tests); `device` is where the exchange tensors live ("cuda" for NCCL, "cpu" for gloo); `sync` is called between library-
+    stream copies and collectives (the two use different streams)."""
+
+    def __init__(self, emap, length, rank=None, world=None, device="cuda", sync=None, halo=2):
+        self.m, self.L, self.halo, self.device = emap, int(length), int(halo), device
+        self.rank = dist.get_rank() if rank is None else rank
+        self.world = dist.get_world_size() if world is None else world
+        self.bounds = [(r * self.L) // self.world for r in range(self.world + 1)]
+        self.row_lo, self.row_hi = self.bounds[self.rank], self.bounds[self.rank + 1]
+        if self.world > 1 and min(b - a for a, b in zip(self.bounds[:-1], self.bounds[1:])) < self.halo:
+            raise ValueError("tiles must be at least `halo` rows high")
+        self.sync = sync if sync is not None else (lambda: None)
+        emap.set_owned_rows(self.row_lo, self.row_hi)
+
+    def _rows(self, plane, row, n, dtype):
+        t = torch.empty((n, self.L), dtype=dtype, device=self.device)
+        for j in range(n):                      # storage rows wrap around (ring buffer)
+            self.m.rows_to_device(plane, (row + j) % self.L, 1, t[j])
+        return t
+
+    def _put(self, plane, row, t):
+        for j in range(t.shape[0]):
+            self.m.rows_from_device(plane, (row + j) % self.L, 1, t[j].contiguous())
+
+    def exchange_halo(self, plane="elevation"):
+        """fetch the `halo` storage rows above and below the own block from the neighbouring tiles into this replica"""
+        if self.world == 1:
+            return
+        h = self.halo
+        dtype = torch.int32 if plane in ("R", "G", "B") else torch.float32
+        mine = torch.cat([self._rows(plane, self.row_lo, h, dtype), self._rows(plane, self.row_hi - h, h, dtype)])   # top, bottom
+        self.sync()
+        allb = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(allb, mine)
+        self.sync()
+        prev_r, next_r = (self.rank - 1) % self.world, (self.rank + 1) % self.world
+        self._put(plane, self.row_lo - h, allb[prev_r][h:])      # the rows just above my block are my predecessor's bottom rows
+        self._put(plane, self.row_hi, allb[next_r][:h])          # the rows just below are my successor's top rows
+        self.sync()
+
+    def map_feature_owned(self):
+        """Map_feature for the owned rows: dict of [rows, L] arrays (numpy) for elevation / var / rough / slope / traver / ..."""
+        self.exchange_halo("elevation")
+        out = self.m.Map_feature(self.L) if hasattr(self.m, "Map_feature") else self.m.map_feature()
+        return {k: np.asarray(v).reshape(self.L, self.L)[self.row_lo:self.row_hi] for k, v in out.items()}
+
+    def gather_full(self, planes=("elevation", "variance")):
+        """assemble whole planes on every rank from the owned blocks (all_gather of padded blocks); returns {plane: tensor [L*L]}"""
+        res = {}
+        hmax = max(b - a for a, b in zip(self.bounds[:-1], self.bounds[1:]))
+        for plane in planes:
+            dtype = torch.int32 if plane in ("R", "G", "B") else torch.float32
+            blk = torch.zeros((hmax, self.L), dtype=dtype, device=self.device)
+            n = self.row_hi - self.row_lo
+            if n:
+                self.m.rows_to_device(plane, self.row_lo, n, blk[:n])
+            self.sync()
+            if self.world > 1:
+                allb = [torch.empty_like(blk) for _ in range(self.world)]
+                dist.all_gather(allb, blk)
+            else:
+                allb = [blk]
+            self.sync()
+            res[plane] = torch.cat([allb[r][: self.bounds[r + 1] - self.bounds[r]] for r in range(self.world)]).reshape(-1)
+        return res
+

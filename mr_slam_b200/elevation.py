@@ -147,6 +147,19 @@ class ElevationMap:
     def Raytracing(self, length):
         check(self._L.mrslam_elev_raytracing(self._h, int(length)))
 
+    PLANES = dict(elevation=0, variance=1, intensity=2, lowest=3, traver=4, R=5, G=6, B=7)
+
+    def set_owned_rows(self, row_lo, row_hi):
+        """tile-sharded global grid: this instance only fuses points that fall into storage rows [row_lo, row_hi)"""
+        check(self._L.mrslam_elev_set_owned_rows(self._h, int(row_lo), int(row_hi)))
+
+    def rows_to_device(self, plane, storage_row, n_rows, out):
+        """copy n_rows storage rows of a plane into the CUDA tensor `out` (stream-ordered on the library stream)"""
+        check(self._L.mrslam_elev_rows_copy(self._h, self.PLANES[plane], int(storage_row), int(n_rows), out.data_ptr(), 0))
+
+    def rows_from_device(self, plane, storage_row, n_rows, src):
+        check(self._L.mrslam_elev_rows_copy(self._h, self.PLANES[plane], int(storage_row), int(n_rows), src.data_ptr(), 1))
+
     def get_map(self):
         n = self.length * self.length
         out = dict(elevation=np.zeros(n, np.float32), variance=np.zeros(n, np.float32), intensity=np.zeros(n, np.float32),

@@ -75,6 +75,8 @@ def _decl(L):
     L.orc_elev_get_map.argtypes = [vp] + [C.c_void_p] * 7
     L.orc_elev_map_feature.argtypes = [vp] + [C.c_void_p] * 9
     L.orc_elev_raytracing.argtypes = [vp]
+    L.orc_elev_set_owned_rows.argtypes = [vp, i, i]
+    L.orc_elev_rows_copy.argtypes = [vp, i, i, i, C.c_void_p, i]
     L.orc_elev_get_state.argtypes = [vp, _p(np.float32), _p(np.int32)]
 
     L.orc_voxelocc.argtypes = [_p(np.float32), i, i, i, i, i, i, i, _p(np.float32), C.c_void_p, C.POINTER(i)]
@@ -271,6 +273,20 @@ class ElevationMap:
 
     def raytracing(self):
         self._L.orc_elev_raytracing(self._h)
+
+    PLANES = dict(elevation=0, variance=1, intensity=2, lowest=3, traver=4, R=5, G=6, B=7)
+
+    def set_owned_rows(self, row_lo, row_hi):
+        self._L.orc_elev_set_owned_rows(self._h, int(row_lo), int(row_hi))
+
+    def rows_to_device(self, plane, storage_row, n_rows, out):
+        """same name as the product class; `out` is a CPU torch tensor / numpy array here"""
+        buf = out.numpy() if hasattr(out, "numpy") else out
+        self._L.orc_elev_rows_copy(self._h, self.PLANES[plane], int(storage_row), int(n_rows), buf.ctypes.data, 0)
+
+    def rows_from_device(self, plane, storage_row, n_rows, src):
+        buf = src.contiguous().numpy() if hasattr(src, "numpy") else np.ascontiguousarray(src)
+        self._L.orc_elev_rows_copy(self._h, self.PLANES[plane], int(storage_row), int(n_rows), buf.ctypes.data, 1)
 
     def get_map(self):
         n = self.length * self.length

@@ -39,6 +39,7 @@ struct ElevMap {
   float central[2] = {0, 0};
   int start[2] = {0, 0};
   float sensor_z = 0;
+  int row_lo = 0, row_hi = 0;  // owned STORAGE rows (tile-sharded grid); [0, L) after init
   std::vector<float> elevation, variance, intensity, lowest, traver;
   std::vector<int> R, G, B;
 
@@ -49,6 +50,8 @@ struct ElevMap {
     obstacle_thr = obst;
     central[0] = central[1] = 0;
     start[0] = start[1] = 0;
+    row_lo = 0;
+    row_hi = L;
     size_t n = (size_t)L * L;
     elevation.assign(n, -10.f);
     variance.assign(n, -10.f);
@@ -210,7 +213,12 @@ int orc_elev_process_points(void* h, int* map_index, const float* px, const floa
       hv += fmaf(b1[2], sJ[2], fmaf(b1[1], sJ[1], b1[0] * sJ[0]));
       var[i] = hv;
       int gi = m->points_to_index(xt, yt);
-      map_index[i] = m->points_to_map_index(xt, yt);
+      int mi = m->points_to_map_index(xt, yt);
+      if (mi != -1 && (mi / m->L < m->row_lo || mi / m->L >= m->row_hi)) {  // a cell of another tile (tile-sharded grid)
+        mi = -1;
+        gi = -1;
+      }
+      map_index[i] = mi;
       if (gi != -1) {
         if (height < m->lowest[gi]) m->lowest[gi] = height + 3 * hv;
       }
@@ -452,6 +460,22 @@ void orc_elev_raytracing(void* h) {
   }
   m->elevation.swap(out);
   std::fill(m->lowest.begin(), m->lowest.end(), 10.f);
+}
+
+void orc_elev_set_owned_rows(void* h, int row_lo, int row_hi) {
+  ElevMap* m = (ElevMap*)h;
+  m->row_lo = row_lo;
+  m->row_hi = row_hi;
+}
+// plane: 0 elevation, 1 variance, 2 intensity, 3 lowest, 4 traver, 5/6/7 R/G/B; buf = n_rows * L 4-byte elements
+void orc_elev_rows_copy(void* h, int plane, int storage_row, int n_rows, void* buf, int to_map) {
+  ElevMap* m = (ElevMap*)h;
+  void* planes[8] = {m->elevation.data(), m->variance.data(), m->intensity.data(), m->lowest.data(), m->traver.data(),
+                     m->R.data(), m->G.data(), m->B.data()};
+  char* mp = (char*)planes[plane] + (size_t)storage_row * m->L * 4;
+  size_t bytes = (size_t)n_rows * m->L * 4;
+  if (to_map) memcpy(mp, buf, bytes);
+  else memcpy(buf, mp, bytes);
 }
 
 void orc_elev_get_map(void* h, float* elevation, float* variance, float* intensity, int* R, int* G, int* B, float* lowest) {

@@ -301,3 +301,65 @@ def test_map_feature_and_raytracing_vs_oracle_full_size(gpu):
         assert ((eg != -10) != (eo != -10)).sum() <= max(3, int(1e-4 * has.sum()))       # borderline cells of the height test only
         assert (g.get_map()["lowest"] == 10).all()
 
+
+def test_tile_ownership_rows_and_halo(gpu):
+    """BASELINE config 5 primitives on the GPU: set_owned_rows (points of other tiles are outside the map), rows copy in both directions,
+    and Map_feature on a tile whose halo rows were filled from the neighbouring tile -- against the CPU oracle twins and against the
+    whole map: union of two tiles == whole map bit for bit (elevation, variance), features on owned rows identical."""
+    import torch
+    from mr_slam_b200 import dist as mdist
+    L, res = 201, 0.15
+    whole = elevation.ElevationMap()
+    whole.Init_GPU_elevationmap(L, res, 2.5, 0.2)
+    tiles = []
+    for r in range(2):
+        m = elevation.ElevationMap()
+        m.Init_GPU_elevationmap(L, res, 2.5, 0.2)
+        tiles.append((m, mdist.TiledElevationMap(m, L, rank=r, world=2, device="cuda")))
+    otile = oracle.ElevationMap(L, res, 2.5, 0.2)
+    otile.set_owned_rows(tiles[1][1].row_lo, tiles[1][1].row_hi)
+    for f in range(3):
+        pose, x, y, z, args = frame(f, "vlp16")
+        n = len(x)
+        pos = pose[:3, 3].astype(np.float32)
+        zi = np.zeros(n, np.int32)
+        for m in [whole] + [t[0] for t in tiles]:
+            m.Move(pos, res, L)
+            r = m.Process_points(x, y, z, args[0], n, *args[1:])
+            m.Fuse(L, n, r[0], zi, zi, zi, np.zeros(n, np.float32), r[4], r[1])
+            if m is tiles[1][0]:
+                r_tile = r
+        otile.move(pos)
+        ro = otile.process_points(x, y, z, *args)
+        otile.fuse(ro[0], zi, zi, zi, np.zeros(n, np.float32), ro[4], ro[1])
+        assert np.array_equal(r_tile[0], ro[0])                       # ownership filter: same indices as the oracle twin
+    W = whole.get_map()
+    union_e = np.empty((L, L), np.float32)
+    union_v = np.empty((L, L), np.float32)
+    for m, t in tiles:
+        g = m.get_map()
+        e = g["elevation"].reshape(L, L)
+        union_e[t.row_lo:t.row_hi] = e[t.row_lo:t.row_hi]
+        union_v[t.row_lo:t.row_hi] = g["variance"].reshape(L, L)[t.row_lo:t.row_hi]
+        outside = np.ones(L, bool)
+        outside[t.row_lo:t.row_hi] = False
+        assert (e[outside] == -10).all()
+    assert np.array_equal(union_e.reshape(-1), W["elevation"]) and np.array_equal(union_v.reshape(-1), W["variance"])
+    assert np.array_equal(tiles[1][0].get_map()["elevation"], otile.get_map()["elevation"])
+    # rows copy round trip + manual halo exchange between the two tile instances (what TiledElevationMap does through all_gather)
+    h = 2
+    (m0, t0), (m1, t1) = tiles
+    buf = torch.empty((h, L), dtype=torch.float32, device="cuda")
+    for src, dst, src_row, dst_row in [(m1, m0, t1.row_lo, t0.row_hi), (m0, m1, t0.row_hi - h, t1.row_lo - h),
+                                       (m1, m0, t1.row_hi - h, (t0.row_lo - h) % L), (m0, m1, t0.row_lo, t1.row_hi % L)]:
+        for j in range(h):
+            src.rows_to_device("elevation", (src_row + j) % L, 1, buf[j])
+            dst.rows_from_device("elevation", (dst_row + j) % L, 1, buf[j])
+    fw = whole.Map_feature(L)
+    for m, t in tiles:
+        ft = m.Map_feature(L)
+        for k in ("elevation", "rough", "slope", "traver"):
+            assert np.array_equal(ft[k].reshape(L, L)[t.row_lo:t.row_hi], fw[k].reshape(L, L)[t.row_lo:t.row_hi]), k
+    with pytest.raises(Exception):
+        m0.set_owned_rows(5, L + 1)
+

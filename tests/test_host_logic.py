@@ -127,3 +127,70 @@ def test_message_key_packing_matches_reference_formulas():
             assert k - ref_key - 1 == idx                        # ICPCheck: id - robotID2Key(robot) - 1
             assert msgs.key_unpack(k) == (robot, idx)
 
+
+def _elev_frames(kind="vlp16", nf=3):
+    for f in range(nf):
+        pose = synth.pose_matrix(2.0 * f + 0.3, -1.0 * f, 0.1 * f, 0.3 * f)
+        pts = synth.make_scan(pose, kind, scan_id=100 + f)
+        ei = synth.elevation_inputs(pose)
+        args = (ei["T"], -5.0, 5.0, ei["min_r"], ei["beam_a"], ei["beam_c"], ei["sensorJacobian"], ei["rotationVariance"],
+                ei["C_SB_transpose"], ei["P_mul_C_BM_transpose"], ei["B_r_BS_skew"])
+        yield pose[:3, 3].astype(np.float32), [np.ascontiguousarray(pts[:, i]) for i in range(3)], args
+
+
+def _feed_oracle(m):
+    for pos, (x, y, z), args in _elev_frames():
+        m.move(pos)
+        r = m.process_points(x, y, z, *args)
+        n = len(x)
+        zi = np.zeros(n, np.int32)
+        m.fuse(r[0], zi, zi, zi, np.zeros(n, np.float32), r[4], r[1])
+
+
+def _tiled_worker(rank, world, port, q):
+    import oracle
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        L, res = 121, 0.25                                   # odd size: uneven tiles
+        full = oracle.ElevationMap(L, res)
+        _feed_oracle(full)
+        m = oracle.ElevationMap(L, res)
+        tiled = mdist.TiledElevationMap(m, L, device="cpu")
+        _feed_oracle(m)                                      # every rank scans all points, keeps its own rows
+        got = tiled.gather_full(("elevation", "variance", "R"))
+        ref = full.get_map()
+        assert np.array_equal(got["elevation"].numpy(), ref["elevation"]) and np.array_equal(got["variance"].numpy(), ref["variance"])
+        assert np.array_equal(got["R"].numpy(), ref["R"])
+        own = m.get_map()["elevation"].reshape(L, L)
+        outside = np.ones(L, bool)
+        outside[tiled.row_lo:tiled.row_hi] = False
+        assert (own[outside] == -10).all()                   # nothing was fused outside the tile
+        feat = tiled.map_feature_owned()                     # halo rows come from the neighbour
+        fref = full.map_feature()
+        for k in ("elevation", "rough", "slope", "traver"):
+            assert np.array_equal(feat[k], fref[k].reshape(L, L)[tiled.row_lo:tiled.row_hi]), k
+        q.put((rank, "ok"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_tiled_global_elevation_world2_gloo():
+    """BASELINE config 5 / SURVEY 8e host logic: storage-row tiles over two processes (gloo, CPU oracle as the map backend): the union of
+    the tiles is the single map bit for bit, and Map_feature on the owned rows -- with the 2-row halo fetched from the neighbour --
+    equals the single-map result, including the rows at the tile border."""
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_tiled_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    assert sorted(q.get(timeout=5) for _ in range(2)) == [(0, "ok"), (1, "ok")]
+
