@@ -111,3 +111,61 @@ def test_solve_translation_row_shifts_vs_numpy_fft(C, shape, row_shift, seed):
         am = int(np.argmax(c.astype(np.float32)))
         if c[am] - np.partition(c, -2)[-2] > 1e-6 * max(1.0, c[am]):       # unique peak: must agree exactly
             assert b[i] == W // 2 - am
+
+
+@settings(max_examples=10, deadline=None)
+@given(st.integers(40, 300), st.sampled_from([5, 15, 20]), st.integers(0, 10**6))
+def test_covariance_oracle_vs_numpy_eigh(n, k, seed):
+    """calculate_covariances (fast_gicp_impl.hpp:241-297): neighbour covariance (divisor k) and the PLANE regularisation
+    V diag(1, 1, 1e-3) V^T, against numpy.linalg.eigh on the same neighbour sets"""
+    rng = np.random.default_rng(seed)
+    pts = (rng.normal(0, 1, (n, 3)) * np.array([3.0, 2.0, 0.2])).astype(np.float32)
+    idx, _ = oracle.knn(pts, pts, k)
+    raw = oracle.covariances(pts, k, oracle.REG_NONE)
+    reg = oracle.covariances(pts, k, oracle.REG_PLANE)
+    for i in range(0, n, 7):
+        nb = pts[idx[i]].astype(np.float64)
+        mean = nb.sum(0) / k
+        C = (nb - mean).T @ (nb - mean) / k
+        assert np.abs(raw[i] - C).max() < 1e-9 * max(1.0, np.abs(C).max())
+        w, V = np.linalg.eigh(C)                                   # ascending
+        if w[1] - w[0] > 1e-6 * w[2] and w[2] - w[1] > 1e-9 * w[2]:   # a well separated smallest eigenvalue -> unique plane normal
+            nrm = V[:, 0]
+            exp = np.eye(3) - (1.0 - 1e-3) * np.outer(nrm, nrm)
+            assert np.abs(reg[i] - exp).max() < 1e-6
+
+
+@settings(max_examples=6, deadline=None)
+@given(st.integers(0, 10**6))
+def test_gicp_oracle_recovers_a_rigid_transform(seed):
+    """round trip: a structured cloud and its rigidly moved copy -> align returns the motion (the 1e-4 bar of the GPU parity tests)"""
+    from mr_slam_b200 import synth
+    rng = np.random.default_rng(seed)
+    src = synth.make_scan(synth.pose_matrix(0.0, 0.0, 0.0, 0.0), "vlp16", scan_id=int(rng.integers(0, 1000)))[::4].astype(np.float32)
+    T = synth.pose_matrix(*rng.normal(0, 0.15, 3), rng.normal(0, 0.03)).astype(np.float64)
+    tgt = (src.astype(np.float64) @ T[:3, :3].T + T[:3, 3]).astype(np.float32)
+    g = oracle.FastGICP()
+    g.set_max_correspondence_distance(2.0)
+    g.set_input_source(src)
+    g.set_input_target(tgt)
+    got = g.align(np.eye(4, dtype=np.float32))
+    assert np.abs(got - T).max() < 2e-3          # float32 clouds: the copy is rounded, so not exactly 1e-4
+
+
+def test_elevation_oracle_kalman_halves_variance():
+    """G_fuse recurrence (gpu_process.cu:477-535): two identical measurements in one cell -> same height, half the variance; a far
+    outlier above the cell replaces it, one below is ignored"""
+    L, res = 20, 0.5
+    m = oracle.ElevationMap(L, res)
+    idx = np.array([5 * L + 7] * 2, np.int32)
+    z = np.zeros(2, np.int32)
+    h = np.array([1.25, 1.25], np.float32)
+    v = np.array([0.04, 0.04], np.float32)
+    m.fuse(idx, z, z, z, np.zeros(2, np.float32), h, v)
+    g = m.get_map()
+    assert g["elevation"][5 * L + 7] == np.float32(1.25) and abs(g["variance"][5 * L + 7] - 0.02) < 1e-7
+    m.fuse(idx[:1], z[:1], z[:1], z[:1], np.zeros(1, np.float32), np.array([9.0], np.float32), np.array([0.01], np.float32))
+    assert m.get_map()["elevation"][5 * L + 7] == np.float32(9.0)           # Mahalanobis > 5 and higher: replaces
+    m.fuse(idx[:1], z[:1], z[:1], z[:1], np.zeros(1, np.float32), np.array([-3.0], np.float32), np.array([0.01], np.float32))
+    assert m.get_map()["elevation"][5 * L + 7] == np.float32(9.0)           # Mahalanobis > 5 and lower: ignored
+    assert (np.delete(m.get_map()["variance"], 5 * L + 7) == np.float32(1e-4)).all()   # every other cell: the 1e-4 floor
