@@ -256,6 +256,12 @@ int mrslam_voxelfeat_transform(const float* point, int size, int max_length, int
  * writes only what generate_RING keeps (channel 2, the max-height image) as d_bev[batch][num_x][num_y]. */
 int mrslam_voxelocc_bev_device(const float* d_points_soa, const long long* offsets_host, int batch, int max_length,
                                int max_height, int num_x, int num_y, float* d_bev);
+/* RING front end from RAW scans in one pass: load_pc_infer (LoopDetection/src/RING_ros/util.py:91-112: keep |x|,|y| < xy_range,
+ * 0 < z < z_range, scale to [-1,1]) fused with the channel-2 (max-height) voxeliser of generate_RING (util.py:174-188).
+ * d_points: device, `stride` floats per point (x y z first), scans concatenated; offsets_host[batch+1] in points.  d_bev:
+ * device float[batch*num_x*num_y].  The reference does both steps on the CPU per scan. */
+int mrslam_ring_scans_to_bev_device(const float* d_points, const long long* offsets_host, int batch, int stride, float xy_range,
+                                    float z_range, int max_length, int max_height, int num_x, int num_y, float* d_bev);
 
 /* ------------------------------------------------------------------------------------------ */
 /* Radon / RING -- replace torch_radon.ParallelBeam.forward (TR/torch_radon/radon.py:62-87,      */

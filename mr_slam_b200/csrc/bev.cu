@@ -29,8 +29,11 @@ struct VoxCfg {
   float max_height;  // polar only
 };
 
+__device__ __forceinline__ bool cart_index_xyz(float x, float y, float z, const VoxCfg& c, int& ix, int& iy, int& ih);
 __device__ __forceinline__ bool cart_index(const float* __restrict__ pt, int i, const VoxCfg& c, int& ix, int& iy, int& ih) {
-  float x = pt[i], y = pt[i + c.size], z = pt[i + 2 * (size_t)c.size];
+  return cart_index_xyz(pt[i], pt[i + c.size], pt[i + 2 * (size_t)c.size], c, ix, iy, ih);
+}
+__device__ __forceinline__ bool cart_index_xyz(float x, float y, float z, const VoxCfg& c, int& ix, int& iy, int& ih) {
   if (x == 0.0f) x = 0.0001f;
   if (y == 0.0f) y = 0.0001f;
   if (z == 0.0f) z = 0.0001f;
@@ -111,6 +114,29 @@ __global__ void k_vox_cart_bev_batch(const float* __restrict__ pts, const long l
     if (!cart_index(pt, i, c, ix, iy, ih)) continue;
     const float z = pt[i + 2 * (size_t)n];
     if (z > 0.0f) atomicMax(&bev_bits[(size_t)b * num_x * num_y + iy + ix * num_y], __float_as_int(z));
+  }
+}
+
+// RING front end in one pass over the RAW scans (AoS rows of `stride` floats, x y z first): load_pc_infer
+// (LoopDetection/src/RING_ros/util.py:91-112 -- keep |x|,|y| < xy_range, 0 < z < z_range, divide by the ranges) fused with the
+// channel-2 voxeliser above.  The compaction the reference does (`pc[conditions]`) only changes the point order, which the
+// max-height image does not depend on.
+__global__ void k_ring_scan_bev_batch(const float* __restrict__ pts, const long long* __restrict__ offsets, int stride, float xy_range,
+                                      float z_range, float gap_x, float gap_y, float gap_h, int num_x, int num_y, int* __restrict__ bev_bits) {
+  const int b = blockIdx.y;
+  const long long o0 = offsets[b], o1 = offsets[b + 1];
+  const int n = (int)(o1 - o0);
+  VoxCfg c;
+  c.size = n; c.gap_x = gap_x; c.gap_y = gap_y; c.gap_h = gap_h; c.num_x = num_x; c.num_y = num_y; c.num_h = 1; c.enough_large = 1;
+  const float* pt = pts + (size_t)o0 * stride;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float* p = pt + (size_t)i * stride;
+    const float x = p[0], y = p[1], z = p[2];
+    if (!(fabsf(x) < xy_range && fabsf(y) < xy_range && z < z_range && z > 0.0f)) continue;
+    const float xs = x / xy_range, ys = y / xy_range, zs = z / z_range;
+    int ix, iy, ih;
+    if (!cart_index_xyz(xs, ys, zs, c, ix, iy, ih)) continue;
+    if (zs > 0.0f) atomicMax(&bev_bits[(size_t)b * num_x * num_y + iy + ix * num_y], __float_as_int(zs));
   }
 }
 
@@ -442,6 +468,41 @@ int mrslam_voxelocc_bev_device(const float* d_points_soa, const long long* offse
     count_launch(1);
   }
   MR_CUDA(cudaGetLastError());
+  return MRSLAM_OK;
+}
+
+int mrslam_ring_scans_to_bev_device(const float* d_points, const long long* offsets_host, int batch, int stride, float xy_range,
+                                    float z_range, int max_length, int max_height, int num_x, int num_y, float* d_bev) {
+  MR_CHECK(ensure_init());
+  if (batch < 0 || stride < 3 || num_x <= 0 || num_y <= 0 || !(xy_range > 0.f) || !(z_range > 0.f) || (batch > 0 && (!offsets_host || !d_bev))) {
+    set_error("ring_scans_to_bev: bad arguments");
+    return MRSLAM_ERR_ARG;
+  }
+  if (batch == 0) return MRSLAM_OK;
+  std::lock_guard<std::mutex> lk(rt().mu);
+  cudaStream_t st = rt().stream;
+  BevScratch& S = bs();
+  MR_CHECK(S.offsets.reserve(batch + 1));
+  MR_CUDA(cudaMemcpyAsync(S.offsets.p, offsets_host, sizeof(long long) * (batch + 1), cudaMemcpyHostToDevice, st));
+  long long maxn = 0;
+  for (int b = 0; b < batch; b++) maxn = std::max(maxn, offsets_host[b + 1] - offsets_host[b]);
+  if (maxn > 0 && !d_points) {
+    set_error("ring_scans_to_bev: null points");
+    return MRSLAM_ERR_ARG;
+  }
+  const float gap_x = (float)(2.0 * (double)(float)max_length / (double)(float)num_x);
+  const float gap_y = (float)(2.0 * (double)(float)max_length / (double)(float)num_y);
+  const float gap_h = (float)(2.0 * (double)(float)max_height / 1.0);
+  MR_CUDA(cudaMemsetAsync(d_bev, 0, sizeof(float) * (size_t)batch * num_x * num_y, st));
+  if (maxn > 0) {
+    int gx = (int)std::min<long long>((maxn + 255) / 256, 64);
+    k_ring_scan_bev_batch<<<dim3(gx, batch), 256, 0, st>>>(d_points, S.offsets.p, stride, xy_range, z_range, gap_x, gap_y, gap_h, num_x, num_y,
+                                                          (int*)d_bev);
+    count_launch(1);
+  }
+  MR_CUDA(cudaGetLastError());
+  // the pageable offsets array was read by an asynchronous copy: do not return before it has been consumed
+  MR_CUDA(cudaStreamSynchronize(st));
   return MRSLAM_OK;
 }
 }

@@ -561,7 +561,10 @@ static int move_locked(Elev* m, const float* pos, float resolution, int length, 
   };
   for (int i = 0; i < 2; i++) {
     if (ishift[i] != 0) {
-      if (ishift[i] >= length) {
+      // |shift| >= length in EITHER direction leaves no cell of the old window inside the new one: clear everything.  (The
+      // reference tests only `ishift >= length`; a large negative shift then clears |ishift| > length strips and writes past
+      // the end of its six planes -- undefined behaviour there, a clear-all here and in the oracle.)
+      if (ishift[i] >= length || ishift[i] <= -length) {
         int n = length * length;
         k_elev_fill<<<(n + 127) / 128, 128, 0, st>>>(m->elevation.p, m->variance.p, m->intensity.p, m->lowest.p, m->traver.p, m->R.p,
                                                     m->G.p, m->B.p, n, 1);
@@ -920,6 +923,12 @@ int mrslam_elev_raytracing(mrslam_elev_t* h, int length) {
   if (length != m->g.L) {
     set_error("Raytracing: length %d does not match the map (%d)", length, m->g.L);
     return MRSLAM_ERR_ARG;
+  }
+  if (m->g.row_lo != 0 || m->g.row_hi != m->g.L) {
+    // a tile of a sharded grid only holds the map_lowest / traversability values of its own rows; rays cross tiles
+    set_error("Raytracing: this map instance owns storage rows [%d, %d) of %d only (tile-sharded grid); gather the planes first",
+              m->g.row_lo, m->g.row_hi, m->g.L);
+    return MRSLAM_ERR_STATE;
   }
   std::lock_guard<std::mutex> lk2(m->mu);
   std::lock_guard<std::mutex> lk(rt().mu);

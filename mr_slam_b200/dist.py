@@ -47,6 +47,98 @@ def allgather_slots(local_slots, async_op=False):
     return (out, work) if async_op else out
 
 
+def neighbor_exchange(offer, send_to, recv_from, out=None, async_op=False):
+    """Point-to-point exchange of candidate clouds: this rank sends `offer` [S, N, 3] to rank `send_to` and receives the same-shaped
+    block of rank `recv_from` -- exactly the bytes the receiver needs (one ncclSend + one ncclRecv in a group), instead of the
+    N-way all-gather whose receive volume grows with the world size.  Returns `out` (and the list of works when async_op=True;
+    `wait_all(works)` orders the current stream after them)."""
+    if out is None:
+        out = torch.empty_like(offer)
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        out.copy_(offer)
+        return (out, []) if async_op else out
+    ops = [dist.P2POp(dist.isend, offer.contiguous(), send_to), dist.P2POp(dist.irecv, out, recv_from)]
+    works = dist.batch_isend_irecv(ops)
+    if async_op:
+        return out, works
+    wait_all(works)
+    return out
+
+
+def wait_all(works):
+    for w in works or []:
+        w.wait()
+
+
+def exchange_requested(clouds, pairs, rank=None, world=None, device=None):
+    """General form of the loop-closure exchange (SURVEY 8e): `clouds` maps this robot's keyframe index -> tensor [N, 3];
+    `pairs` is the GLOBAL candidate list (src_robot, src_kf, tgt_robot, tgt_kf).  Every rank sends each peer only the target
+    clouds that peer's pairs ask for (one packed buffer per peer, grouped ncclSend/ncclRecv) and gets back a dict
+    (tgt_robot, tgt_kf) -> tensor for the pairs it refines.  All clouds must have the same shape."""
+    rank = dist.get_rank() if rank is None else rank
+    world = dist.get_world_size() if world is None else world
+    want = {}     # peer -> sorted list of (robot, kf) I need from it
+    give = {}     # peer -> sorted list of kf it needs from me
+    for p in pairs:
+        a, b = owner_of_pair(p, world), p[2] % world
+        if a == b:
+            continue
+        if a == rank:
+            want.setdefault(b, set()).add((p[2], p[3]))
+        if b == rank:
+            give.setdefault(a, set()).add(p[3])
+    want = {k: sorted(v) for k, v in want.items()}
+    give = {k: sorted(v) for k, v in give.items()}
+    any_cloud = next(iter(clouds.values()))
+    ops, recv_bufs, keep = [], {}, []
+    for peer, kfs in sorted(give.items()):
+        buf = torch.stack([clouds[k] for k in kfs]).contiguous()
+        keep.append(buf)
+        ops.append(dist.P2POp(dist.isend, buf, peer))
+    for peer, keys in sorted(want.items()):
+        buf = torch.empty((len(keys),) + tuple(any_cloud.shape), dtype=any_cloud.dtype, device=any_cloud.device if device is None else device)
+        recv_bufs[peer] = buf
+        ops.append(dist.P2POp(dist.irecv, buf, peer))
+    if ops:
+        wait_all(dist.batch_isend_irecv(ops))
+    got = {}
+    for peer, keys in want.items():
+        for j, key in enumerate(keys):
+            got[key] = recv_bufs[peer][j]
+    for p in pairs:   # targets that live on this rank need no exchange
+        if owner_of_pair(p, world) == rank and p[2] % world == rank:
+            got[(p[2], p[3])] = clouds[p[3]]
+    return got
+
+
+def shard_batch(n_items, rank, world):
+    """Contiguous split of a batch of independent units (RING scans): [lo, hi) of this rank."""
+    return (rank * n_items) // world, ((rank + 1) * n_items) // world
+
+
+def allgather_descriptors(local_desc, n_total):
+    """RING multi-GPU step (SURVEY 8e): every rank has built the descriptors of its shard of the scan batch (`shard_batch`);
+    one all-gather makes the whole database [n_total, ...] available on every rank, which then correlates its own queries
+    against all of it.  `local_desc` is a real tensor [n_local, ...] (complex descriptors as view_as_real); shards may differ
+    by one scan, so they are padded to the largest."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return local_desc
+    world = dist.get_world_size()
+    nmax = (n_total + world - 1) // world
+    pad = torch.zeros((nmax,) + tuple(local_desc.shape[1:]), dtype=local_desc.dtype, device=local_desc.device)
+    pad[: local_desc.shape[0]] = local_desc
+    out = torch.empty((world,) + tuple(pad.shape), dtype=pad.dtype, device=pad.device)
+    if pad.is_cuda:
+        dist.all_gather_into_tensor(out, pad)
+    else:
+        dist.all_gather(list(out.unbind(0)), pad)
+    parts = []
+    for r in range(world):
+        lo, hi = shard_batch(n_total, r, world)
+        parts.append(out[r, : hi - lo])
+    return torch.cat(parts)
+
+
 def gather_results(local_T, local_ids, n_total):
     """local_T: [n_local,4,4] float32, local_ids: global pair indices.  Returns [n_total,4,4] on every rank."""
     T = torch.zeros((n_total, 4, 4), dtype=torch.float32, device=local_T.device)
@@ -99,18 +191,33 @@ class TiledElevationMap:
         self.row_lo, self.row_hi = self.bounds[self.rank], self.bounds[self.rank + 1]
         if self.world > 1 and min(b - a for a, b in zip(self.bounds[:-1], self.bounds[1:])) < self.halo:
             raise ValueError("tiles must be at least `halo` rows high")
+        if sync is None and str(device).startswith("cuda"):
+            # rows_to_device / rows_from_device enqueue D2D copies on the LIBRARY stream while torch.cat / the collectives run
+            # on torch's and NCCL's streams: without an explicit order a gather could read half-written rows
+            from ._lib import lib
+
+            def sync():
+                lib().mrslam_device_synchronize()
+                torch.cuda.synchronize()
         self.sync = sync if sync is not None else (lambda: None)
         emap.set_owned_rows(self.row_lo, self.row_hi)
 
+    def _spans(self, row, n):
+        """storage rows wrap around (ring buffer): [row, row+n) as at most two contiguous spans (start, count, offset)"""
+        row %= self.L
+        first = min(n, self.L - row)
+        return [(row, first, 0)] + ([(0, n - first, first)] if n > first else [])
+
     def _rows(self, plane, row, n, dtype):
         t = torch.empty((n, self.L), dtype=dtype, device=self.device)
-        for j in range(n):                      # storage rows wrap around (ring buffer)
-            self.m.rows_to_device(plane, (row + j) % self.L, 1, t[j])
+        for start, cnt, off in self._spans(row, n):
+            self.m.rows_to_device(plane, start, cnt, t[off:off + cnt])
         return t
 
     def _put(self, plane, row, t):
-        for j in range(t.shape[0]):
-            self.m.rows_from_device(plane, (row + j) % self.L, 1, t[j].contiguous())
+        t = t.contiguous()
+        for start, cnt, off in self._spans(row, t.shape[0]):
+            self.m.rows_from_device(plane, start, cnt, t[off:off + cnt])
 
     def exchange_halo(self, plane="elevation"):
         """fetch the `halo` storage rows above and below the own block from the neighbouring tiles into this replica"""
@@ -120,8 +227,13 @@ class TiledElevationMap:
         dtype = torch.int32 if plane in ("R", "G", "B") else torch.float32
         mine = torch.cat([self._rows(plane, self.row_lo, h, dtype), self._rows(plane, self.row_hi - h, h, dtype)])   # top, bottom
         self.sync()
-        allb = [torch.empty_like(mine) for _ in range(self.world)]
-        dist.all_gather(allb, mine)
+        if mine.is_cuda:
+            allt = torch.empty((self.world,) + tuple(mine.shape), dtype=mine.dtype, device=mine.device)
+            dist.all_gather_into_tensor(allt, mine)
+            allb = list(allt.unbind(0))
+        else:
+            allb = [torch.empty_like(mine) for _ in range(self.world)]
+            dist.all_gather(allb, mine)
         self.sync()
         prev_r, next_r = (self.rank - 1) % self.world, (self.rank + 1) % self.world
         self._put(plane, self.row_lo - h, allb[prev_r][h:])      # the rows just above my block are my predecessor's bottom rows

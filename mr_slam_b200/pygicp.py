@@ -311,6 +311,12 @@ def merge_nearest_keyframes(keyframes, transforms, xy_limit=60.0, leaf=0.2, as_c
     k = len(keyframes)
     T = np.ascontiguousarray(np.asarray(transforms, np.float32).reshape(k, 16))
     on_dev = k > 0 and hasattr(keyframes[0], "data_ptr")
+    # one row stride for the whole pointer table: a list mixing (n,3) and (n,4) keyframes would be read with the wrong stride
+    widths = {int(a.shape[1]) if len(a.shape) == 2 else -1 for a in keyframes}
+    if k and (len(widths) != 1 or min(widths) < 3):
+        raise ValueError("merge_nearest_keyframes: every keyframe must be (n_i, c) with the same c >= 3, got widths %s" % sorted(widths))
+    if k and any(hasattr(a, "data_ptr") != on_dev for a in keyframes):
+        raise ValueError("merge_nearest_keyframes: keyframes must be all CUDA tensors or all host arrays")
     if on_dev:
         kfs = [t.contiguous().float() for t in keyframes]
         ptrs = (C.c_void_p * k)(*[t.data_ptr() for t in kfs])

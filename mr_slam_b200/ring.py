@@ -42,6 +42,22 @@ def bev_batch_device(d_pts_soa, offsets, num_x=NUM_RING, num_y=NUM_SECTOR):
     return bev
 
 
+def scans_to_bev_device(d_scans, n_points=None, offsets=None, xy_range=70.0, z_range=30.0, num_x=NUM_RING, num_y=NUM_SECTOR):
+    """RAW scans -> max-height BEV images in one kernel: load_pc_infer (util.py:91-112) + voxelocc channel 2 (util.py:174-188).
+    d_scans: CUDA float32 [B, N, C>=3] (offsets None: every scan has N points) or [sum N_i, C] with `offsets` (B+1, points)."""
+    if offsets is None:
+        B, N, Cc = d_scans.shape
+        offsets = np.arange(B + 1, dtype=np.int64) * N
+    else:
+        offsets = np.ascontiguousarray(offsets, np.int64)
+        B, Cc = len(offsets) - 1, d_scans.shape[-1]
+    bev = torch.empty((B, num_x, num_y), dtype=torch.float32, device=d_scans.device)
+    torch.cuda.current_stream(d_scans.device).synchronize()
+    check(lib().mrslam_ring_scans_to_bev_device(ptr(d_scans), offsets.ctypes.data, B, int(Cc), float(xy_range), float(z_range), MAX_LENGTH,
+                                                MAX_HEIGHT, num_x, num_y, ptr(bev)))
+    return bev
+
+
 def ring_angles(device, n=NUM_RING):
     return torch.from_numpy(np.linspace(0, 2 * np.pi, n).astype(np.float32)).to(device)  # util.py:192 (endpoint inclusive)
 

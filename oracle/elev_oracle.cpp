@@ -136,7 +136,9 @@ void orc_elev_move(void* h, const float* current_position3, float resolution, in
   for (int i = 0; i < 2; i++) aligned_shift_out2[i] = (float)ishift[i] * resolution;
   for (int i = 0; i < 2; i++) {
     if (ishift[i] != 0) {
-      if (ishift[i] >= length) {  // (sic) only the positive overflow clears everything in the reference
+      // The reference tests only `ishift >= length`; a negative shift of >= length cells then clears more strips than the map has
+      // and writes out of bounds (undefined behaviour).  Oracle and CUDA path both treat |shift| >= length as clear-all.
+      if (ishift[i] >= length || ishift[i] <= -length) {
         for (size_t c = 0; c < (size_t)length * length; c++) m->clear_cell(c, true);
       } else {
         int sign = ishift[i] > 0 ? 1 : -1;

@@ -82,6 +82,31 @@ def test_batched_device_bev_equals_per_scan(gpu):
         assert np.array_equal(bev[i], exp)
 
 
+def test_fused_scan_to_bev_equals_load_pc_infer_plus_voxelocc(gpu):
+    """mrslam_ring_scans_to_bev_device (raw scans -> BEV in one kernel) == load_pc_infer (restated in synth.ring_preprocess, RING
+    util.py:91-112) followed by the voxelocc oracle, bit for bit -- including points on the filter limits, z = 0 and NaNs."""
+    import torch
+    raw = [synth.make_scan(synth.pose_matrix(i, -i, 0, 0.2 * i), "vlp16", 60 + i) + np.array([0, 0, 1.8], np.float32) for i in range(3)]
+    edge = np.array([[70.0, 0, 1], [-70.0, 0, 1], [69.99999, 1, 1], [0, 0, 0], [1, 1, 30.0], [1, 1, 29.999998], [np.nan, 0, 1],
+                     [0.0, 0.0, 5.0], [5, -69.99999, 0.5]], np.float32)
+    raw[1] = np.concatenate([raw[1][:-len(edge)], edge]).astype(np.float32)
+    d = torch.from_numpy(np.stack(raw)).cuda()
+    bev = ring.scans_to_bev_device(d).cpu().numpy()
+    for i, r in enumerate(raw):
+        p = synth.ring_preprocess(r)
+        soa = np.ascontiguousarray(p.T.reshape(-1))
+        exp = oracle.voxelocc(soa, len(p), 1, 1, 120, 120, 1, 1).reshape(-1, 3)[:, 2].reshape(120, 120)
+        assert np.array_equal(bev[i], exp), i
+    # ragged batch with 4 floats per point (x y z intensity) and an empty scan
+    rag = [np.concatenate([r[: 1000 * (i + 1)], np.ones((1000 * (i + 1), 1), np.float32)], 1) for i, r in enumerate(raw)] + [np.zeros((0, 4), np.float32)]
+    offs = np.concatenate([[0], np.cumsum([len(r) for r in rag])]).astype(np.int64)
+    bev2 = ring.scans_to_bev_device(torch.from_numpy(np.concatenate(rag)).cuda(), offsets=offs).cpu().numpy()
+    for i, r in enumerate(rag):
+        p = synth.ring_preprocess(r[:, :3])
+        exp = oracle.voxelocc(np.ascontiguousarray(p.T.reshape(-1)) if len(p) else np.zeros(3, np.float32), len(p), 1, 1, 120, 120, 1, 1)
+        assert np.array_equal(bev2[i], exp.reshape(-1, 3)[:, 2].reshape(120, 120)), i
+
+
 def test_empty_and_argument_errors(gpu):
     out = np.zeros(3, np.float32)
     t = voxelocc.GPUTransformer(np.zeros(3, np.float32), 0, 1, 1, 120, 120, 1, 1)

@@ -64,6 +64,30 @@ def test_process_fuse_sequence_vs_oracle(gpu, L, res, kind):
     assert all(np.array_equal(a, b) for a, b in zip(g.state(), o.state()))
 
 
+@pytest.mark.parametrize("jump", [-(2 * 60 + 3), -60, 2 * 60 + 3, -59])
+def test_move_large_jump_matches_oracle(gpu, jump):
+    """|shift| >= length in either direction is a clear-all (the reference's one-sided test overruns its planes
+    for large negative shifts); shifts just below the length still clear strips.  Map state must equal the oracle's."""
+    L, res = 60, 0.2
+    g = elevation.ElevationMap()
+    g.Init_GPU_elevationmap(L, res, 2.5, 0.2)
+    o = oracle.ElevationMap(L, res, 2.5, 0.2)
+    pose, x, y, z, args = frame(0, "vlp16")
+    n = len(x)
+    p0 = pose[:3, 3].astype(np.float32)
+    for pos in (p0, p0 + np.array([jump * res, 0.0, 0.0], np.float32), p0 + np.array([jump * res, -jump * res, 0.0], np.float32)):
+        for a, b in zip(g.Move(pos, res, L), o.move(pos)):
+            assert np.array_equal(a, b)
+        rg = g.Process_points(x, y, z, args[0], n, *args[1:])
+        ro = o.process_points(x, y, z, *args)
+        zi = np.zeros(n, np.int32)
+        g.Fuse(L, n, rg[0], zi, zi, zi, np.zeros(n, np.float32), rg[4], rg[1])
+        o.fuse(ro[0], zi, zi, zi, np.zeros(n, np.float32), ro[4], ro[1])
+        mg, mo = g.get_map(), o.get_map()
+        for k in ("elevation", "variance", "intensity"):
+            assert np.array_equal(mg[k], mo[k]), k
+
+
 def test_many_points_per_cell_order_dependence(gpu):
     """The Mahalanobis branch makes the result depend on the per-cell point order: feed thousands of points into a handful
     of cells, in an order where sorting by height would give a different answer."""

@@ -79,6 +79,26 @@ def _worker(rank, world, port, q):
         T_all = mdist.gather_results(T_local, mine, len(pairs))
         for i in range(len(pairs)):
             assert torch.equal(T_all[i], torch.eye(4) * (i + 1))
+        # neighbour-only exchange (what bench.py uses at N > 1): this rank offers the targets of rank-1's pairs
+        offer = torch.full((S, N, 3), 10.0 + rank)
+        got = mdist.neighbor_exchange(offer, send_to=(rank - 1) % world, recv_from=(rank + 1) % world)
+        assert torch.equal(got, torch.full((S, N, 3), 10.0 + (rank + 1) % world))
+        got2, works = mdist.neighbor_exchange(offer, (rank - 1) % world, (rank + 1) % world, async_op=True)
+        mdist.wait_all(works)
+        assert torch.equal(got2, got)
+        # general form: every rank receives exactly the clouds its pairs ask for
+        clouds = {kf: torch.full((N, 3), 100.0 * rank + kf) for kf in range(S)}
+        pairs2 = [(r, i, (r + 1) % world, (i + 1) % S) for r in range(world) for i in range(S)] + [(0, 0, 0, 1)]
+        gotd = mdist.exchange_requested(clouds, pairs2, rank, world)
+        for p in pairs2:
+            if mdist.owner_of_pair(p, world) == rank:
+                assert torch.equal(gotd[(p[2], p[3])], torch.full((N, 3), 100.0 * p[2] + p[3]))
+        # RING batch sharding + descriptor all-gather (uneven shards)
+        n_total = 7
+        lo, hi = mdist.shard_batch(n_total, rank, world)
+        local_desc = torch.arange(lo, hi, dtype=torch.float32).view(-1, 1, 1).repeat(1, 4, 2)
+        db = mdist.allgather_descriptors(local_desc, n_total)
+        assert db.shape == (n_total, 4, 2) and torch.equal(db[:, 0, 0], torch.arange(n_total, dtype=torch.float32))
         q.put((rank, "ok"))
     finally:
         dist.destroy_process_group()
@@ -101,15 +121,33 @@ def test_exchange_helpers_world2_gloo():
     assert got == [(0, "ok"), (1, "ok")]
 
 
-def test_bench_reference_arm_prints_contract_line():
+def _bench_ref(extra, env):
     import json
     import subprocess
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
-                       capture_output=True, text=True, timeout=600)
+    e = dict(os.environ, BENCH_REF_BUDGET_S="4", **env)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"] + extra,
+                       capture_output=True, text=True, timeout=600, env=e)
     assert r.returncode == 0, r.stderr
     line = json.loads(r.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
-    assert line["e2e"]["h2d_bytes_per_step"] == 0
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
+    return line
+
+
+def test_bench_reference_arm_prints_contract_line():
+    """--impl reference (the CPU oracle port): contract keys, and the config dict is the one our GPU arm prints for the same flags"""
+    sys.path.insert(0, ROOT)
+    import bench
+    line = _bench_ref(["--pairs", "2"], {})
+    assert line["metric"] == "gicp_aligns_per_s" and line["config"] == bench.config_for("cfg2", 2, 1)
+    assert "elevation_cell_fuses_per_s" in line["cpu_baseline"] and line["cpu_baseline"]["value_8_threads"] > 0
+
+
+def test_bench_reference_arm_ring_and_tiled():
+    line = _bench_ref(["--workload", "ring"], {"BENCH_RING_SCANS": "4", "BENCH_RING_BASE": "2"})
+    assert line["metric"] == "ring_descriptors_per_s" and line["unit"] == "descriptors/s"
+    line = _bench_ref(["--workload", "tiled"], {"BENCH_TILED_FRAMES": "3", "BENCH_TILED_BASE": "2", "BENCH_TILED_L": "400"})
+    assert line["metric"] == "elevation_cell_fuses_per_s" and line["scaling"] == "strong"
 
 
 def test_message_key_packing_matches_reference_formulas():
@@ -194,3 +232,29 @@ def test_tiled_global_elevation_world2_gloo():
         assert p.exitcode == 0
     assert sorted(q.get(timeout=5) for _ in range(2)) == [(0, "ok"), (1, "ok")]
 
+
+
+def test_oracle_move_large_negative_jump_clears_everything():
+    """a first Move of -(2L+3) cells (the reference's one-sided `ishift >= length` test would clear |ishift| strips
+    and run off the planes) is a clear-all in the oracle, exactly like a positive jump of the same size."""
+    import oracle
+    L, res = 40, 0.25
+    for sgn in (-1.0, 1.0):
+        m = oracle.ElevationMap(L, res)
+        _feed_oracle_small(m)
+        assert (m.get_map()["elevation"] != -10).any()
+        pos = np.array([sgn * (2 * L + 3) * res, 0.0, 0.0], np.float32)
+        m.move(pos)
+        mp = m.get_map()
+        assert (mp["elevation"] == -10).all()
+        c, s = m.state()
+        assert 0 <= s[0] < L and 0 <= s[1] < L
+
+
+def _feed_oracle_small(m):
+    for pos, (x, y, z), args in _elev_frames(nf=1):
+        m.move(np.zeros(3, np.float32))
+        r = m.process_points(x, y, z, *args)
+        n = len(x)
+        zi = np.zeros(n, np.int32)
+        m.fuse(r[0], zi, zi, zi, np.zeros(n, np.float32), r[4], r[1])
