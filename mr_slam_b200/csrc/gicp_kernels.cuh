@@ -434,6 +434,7 @@ struct KnnParams {
   int* knn_idx;     // optional test hook, original order [n*k]
   float* knn_sqd;   // optional
   unsigned long long* stat_pairs;  // optional: number of (query,candidate) distance evaluations
+  unsigned char* fb;  // [ceil(ntiles/4)] per-block flag written by k_knn_search_v2: 1 = this block must be redone by k_knn_search
 };
 
 constexpr int SGROUP = MR_SGROUP;  // super-tile box tests kept in flight together (SGROUP x 32 boxes)
@@ -576,9 +577,10 @@ constexpr int KCAND = 64;
 #endif
 
 template <bool STATS>
-__global__ void __launch_bounds__(128, 8) k_knn_search(const KnnParams* __restrict__ plist) {
+__global__ void __launch_bounds__(128, 8) k_knn_search(const KnnParams* __restrict__ plist, int only_flagged) {
   __shared__ int s_list[4][KCAND];
   const KnnParams P = plist[blockIdx.y];
+  if (only_flagged && (blockIdx.x * 4 >= P.ntiles || !P.fb[blockIdx.x])) return;  // second pass behind k_knn_search_v2
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int qt = blockIdx.x * 4 + wib;
   if (qt >= P.ntiles) return;  // warp-uniform; no block-level barrier in this kernel
@@ -693,6 +695,332 @@ __global__ void __launch_bounds__(128, 8) k_knn_search(const KnnParams* __restri
     atomicAdd(P.stat_pairs + 2, inserts);
     atomicAdd(P.stat_pairs + 4, shared_ok ? 0ull : 1ull);
     atomicAdd(P.stat_pairs + 5, (unsigned long long)ncand);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// kNN v2 (k <= 15): the same exact tiled brute force, re-organised around two observations from the round-1 profile
+// (701 warp-instructions per query, 30 % of them serial shuffle-up insertions, 20 % the 64-bit bitonic sort of the own tile):
+//   * list maintenance is ~6x cheaper LANE-PER-QUERY: each lane keeps the k-best list of ITS query as 16 sorted 64-bit
+//     (distance, index) keys in registers and merges candidates sixteen at a time with fully unrolled sorting networks
+//     (Batcher odd-even sort of the batch, 63 compare-exchanges; bitonic merge with the list, 16 + 32) -- no shuffles, 32
+//     queries per instruction;
+//   * distance evaluation is cheapest WARP-PER-QUERY (one candidate point per lane), but a visit does not have to touch the
+//     list: qualifiers (key < the query's current k-th key) are ballot-compacted into a per-query buffer in shared memory as
+//     16-bit (staged tile, lane) ids, at a cost that does not depend on how many there are.
+// One block = four consecutive query tiles (128 queries).  Their candidate tiles -- every tile whose box is within
+// R = max over the block's queries of the own-tile k-th distance of the block's bounding box -- are found ONCE per block and
+// staged in shared memory 32 tiles at a time by 1-D bulk-async copies (cp.async.bulk, completion on an mbarrier), while the
+// lanes compute which staged tiles their own query needs (point-to-box test against the query's own k-th distance).
+// Exactness: a tile is skipped for a query only if its box is provably farther than the query's current k-th key, and a
+// candidate is dropped only if its key is not below that key, so the final list is the exact kNN under (distance, index).
+// Blocks with more than V2_MAXC candidate tiles are flagged in P.fb and redone by k_knn_search.
+// ---------------------------------------------------------------------------------------------
+constexpr int KP = 16;
+constexpr int V2_CH = 32;
+constexpr int V2_MAXC = 256;
+constexpr int V2_CAP = 64;
+constexpr int V2_BSTRIDE = V2_CAP + 2;  // 66 u16 = 33 words per row: lane q reading row q is bank-conflict free
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// 1-D bulk asynchronous copy global -> shared (TMA engine, SASS UBLKCP); bytes and both addresses are multiples of 16
+__device__ __forceinline__ void bulk_load_1d(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+__device__ __forceinline__ void key_ce(u64& a, u64& b) {
+  const bool sw = b < a;
+  const u64 lo = sw ? b : a, hi = sw ? a : b;
+  a = lo;
+  b = hi;
+}
+// Batcher's odd-even merge sort of 16 keys held in registers: 63 compare-exchanges, every index a compile-time constant
+__device__ __forceinline__ void key_sort16(u64 (&v)[KP]) {
+  // (generated from the loop form p = 1,2,4,8; k = p..1; j = k % p, step 2k; i < k; same 2p-block -> compare v[i+j], v[i+j+k])
+  key_ce(v[0], v[1]); key_ce(v[2], v[3]); key_ce(v[4], v[5]); key_ce(v[6], v[7]); key_ce(v[8], v[9]);
+  key_ce(v[10], v[11]); key_ce(v[12], v[13]); key_ce(v[14], v[15]); key_ce(v[0], v[2]); key_ce(v[1], v[3]);
+  key_ce(v[4], v[6]); key_ce(v[5], v[7]); key_ce(v[8], v[10]); key_ce(v[9], v[11]); key_ce(v[12], v[14]);
+  key_ce(v[13], v[15]); key_ce(v[1], v[2]); key_ce(v[5], v[6]); key_ce(v[9], v[10]); key_ce(v[13], v[14]);
+  key_ce(v[0], v[4]); key_ce(v[1], v[5]); key_ce(v[2], v[6]); key_ce(v[3], v[7]); key_ce(v[8], v[12]);
+  key_ce(v[9], v[13]); key_ce(v[10], v[14]); key_ce(v[11], v[15]); key_ce(v[2], v[4]); key_ce(v[3], v[5]);
+  key_ce(v[10], v[12]); key_ce(v[11], v[13]); key_ce(v[1], v[2]); key_ce(v[3], v[4]); key_ce(v[5], v[6]);
+  key_ce(v[9], v[10]); key_ce(v[11], v[12]); key_ce(v[13], v[14]); key_ce(v[0], v[8]); key_ce(v[1], v[9]);
+  key_ce(v[2], v[10]); key_ce(v[3], v[11]); key_ce(v[4], v[12]); key_ce(v[5], v[13]); key_ce(v[6], v[14]);
+  key_ce(v[7], v[15]); key_ce(v[4], v[8]); key_ce(v[5], v[9]); key_ce(v[6], v[10]); key_ce(v[7], v[11]);
+  key_ce(v[2], v[4]); key_ce(v[3], v[5]); key_ce(v[6], v[8]); key_ce(v[7], v[9]); key_ce(v[10], v[12]);
+  key_ce(v[11], v[13]); key_ce(v[1], v[2]); key_ce(v[3], v[4]); key_ce(v[5], v[6]); key_ce(v[7], v[8]);
+  key_ce(v[9], v[10]); key_ce(v[11], v[12]); key_ce(v[13], v[14]);
+}
+// L (sorted) <- the 16 smallest of L u B (both sorted ascending): element-wise min against the reversed batch leaves a bitonic
+// sequence holding exactly those 16, which the bitonic merge network sorts (16 half + 32 full compare-exchanges)
+__device__ __forceinline__ void key_merge16(u64 (&L)[KP], const u64 (&B)[KP]) {
+#pragma unroll
+  for (int i = 0; i < KP; i++) L[i] = B[KP - 1 - i] < L[i] ? B[KP - 1 - i] : L[i];
+#pragma unroll
+  for (int kk = KP / 2; kk >= 1; kk >>= 1)
+#pragma unroll
+    for (int i = 0; i < KP; i++)
+      if ((i & kk) == 0) key_ce(L[i], L[i | kk]);
+}
+
+template <bool STATS>
+__global__ void __launch_bounds__(128, 4) k_knn_search_v2(const KnnParams* __restrict__ plist) {
+  __shared__ __align__(128) float4 s_stage[V2_CH * TILE];  // candidate tiles of the current chunk (bulk-copy destination)
+  __shared__ __align__(16) float4 s_q[4][TILE];            // the block's own four tiles
+  __shared__ __align__(16) float4 s_box[V2_MAXC][2];       // candidate boxes (min xyz, max xyz)
+  __shared__ int s_cand[V2_MAXC];                          // candidate tile ids
+  __shared__ __align__(16) unsigned short s_buf[4][TILE][V2_BSTRIDE];  // per query: buffered qualifiers (staged slot * 32 + lane)
+  __shared__ __align__(8) unsigned long long s_mbar;
+  __shared__ float s_wbox[4][6];
+  __shared__ float s_wR[4];
+  __shared__ int s_ncand;
+
+  const KnnParams P = plist[blockIdx.y];
+  const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+  const int qt0 = blockIdx.x * 4;
+  if (qt0 >= P.ntiles) return;  // block-uniform
+  const int qt = qt0 + wib;
+  const bool wvalid = qt < P.ntiles;
+  const int k = P.k, ntp = P.ntiles_pad, nsp = P.nsuper_pad;
+  const unsigned lt = (1u << lane) - 1u;
+  if (tid == 0) {
+    mbar_init(&s_mbar, 1);
+    s_ncand = 0;
+    fence_mbar_init();
+  }
+  // ---- own tile -> shared; lane-per-query initial list from its 32 points (two batches of 16) ----
+  const float4 qmine = wvalid ? P.psort[(size_t)qt * TILE + lane] : make_float4(PAD_COORD, PAD_COORD, PAD_COORD, __int_as_float(PAD_IDX));
+  s_q[wib][lane] = qmine;
+  __syncwarp();
+  const float qx = qmine.x, qy = qmine.y, qz = qmine.z;
+  const int qidx = __float_as_int(qmine.w);
+  const bool qvalid = wvalid && qidx != PAD_IDX;
+  // The list always holds 16 keys: KP - k minimal sentinels (key 0) in front, so that the k-th best is L[KP-1] whatever k is
+  // and every index into L stays a compile-time constant.  (A real key 0 -- point 0 at distance 0 -- is identical to a
+  // sentinel, so it does not matter which of the two copies ends up in front.)
+  u64 L[KP];
+#pragma unroll
+  for (int i = 0; i < KP; i++) L[i] = (i < KP - k) ? 0ull : KEY_NONE;
+#pragma unroll
+  for (int h = 0; h < 2; h++) {
+    u64 Bt[KP];
+#pragma unroll
+    for (int j = 0; j < KP; j++) {
+      const float4 c = s_q[wib][h * KP + j];
+      Bt[j] = make_key(dist2(qx, qy, qz, c.x, c.y, c.z), __float_as_int(c.w));
+    }
+    key_sort16(Bt);
+    key_merge16(L, Bt);
+  }
+  float tau_d = key_dist(L[KP - 1]);
+  unsigned long long st_visits = 0, st_quals = 0, st_rounds = 0, st_oflow = 0;
+
+  // ---- block-wide candidate tiles: box within R of the block's box, R = largest own-tile k-th distance of the block ----
+  {
+    const float Rw = warp_max(qvalid ? tau_d : 0.0f);
+    if (lane == 0) s_wR[wib] = Rw;
+    if (lane < 6) s_wbox[wib][lane] = wvalid ? P.tb[(size_t)lane * ntp + qt] : (lane < 3 ? FLT_MAX : -FLT_MAX);
+  }
+  __syncthreads();
+  float a[6], Rblk;
+  {
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      a[c] = fminf(fminf(s_wbox[0][c], s_wbox[1][c]), fminf(s_wbox[2][c], s_wbox[3][c]));
+      a[3 + c] = fmaxf(fmaxf(s_wbox[0][3 + c], s_wbox[1][3 + c]), fmaxf(s_wbox[2][3 + c], s_wbox[3][3 + c]));
+    }
+    Rblk = fmaxf(fmaxf(s_wR[0], s_wR[1]), fmaxf(s_wR[2], s_wR[3]));
+  }
+#pragma unroll 1
+  for (int s0 = wib * 32; s0 < P.nsuper; s0 += 128) {
+    const int sidx = s0 + lane;
+    const float bs = (sidx < P.nsuper) ? box_box_dist2(a, P.sb, nsp, sidx) : INFINITY;
+    unsigned ms = __ballot_sync(FULL, bs * CULL_SAFETY <= Rblk);
+    while (ms) {
+      const int js = __ffs(ms) - 1;
+      ms &= ms - 1;
+      const int t = (s0 + js) * 32 + lane;
+      float b6[6];
+#pragma unroll
+      for (int c = 0; c < 6; c++) b6[c] = P.tb[(size_t)c * ntp + t];  // t < ntiles_pad always
+      const float gx = fmaxf(0.0f, fmaxf(b6[0] - a[3], a[0] - b6[3])), gy = fmaxf(0.0f, fmaxf(b6[1] - a[4], a[1] - b6[4])),
+                  gz = fmaxf(0.0f, fmaxf(b6[2] - a[5], a[2] - b6[5]));
+      const bool pass = t < P.ntiles && (gx * gx + gy * gy + gz * gz) * CULL_SAFETY <= Rblk;
+      const unsigned mt = __ballot_sync(FULL, pass);
+      if (mt) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&s_ncand, __popc(mt));
+        base = __shfl_sync(FULL, base, 0);
+        const int pos = base + __popc(mt & lt);
+        if (pass && pos < V2_MAXC) {
+          s_cand[pos] = t;
+          s_box[pos][0] = make_float4(b6[0], b6[1], b6[2], 0.0f);
+          s_box[pos][1] = make_float4(b6[3], b6[4], b6[5], 0.0f);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  const int ncand = s_ncand;
+  if (ncand > V2_MAXC) {  // block-uniform: too many candidates for the staged scheme (huge R: sparse outliers, n < k)
+    if (tid == 0) {
+      P.fb[blockIdx.x] = 1;
+      if (STATS && P.stat_pairs) atomicAdd(P.stat_pairs + 4, 1ull << 32);  // high word: blocks handed to k_knn_search
+    }
+    return;
+  }
+  if (tid == 0) P.fb[blockIdx.x] = 0;
+
+  // ---- chunks of V2_CH staged tiles: warp-per-query scan into the buffers, lane-per-query merge into the lists ----
+  int cnt = 0;  // buffered qualifiers of MY query
+  unsigned phase = 0;
+#pragma unroll 1
+  for (int c0 = 0; c0 < ncand; c0 += V2_CH) {
+    const int nch = min(V2_CH, ncand - c0);
+    __syncthreads();  // every warp is done with the previous chunk
+    if (wib == 0) {
+      if (lane == 0) mbar_arrive_expect_tx(&s_mbar, (unsigned)nch * TILE * 16u);
+      __syncwarp();
+      if (lane < nch) bulk_load_1d(&s_stage[lane * TILE], P.psort + (size_t)s_cand[c0 + lane] * TILE, TILE * 16u, &s_mbar);
+    }
+    // while the copies fly: which staged tiles does MY query need?  (point-to-box distance against my current k-th distance)
+    unsigned need = 0;
+#pragma unroll 4
+    for (int i = 0; i < nch; i++) {
+      const float4 bmn = s_box[c0 + i][0], bmx = s_box[c0 + i][1];
+      const float gx = fmaxf(0.0f, fmaxf(bmn.x - qx, qx - bmx.x)), gy = fmaxf(0.0f, fmaxf(bmn.y - qy, qy - bmx.y)),
+                  gz = fmaxf(0.0f, fmaxf(bmn.z - qz, qz - bmx.z));
+      const bool nd = (gx * gx + gy * gy + gz * gz) * CULL_SAFETY <= tau_d && s_cand[c0 + i] != qt;
+      need |= nd ? (1u << i) : 0u;
+    }
+    if (!qvalid) need = 0;
+    mbar_wait(&s_mbar, phase);
+    phase ^= 1u;
+
+    int qi = 0;
+#pragma unroll 1
+    while (true) {
+      bool overflow = false;
+#pragma unroll 1
+      for (; qi < TILE; qi++) {
+        unsigned m = __shfl_sync(FULL, need, qi);
+        if (!m) continue;
+        const float ox = __shfl_sync(FULL, qx, qi), oy = __shfl_sync(FULL, qy, qi), oz = __shfl_sync(FULL, qz, qi);
+        const u64 otau = __shfl_sync(FULL, L[KP - 1], qi);
+        int ocnt = __shfl_sync(FULL, cnt, qi);
+        unsigned short* row = &s_buf[wib][qi][0];
+        while (m) {
+          const int i = __ffs(m) - 1;
+          const float4 c = s_stage[i * TILE + lane];
+          const u64 ckey = make_key(dist2(ox, oy, oz, c.x, c.y, c.z), __float_as_int(c.w));
+          const bool pass = ckey < otau;
+          const unsigned bal = __ballot_sync(FULL, pass);
+          const int np = __popc(bal);
+          if (ocnt + np > V2_CAP) {  // warp-uniform: merge what is buffered first, then come back to this tile
+            overflow = true;
+            break;
+          }
+          if (pass) row[ocnt + __popc(bal & lt)] = (unsigned short)(i * TILE + lane);
+          ocnt += np;
+          m &= m - 1;
+          if (STATS) st_visits++, st_quals += np;
+        }
+        if (lane == qi) {
+          cnt = ocnt;
+          need = m;  // non-zero only after an overflow: the tiles of this query still to visit
+        }
+        if (overflow) break;
+      }
+      __syncwarp();
+      // ---- lane-per-query merge of the buffered qualifiers, 16 per round (the staged tiles are still resident) ----
+      const int rounds = (__reduce_max_sync(FULL, cnt) + KP - 1) / KP;
+#pragma unroll 1
+      for (int r = 0; r < rounds; r++) {
+        u64 Bt[KP];
+        const unsigned* rowq = reinterpret_cast<const unsigned*>(&s_buf[wib][lane][r * KP]);
+#pragma unroll
+        for (int j2 = 0; j2 < KP / 2; j2++) {
+          const unsigned two = rowq[j2];
+#pragma unroll
+          for (int hh = 0; hh < 2; hh++) {
+            const int j = 2 * j2 + hh;
+            const unsigned id = hh ? (two >> 16) : (two & 0xffffu);
+            u64 key = KEY_NONE;
+            if (r * KP + j < cnt) {
+              const float4 c = s_stage[id];
+              key = make_key(dist2(qx, qy, qz, c.x, c.y, c.z), __float_as_int(c.w));
+            }
+            Bt[j] = key;
+          }
+        }
+        key_sort16(Bt);
+        key_merge16(L, Bt);
+        if (STATS) st_rounds++;
+      }
+      cnt = 0;
+      tau_d = key_dist(L[KP - 1]);
+      __syncwarp();
+      if (!overflow) break;
+      if (STATS) st_oflow++;
+    }
+  }
+
+  // ---- results: neighbour j of my query is L[KP - k + j]; transpose through shared memory for coalesced stores ----
+  __syncwarp();
+  int* s_out = reinterpret_cast<int*>(&s_buf[wib][0][0]);  // 32 x k ints <= 1920 B of this warp's 4224 B buffer
+#pragma unroll
+  for (int i = 0; i < KP; i++) {
+    const int j = i - (KP - k);
+    if (j >= 0) s_out[lane * k + j] = key_idx(L[i]);
+  }
+  __syncwarp();
+  if (wvalid) {
+    int* dst = P.ids + (size_t)qt * TILE * k;
+    for (int e = lane; e < TILE * k; e += 32) dst[e] = s_out[e];
+  }
+  if (P.knn_idx && qvalid) {
+#pragma unroll
+    for (int i = 0; i < KP; i++) {
+      const int j = i - (KP - k);
+      if (j >= 0) {
+        const int id = key_idx(L[i]);
+        const bool real = id != PAD_IDX;
+        P.knn_idx[(size_t)qidx * k + j] = real ? id : -1;
+        if (P.knn_sqd) P.knn_sqd[(size_t)qidx * k + j] = real ? key_dist(L[i]) : INFINITY;
+      }
+    }
+  }
+  if (STATS && P.stat_pairs && wvalid) {
+    st_visits = __shfl_sync(FULL, st_visits, 0);
+    if (lane == 0) {
+      atomicAdd(P.stat_pairs, st_visits * 32ull + 1024ull);  // (query, candidate) distance evaluations of this warp (32 x 32 own tile incl.)
+      atomicAdd(P.stat_pairs + 2, st_quals);
+      atomicAdd(P.stat_pairs + 5, (unsigned long long)ncand);
+      atomicAdd(P.stat_pairs + 6, st_rounds);
+      atomicAdd(P.stat_pairs + 7, st_oflow);
+    }
   }
 }
 

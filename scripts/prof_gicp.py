@@ -23,6 +23,10 @@ for rep in range(reps):
     nl, ne = regs[0].eval_counts()
     print(f"   knn pair evals/query {L.mrslam_gicp_stats_get(0)/(B*2*120000):.0f}, nn1 pair evals/query/pass {L.mrslam_gicp_stats_get(1)/(B*nl*120000):.0f} ({nl} passes), knn insert rounds/query {L.mrslam_gicp_stats_get(2)/(B*2*120000):.1f}, nn1 max tiles in one warp {L.mrslam_gicp_stats_get(3)}, mean tiles per warp-pass {L.mrslam_gicp_stats_get(1)/32/(B*nl*3750):.1f}")
     print(f"   knn tiles on the per-query fallback path {L.mrslam_gicp_stats_get(4)} of {B*2*3750}, mean shared candidates per tile {L.mrslam_gicp_stats_get(5)/(B*2*3750):.1f}")
+    g = L.mrslam_gicp_stats_get
+    nq, nw = B * 2 * 120000, B * 2 * 3750
+    print(f"   knn v2: visits/query {(g(0) - 1024 * nw) / 32 / nq:.2f}, qualifiers/query {g(2) / nq:.1f}, merge rounds/warp {g(6) / nw:.2f}, overflow flushes {g(7)}, "
+          f"blocks handed to the general kernel {g(4) >> 32} of {nw // 4}, candidate tiles per block {g(5) / nw:.1f}")
     print(f"rep {rep}: batch {B}: {dt*1e3:.2f} ms, {B/dt:.1f} aligns/s, pair evals {pairs:.3e} ({pairs/B/ (2*120000):.0f} per query-pass avg over passes), err {synth.pose_error(Ts[0], Tgt)}")
     L.mrslam_gicp_stats_enable(0)
     _lib.prof_enable(True)
