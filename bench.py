@@ -559,15 +559,49 @@ def run_cfg2(args):
         # buffers for the next batch -- holding them across steps would make every other step allocate 64 fresh clouds
         return t_gicp, t_elev, fused, Ts, (sum(c[0] for c in counts), sum(c[1] for c in counts))
 
+    # device staging of the e2e elevation uploads (x, y, z SoA per frame) and the frames that point at it
+    stage_soa = [torch.empty_like(s_) for s_ in soa_dev]
+    stage_frames = [elevation.ElevationMap.make_frame(stage_soa[i][0], stage_soa[i][1], stage_soa[i][2], N_POINTS, *elev_args(i), near_filter=near_filter,
+                                                      position=pairs[i]["pose"][:3, 3].astype(np.float32)) for i in range(n_pairs)]
+    soa_pin_t = [torch.from_numpy(h) for h in soa_host]
+    copy_stream = torch.cuda.Stream(device=dev)
+
     def step_e2e():
-        """same step through the C-ABI with HOST buffers (pinned): H2D of every cloud, D2H of the results"""
+        """The same step with HOST inputs (pinned) through the public API: H2D of every cloud (GICP) and of every scan's x, y, z
+        (elevation), results (32 transforms, the fused count) back on the host.  The elevation scans go up on a copy stream
+        while the GICP clouds are packed, and are fused on the device by the replay entry point (ElevationMap::add-style: the
+        per-point outputs of Process_points never leave the GPU)."""
+        e0, e1 = ev(), ev()
+        C.record(e0)
+        with torch.cuda.stream(copy_stream):
+            for i in range(n_pairs):
+                stage_soa[i].copy_(soa_pin_t[i], non_blocking=True)
+            up = torch.cuda.Event()
+            up.record()
+        regs = new_regs()
+        for i, g in enumerate(regs):
+            g.set_input_source(src_host[i].numpy())
+        pygicp.prepare_batch(regs, pygicp.SOURCE)
+        for i, g in enumerate(regs):
+            g.set_input_target(tgt_host[i].numpy())
+        lib_stream.wait_event(up)
+        emap.process_fuse_device_batch(stage_frames, ELEV_RES, ELEV_L, asynchronous=True)
+        Ts = pygicp.align_batch(regs, guesses)  # reads back 32 x 4x4
+        fused = emap.fused_total(reset=True)
+        C.record(e1)
+        e1.synchronize()
+        return e0.elapsed_time(e1), fused, Ts
+
+    def step_e2e_compat():
+        """the reference-shaped calls with HOST buffers: per frame Move + Process_points (5 output arrays back to the host) +
+        Fuse (7 input arrays up again), as the elevation_mapping node drives libgpu.so"""
         e0, e1 = ev(), ev()
         C.record(e0)
         regs = new_regs()
         for i, g in enumerate(regs):
             g.set_input_source(src_host[i].numpy())
             g.set_input_target(tgt_host[i].numpy())
-        Ts = pygicp.align_batch(regs, guesses)  # reads back 32 x 4x4
+        Ts = pygicp.align_batch(regs, guesses)
         zeros_i, zeros_f = zeros_i_pin, zeros_f_pin
         fused = 0
         for i in range(n_pairs):
@@ -653,19 +687,32 @@ def run_cfg2(args):
     # accuracy of the last step against ground truth (sanity, not the parity gate)
     errs = [synth.pose_error(last_Ts[i], pairs[i]["T_gt"]) for i in range(n_pairs)]
 
-    # ---- timed region: end to end through the C-ABI with host buffers ----
+    # ---- timed region: end to end with host buffers ----
     for _ in range(2):
         step_e2e()
     C.barrier()
     te2e = 0.0
     for _ in range(args.steps):
-        t, _, _ = step_e2e()
+        t, fused_e2e, Ts_e2e = step_e2e()
         te2e += t
     C.barrier()
     te2e_ms = C.reduce(te2e, "max")
     e2e_value = aligns_total / (te2e_ms * 1e-3)
-    h2d = n_pairs * 2 * N_POINTS * 12 + n_pairs * (3 * N_POINTS * 4 + 7 * N_POINTS * 4)
-    d2h = n_pairs * 64 + n_pairs * 5 * N_POINTS * 4
+    e2e_same = bool(np.array_equal(np.asarray(Ts_e2e).view(np.uint32), last_Ts.view(np.uint32)))
+    h2d = n_pairs * 2 * N_POINTS * 12 + n_pairs * 3 * N_POINTS * 4
+    d2h = n_pairs * 64 + 8
+    # the reference-shaped (stateless Process_points / Fuse) host path, fewer repetitions
+    step_e2e_compat()
+    C.barrier()
+    tcomp = 0.0
+    NCOMP = max(2, args.steps // 3)
+    for _ in range(NCOMP):
+        t, _, _ = step_e2e_compat()
+        tcomp += t
+    C.barrier()
+    tcomp_ms = C.reduce(tcomp, "max") / NCOMP
+    h2d_c = n_pairs * 2 * N_POINTS * 12 + n_pairs * (3 * N_POINTS * 4 + 7 * N_POINTS * 4)
+    d2h_c = n_pairs * 64 + n_pairs * 5 * N_POINTS * 4
 
     # ---- CPU baseline (rank 0, bounded sample) ----
     cpu = None
@@ -745,7 +792,12 @@ def run_cfg2(args):
                           "cell_fuses_per_step": fused_all / args.steps / world, "ms_per_step": seq_e_ms / SEQ_STEPS,
                           "grid": "%dx%d @ %.2f m" % (ELEV_L, ELEV_L, ELEV_RES), "near_filter": near_filter},
             "e2e": {"value": e2e_value, "unit": "aligns/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": te2e_ms / args.steps},
+                    "ms_per_step": te2e_ms / args.steps, "transforms_bitwise_equal_device_path": e2e_same,
+                    "path": "host clouds -> set_input_* / align_batch; host scans -> device staging (copy stream) -> process_fuse_device_batch; "
+                            "32 transforms + fused count back",
+                    "compat": {"value": n_pairs * world / (tcomp_ms * 1e-3), "unit": "aligns/s", "ms_per_step": tcomp_ms,
+                               "h2d_bytes_per_step": h2d_c, "d2h_bytes_per_step": d2h_c,
+                               "path": "reference-shaped stateless calls per frame: Move + Process_points (5 arrays D2H) + Fuse (7 arrays H2D)"}},
             "parity": parity,
             "cpu_affinity": ("rank 0 bound to the %d cores NVML lists for its GPU" % len(C.cores)) if C.cores else "unbound",
             "gpu_launches": int(launches),

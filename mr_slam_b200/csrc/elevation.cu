@@ -107,20 +107,15 @@ __global__ void k_elev_clear_region(float* elevation, float* variance, float* in
   }
 }
 
-// G_pointsprocess.  Outputs -1 everywhere for dropped points.  keys[i] = map_index or `cells` (sorts last).
-__global__ void k_elev_process(const float* __restrict__ px, const float* __restrict__ py, const float* __restrict__ pz, int n,
-                               ProcParams P, ElevGeom g, float* __restrict__ lowest, int* __restrict__ map_index,
-                               float* __restrict__ var, float* __restrict__ x_ts, float* __restrict__ y_ts, float* __restrict__ z_ts,
-                               int* __restrict__ keys, int* __restrict__ vals) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const float x = px[i], y = py[i], z = pz[i];
+// G_pointsprocess for ONE point.  Outputs -1 everywhere for dropped points.
+__device__ __forceinline__ void elev_process_point(float x, float y, float z, const ProcParams& P, const ElevGeom& g, float* __restrict__ lowest,
+                                                   int& mi, float& hv, float& xt, float& yt, float& zt) {
   const float* T = P.T;
   const float height = fmaf(T[10], z, fmaf(T[9], y, T[8] * x)) + T[11];
   int flag = 0;
   if (P.near_filter && ((x > -1.5f && x < 1.5f && y > -1.5f && y < 1.5f) || (y > -1.0f && y < 1.0f) || y > 0.0f)) flag = 1;
-  int mi = -1;
-  float hv = -1.f, xt = -1.f, yt = -1.f, zt = -1.f;
+  mi = -1;
+  hv = -1.f; xt = -1.f; yt = -1.f; zt = -1.f;
   if (((double)height > P.lower && (double)height < P.upper) && flag == 0) {
     xt = fmaf(T[2], z, fmaf(T[1], y, T[0] * x)) + T[3];
     yt = fmaf(T[6], z, fmaf(T[5], y, T[4] * x)) + T[7];
@@ -158,6 +153,18 @@ __global__ void k_elev_process(const float* __restrict__ px, const float* __rest
       if (height == lowest[gi]) lowest[gi] = lowest[gi] + 3 * hv;
     }
   }
+}
+
+// keys[i] = map_index or `cells` (sorts last).
+__global__ void k_elev_process(const float* __restrict__ px, const float* __restrict__ py, const float* __restrict__ pz, int n,
+                               ProcParams P, ElevGeom g, float* __restrict__ lowest, int* __restrict__ map_index,
+                               float* __restrict__ var, float* __restrict__ x_ts, float* __restrict__ y_ts, float* __restrict__ z_ts,
+                               int* __restrict__ keys, int* __restrict__ vals) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int mi;
+  float hv, xt, yt, zt;
+  elev_process_point(px[i], py[i], pz[i], P, g, lowest, mi, hv, xt, yt, zt);
   if (map_index) map_index[i] = mi;
   if (var) var[i] = hv;
   if (x_ts) {
@@ -168,6 +175,66 @@ __global__ void k_elev_process(const float* __restrict__ px, const float* __rest
   if (keys) {
     keys[i] = (mi >= 0 && zt != -1.f) ? mi : g.L * g.L;
     vals[i] = i;
+  }
+}
+
+// ---- whole-batch replay (mrslam_elev_process_fuse_device_batch): every frame of a replay in ONE pass ----------------------
+// Frame f's geometry (after its Move) and sensor parameters live in a device table; all frames are processed by one launch
+// (blockIdx.y = frame) into concatenated per-point arrays.  vals = frame << 24 | point index; the stable sort by cell then
+// leaves every run in (frame, point) order -- the order in which the per-frame path applies its updates.
+struct BatchFrame {
+  const float *x, *y, *z;
+  int n, off;
+  ElevGeom g;
+  ProcParams P;
+};
+constexpr int ELEV_GROUP = 64;  // frames per group: one bit per frame in the clear masks
+
+__global__ void k_elev_process_batch(const BatchFrame* __restrict__ frames, int cells, float* __restrict__ lowest, float* __restrict__ ph,
+                                     float* __restrict__ pv, int* __restrict__ keys, int* __restrict__ vals) {
+  const int f = blockIdx.y;
+  const BatchFrame& F = frames[f];
+  const int n = F.n, off = F.off;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    int mi;
+    float hv, xt, yt, zt;
+    elev_process_point(F.x[i], F.y[i], F.z[i], F.P, F.g, lowest, mi, hv, xt, yt, zt);
+    ph[off + i] = zt;
+    pv[off + i] = hv;
+    keys[off + i] = (mi >= 0 && zt != -1.f) ? mi : cells;
+    vals[off + i] = (f << 24) | i;
+  }
+}
+
+struct BatchOffsets {
+  int off[ELEV_GROUP];
+};
+__global__ void k_elev_gather_batch(const int* __restrict__ order, int n, BatchOffsets bo, const float* __restrict__ ph,
+                                    const float* __restrict__ pv, float2* __restrict__ hv, unsigned char* __restrict__ fr) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const int v = order[j];
+  const int f = v >> 24, pi = bo.off[f] + (v & 0xffffff);
+  hv[j] = make_float2(ph[pi], pv[pi]);
+  fr[j] = (unsigned char)f;
+}
+
+// the strips every Move of the group clears, applied up front (a cell that is cleared at frame f keeps nothing of the frames
+// before f, so its earlier points are skipped by the run walk below instead)
+struct ClearTab {
+  int start, shift, row_flag;
+};
+__global__ void k_elev_clear_tab(float* elevation, float* variance, float* intensity, int* R, int* G, int* B, int L,
+                                 const ClearTab* __restrict__ tab) {
+  const ClearTab t = tab[blockIdx.y];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < L * t.shift; i += gridDim.x * blockDim.x) {
+    size_t c = t.row_flag ? (size_t)t.start * L + i : (size_t)(i / t.shift) * L + i % t.shift + t.start;
+    intensity[c] = 0;
+    elevation[c] = -10;
+    variance[c] = -10;
+    R[c] = 0;
+    G[c] = 0;
+    B[c] = 0;
   }
 }
 
@@ -289,6 +356,79 @@ __global__ void k_elev_fuse_segments(const int* __restrict__ keys, int n, int ce
   if (n_fused) atomicAdd(n_fused, (unsigned long long)(end - i));
 }
 
+// Run walk of a whole group of frames: the per-frame walk above plus, inside a run, (1) the clamp that ends every frame
+// (gpu_process.cu:531-532: variance < 1e-4 -> 1e-4) whenever the frame number changes and (2) the Moves: rowclr / colclr hold,
+// per storage row / column, one bit per frame whose Move cleared it (k_elev_clear_tab has already applied the clears), so a
+// run only applies the points of frames >= the last clear of its cell.  Result: exactly the state the per-frame sequence
+// Move, Process_points, Fuse leaves, with one sort and one walk for the whole group.
+__global__ void k_elev_fuse_runs_batch(const int* __restrict__ keys, int n, int cells, int L, const float2* __restrict__ hv,
+                                       const unsigned char* __restrict__ fr, const unsigned long long* __restrict__ rowclr,
+                                       const unsigned long long* __restrict__ colclr, float* __restrict__ elevation,
+                                       float* __restrict__ variance, unsigned long long* n_fused) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int c = keys[i];
+  if (c >= cells) return;
+  if (i > 0 && keys[i - 1] == c) return;  // not the head of a run
+  int lo = i, step = 1;
+  while (lo + step < n && keys[lo + step] == c) {
+    lo += step;
+    step <<= 1;
+  }
+  int hi = min(lo + step, n);
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (keys[mid] == c) lo = mid;
+    else hi = mid;
+  }
+  const int end = hi;
+  int first_frame = 0;
+  if (rowclr) {
+    const unsigned long long clr = rowclr[c / L] | colclr[c % L];
+    first_frame = clr ? 63 - __clzll((long long)clr) : 0;  // frames before the last clear of this cell leave no trace
+  }
+  float e = elevation[c], v = variance[c];
+  int prev_f = -1;
+  for (int j0 = i; j0 < end; j0 += 4) {
+    float2 m4[4];
+    int f4[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int j = min(j0 + u, end - 1);
+      m4[u] = hv[j];
+      f4[u] = fr[j];
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      if (j0 + u >= end) break;
+      const int f = f4[u];
+      if (f < first_frame) continue;
+      if (f != prev_f) {
+        if (prev_f >= 0 && v < 0.0001f) v = 0.0001f;  // end of frame prev_f
+        prev_f = f;
+      }
+      const float h = m4[u].x, hvv = m4[u].y;
+      if (e == -10.f) {
+        e = h;
+        v = hvv;
+      } else if (elev_mahal_gt5(h, e, v)) {
+        if (e < h) {
+          e = h;
+          v = hvv;
+        }
+      } else {
+        const float ne = fmaf(v, h, hvv * e) / (v + hvv);
+        const float nv = (hvv * v) / (hvv + v);
+        e = ne;
+        v = nv;
+      }
+    }
+  }
+  elevation[c] = e;
+  variance[c] = v;  // the clamp of the last frame follows as k_elev_clamp_var over the whole map
+  if (n_fused) atomicAdd(n_fused, (unsigned long long)(end - i));
+}
+
 // tail of G_fuse (gpu_process.cu:531-532): every cell, including empty ones
 __global__ void k_elev_clamp_var(float* __restrict__ variance, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -336,6 +476,15 @@ struct Elev {
   // f+1 (aux stream) with the run walk of frame f (library stream)
   DevBuf<int> keys2, keys_alt2, vals2, vals_alt2;
   DevBuf<float2> ghv2;
+  // one-pass replay of a group of frames: frame table, clear table, per-row / per-column clear masks (pinned staging + device)
+  DevBuf<BatchFrame> d_frames;
+  PinBuf<BatchFrame> h_frames;
+  DevBuf<ClearTab> d_ctab;
+  PinBuf<ClearTab> h_ctab;
+  DevBuf<unsigned long long> d_clr;
+  PinBuf<unsigned long long> h_clr;
+  DevBuf<unsigned char> gfr;
+  StageFence batch_fence;
   cudaStream_t aux = nullptr;
   cudaEvent_t ev_start = nullptr, ev_a[2] = {nullptr, nullptr}, ev_b[2] = {nullptr, nullptr};
   // asynchronous replay: the map-writing half runs on `bstream` instead of the library stream, so that an unrelated batch
@@ -376,6 +525,7 @@ struct Elev {
     gcol.release();
     feat.release();
     feat_i.release();
+    d_frames.release(); h_frames.release(); d_ctab.release(); h_ctab.release(); d_clr.release(); h_clr.release(); gfr.release();
     if (bstream) cudaStreamSynchronize(bstream);
     if (aux) cudaStreamDestroy(aux);
     if (bstream) cudaStreamDestroy(bstream);
@@ -384,6 +534,17 @@ struct Elev {
     aux = bstream = nullptr;
     ev_start = ev_a[0] = ev_a[1] = ev_b[0] = ev_b[1] = ev_done = nullptr;
     pending_join = false;
+  }
+  int reserve_batch(size_t total, int nframes) {
+    size_t t = std::max<size_t>(total, 1);
+    MR_CHECK(pzt.reserve(t)); MR_CHECK(pvar.reserve(t));
+    MR_CHECK(keys.reserve(t)); MR_CHECK(keys_alt.reserve(t)); MR_CHECK(vals.reserve(t)); MR_CHECK(vals_alt.reserve(t));
+    MR_CHECK(ghv.reserve(t)); MR_CHECK(gfr.reserve(t));
+    MR_CHECK(counter.reserve(2));
+    MR_CHECK(d_frames.reserve(nframes)); MR_CHECK(h_frames.reserve(nframes));
+    MR_CHECK(d_ctab.reserve(4 * nframes)); MR_CHECK(h_ctab.reserve(4 * nframes));
+    MR_CHECK(d_clr.reserve(2 * (size_t)g.L)); MR_CHECK(h_clr.reserve(2 * (size_t)g.L));
+    return MRSLAM_OK;
   }
   int ensure_pipeline(int n) {
     size_t m = std::max(n, 1);
@@ -526,8 +687,14 @@ int mrslam_elev_move(mrslam_elev_t* h, const float* pos, float resolution, int l
   return move_locked(m, pos, resolution, length, central_out, start_out, shift_out, rt().stream);
 }
 
-static int move_locked(Elev* m, const float* pos, float resolution, int length, float* central_out, int* start_out, float* shift_out,
-                       cudaStream_t st) {
+// Move (gpu_process.cu:1002-1081) as a host-side plan: the new geometry plus the strips (or everything) to clear.
+struct MovePlan {
+  bool clear_all = false;
+  int nstrips = 0;
+  int start[4], shift[4], row_flag[4];
+  float ashift[2];
+};
+static void plan_move(Elev* m, const float* pos, float resolution, int length, MovePlan& mp) {
   int ishift[2];
   float pshift[2];
   m->sensor_z = pos[2];
@@ -536,28 +703,14 @@ static int move_locked(Elev* m, const float* pos, float resolution, int length, 
   pshift[0] = pos[0] - hc[0];
   pshift[1] = pos[1] - hc[1];
   index_shift(ishift, pshift, resolution);
-  float ashift[2];
-  for (int i = 0; i < 2; i++) ashift[i] = (float)ishift[i] * resolution;
-  ClearRegions cr;
-  cr.count = 0;
-  int max_cnt = 0;
-  auto flush_clears = [&]() {
-    if (cr.count == 0) return;
-    k_elev_clear_region<<<dim3((max_cnt + 255) / 256, cr.count), 256, 0, st>>>(m->elevation.p, m->variance.p, m->intensity.p, m->R.p,
-                                                                                m->G.p, m->B.p, length, cr);
-    count_launch(1);
-    cr.count = 0;
-    max_cnt = 0;
-  };
+  for (int i = 0; i < 2; i++) mp.ashift[i] = (float)ishift[i] * resolution;
   // strips of one axis never overlap each other; a row strip and a column strip may, but both write the same constants
   auto clear = [&](int start, int ncell, int row) {
-    int cnt = ncell * length;
-    if (cnt <= 0) return;
-    cr.start[cr.count] = start;
-    cr.shift[cr.count] = ncell;
-    cr.row_flag[cr.count] = row;
-    cr.count++;
-    max_cnt = std::max(max_cnt, cnt);
+    if (ncell * length <= 0) return;
+    mp.start[mp.nstrips] = start;
+    mp.shift[mp.nstrips] = ncell;
+    mp.row_flag[mp.nstrips] = row;
+    mp.nstrips++;
   };
   for (int i = 0; i < 2; i++) {
     if (ishift[i] != 0) {
@@ -565,10 +718,7 @@ static int move_locked(Elev* m, const float* pos, float resolution, int length, 
       // reference tests only `ishift >= length`; a large negative shift then clears |ishift| > length strips and writes past
       // the end of its six planes -- undefined behaviour there, a clear-all here and in the oracle.)
       if (ishift[i] >= length || ishift[i] <= -length) {
-        int n = length * length;
-        k_elev_fill<<<(n + 127) / 128, 128, 0, st>>>(m->elevation.p, m->variance.p, m->intensity.p, m->lowest.p, m->traver.p, m->R.p,
-                                                    m->G.p, m->B.p, n, 1);
-        count_launch(1);
+        mp.clear_all = true;
       } else {
         int sign = ishift[i] > 0 ? 1 : -1;
         int startIndex = hs[i] - (sign > 0 ? 1 : 0);
@@ -587,15 +737,44 @@ static int move_locked(Elev* m, const float* pos, float resolution, int length, 
     }
     hs[i] -= ishift[i];
     hs[i] = index_to_range(hs[i], length);
-    hc[i] = position_to_range(hc[i], ashift[i], resolution);
+    hc[i] = position_to_range(hc[i], mp.ashift[i], resolution);
   }
-  flush_clears();
-  MR_CUDA(cudaGetLastError());
   m->g.cx = hc[0]; m->g.cy = hc[1];
   m->g.sx = hs[0]; m->g.sy = hs[1];
-  if (central_out) { central_out[0] = hc[0]; central_out[1] = hc[1]; }
-  if (start_out) { start_out[0] = hs[0]; start_out[1] = hs[1]; }
-  if (shift_out) { shift_out[0] = ashift[0]; shift_out[1] = ashift[1]; }
+}
+static int apply_move_clears(Elev* m, const MovePlan& mp, int length, cudaStream_t st) {
+  if (mp.clear_all) {
+    int n = length * length;
+    k_elev_fill<<<(n + 127) / 128, 128, 0, st>>>(m->elevation.p, m->variance.p, m->intensity.p, m->lowest.p, m->traver.p, m->R.p,
+                                                m->G.p, m->B.p, n, 1);
+    count_launch(1);
+  }
+  if (mp.nstrips > 0) {
+    ClearRegions cr;
+    cr.count = mp.nstrips;
+    int max_cnt = 0;
+    for (int k = 0; k < mp.nstrips; k++) {
+      cr.start[k] = mp.start[k];
+      cr.shift[k] = mp.shift[k];
+      cr.row_flag[k] = mp.row_flag[k];
+      max_cnt = std::max(max_cnt, mp.shift[k] * length);
+    }
+    k_elev_clear_region<<<dim3((max_cnt + 255) / 256, cr.count), 256, 0, st>>>(m->elevation.p, m->variance.p, m->intensity.p, m->R.p,
+                                                                                m->G.p, m->B.p, length, cr);
+    count_launch(1);
+  }
+  MR_CUDA(cudaGetLastError());
+  return MRSLAM_OK;
+}
+
+static int move_locked(Elev* m, const float* pos, float resolution, int length, float* central_out, int* start_out, float* shift_out,
+                       cudaStream_t st) {
+  MovePlan mp;
+  plan_move(m, pos, resolution, length, mp);
+  MR_CHECK(apply_move_clears(m, mp, length, st));
+  if (central_out) { central_out[0] = m->g.cx; central_out[1] = m->g.cy; }
+  if (start_out) { start_out[0] = m->g.sx; start_out[1] = m->g.sy; }
+  if (shift_out) { shift_out[0] = mp.ashift[0]; shift_out[1] = mp.ashift[1]; }
   return MRSLAM_OK;
 }
 
@@ -699,7 +878,7 @@ int mrslam_elev_process_fuse_device(mrslam_elev_t* h, const float* d_x, const fl
 // the per-frame sequence, with the map-independent half of frame f+1 (process, sort by cell, gather; aux stream) running
 // under the run walk of frame f (library stream).  `lowest` is only touched by the process kernels (aux stream, in frame
 // order); elevation / variance / colour only by clear, fuse and clamp (library stream, in frame order).
-static int elev_batch(mrslam_elev_t* h, const mrslam_elev_frame_t* frames, int nframes, float resolution, int length, bool async) {
+static int elev_batch_pipelined(mrslam_elev_t* h, const mrslam_elev_frame_t* frames, int nframes, float resolution, int length, bool async) {
   REQ(h);
   Elev* m = E(h);
   REQ_INIT(m);
@@ -772,6 +951,167 @@ static int elev_batch(mrslam_elev_t* h, const mrslam_elev_frame_t* frames, int n
     MR_CUDA(cudaEventRecord(m->ev_b[s], st));
   }
   MR_CUDA(cudaGetLastError());
+  if (async) {
+    MR_CUDA(cudaEventRecord(m->ev_done, st));
+    m->pending_join = true;
+  }
+  return MRSLAM_OK;
+}
+
+// The whole replay in one pass per group of <= 64 frames: host-side Move plans (geometry per frame, strips to clear, one bit per
+// frame in per-row / per-column clear masks) -> one clear launch, one process launch over all frames, ONE stable sort by cell of
+// all points (the concatenation is in (frame, point) order, so is every run afterwards), one gather, one run walk that applies the
+// frame-end clamps and skips what a later Move wiped, one clamp.  ~10 launches for a group instead of ~8 per frame, and the sort /
+// walk work on millions of keys instead of 120 k at a time.  Bit-identical to the per-frame sequence
+// (tests/test_elevation_gpu.py::test_pipelined_batch_equals_per_frame_sequence).
+static int elev_group_onepass(Elev* m, const mrslam_elev_frame_t* frames, int nframes, float resolution, int length, cudaStream_t st) {
+  const int L = m->g.L, cells = m->cells();
+  size_t total = 0;
+  int max_n = 0;
+  for (int f = 0; f < nframes; f++) {
+    total += (size_t)frames[f].n;
+    max_n = std::max(max_n, frames[f].n);
+  }
+  if (total >= (1ull << 31) || max_n >= (1 << 24)) {
+    set_error("process_fuse_device_batch: too many points in one group");
+    return MRSLAM_ERR_ARG;
+  }
+  MR_CHECK(m->batch_fence.wait());
+  MR_CHECK(m->reserve_batch(total, nframes));
+  unsigned long long* rowclr = m->h_clr.p;
+  unsigned long long* colclr = m->h_clr.p + L;
+  memset(m->h_clr.p, 0, sizeof(unsigned long long) * 2 * (size_t)L);
+  int nclear = 0, max_cnt = 0;
+  bool any_move = false;
+  BatchOffsets bo;
+  size_t off = 0;
+  for (int f = 0; f < nframes; f++) {
+    const mrslam_elev_frame_t& F = frames[f];
+    if (F.do_move) {
+      MovePlan mp;
+      plan_move(m, F.position, resolution, length, mp);
+      if (mp.clear_all) {  // cannot happen here: the caller splits groups at clear-all moves
+        set_error("internal: clear-all move inside a group");
+        return MRSLAM_ERR_STATE;
+      }
+      for (int k = 0; k < mp.nstrips; k++) {
+        m->h_ctab.p[nclear++] = ClearTab{mp.start[k], mp.shift[k], mp.row_flag[k]};
+        max_cnt = std::max(max_cnt, mp.shift[k] * L);
+        unsigned long long* msk = mp.row_flag[k] ? rowclr : colclr;
+        for (int r = 0; r < mp.shift[k]; r++) msk[mp.start[k] + r] |= 1ull << f;
+        any_move = true;
+      }
+    }
+    BatchFrame& B = m->h_frames.p[f];
+    B.x = F.d_x; B.y = F.d_y; B.z = F.d_z;
+    B.n = F.n;
+    B.off = (int)off;
+    B.g = m->g;
+    fill_proc(B.P, F.T16, F.lower, F.upper, F.min_r, F.beam_a, F.beam_c, F.sJ, F.rotVar, F.CSBT, F.PCBM, F.BrBS, F.near_filter);
+    bo.off[f] = (int)off;
+    off += (size_t)F.n;
+  }
+  for (int f = nframes; f < ELEV_GROUP; f++) bo.off[f] = 0;
+  MR_CUDA(cudaMemcpyAsync(m->d_frames.p, m->h_frames.p, sizeof(BatchFrame) * nframes, cudaMemcpyHostToDevice, st));
+  if (nclear) MR_CUDA(cudaMemcpyAsync(m->d_ctab.p, m->h_ctab.p, sizeof(ClearTab) * nclear, cudaMemcpyHostToDevice, st));
+  if (any_move) MR_CUDA(cudaMemcpyAsync(m->d_clr.p, m->h_clr.p, sizeof(unsigned long long) * 2 * (size_t)L, cudaMemcpyHostToDevice, st));
+  MR_CHECK(m->batch_fence.mark(st));
+  if (nclear) {
+    k_elev_clear_tab<<<dim3((max_cnt + 255) / 256, nclear), 256, 0, st>>>(m->elevation.p, m->variance.p, m->intensity.p, m->R.p, m->G.p,
+                                                                           m->B.p, L, m->d_ctab.p);
+    count_launch(1);
+  }
+  const int n = (int)total;
+  if (n > 0) {
+    {
+      ProfScope ps(PROF_ELEV_PROCESS);
+      // grid-stride over the points of a frame: enough blocks to fill the GPU whatever the number of frames
+      const int gx = std::max(1, std::min((max_n + 255) / 256, std::max(64, 4096 / nframes)));
+      k_elev_process_batch<<<dim3(gx, nframes), 256, 0, st>>>(m->d_frames.p, cells, m->lowest.p, m->pzt.p, m->pvar.p, m->keys.p, m->vals.p);
+      count_launch(1);
+    }
+    ProfScope ps(PROF_ELEV_FUSE);
+    int bits = 1;
+    while ((1ll << bits) <= cells) bits++;
+    cub::DoubleBuffer<int> dk(m->keys.p, m->keys_alt.p), dv(m->vals.p, m->vals_alt.p);
+    size_t tmp = 0;
+    MR_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp, dk, dv, n, 0, bits, st));
+    MR_CHECK(m->cubtmp.reserve(tmp));
+    MR_CUDA(cub::DeviceRadixSort::SortPairs(m->cubtmp.p, tmp, dk, dv, n, 0, bits, st));
+    k_elev_gather_batch<<<(n + 255) / 256, 256, 0, st>>>(dv.Current(), n, bo, m->pzt.p, m->pvar.p, m->ghv.p, m->gfr.p);
+    k_elev_fuse_runs_batch<<<(n + 127) / 128, 128, 0, st>>>(dk.Current(), n, cells, L, m->ghv.p, m->gfr.p, any_move ? m->d_clr.p : nullptr,
+                                                           any_move ? m->d_clr.p + L : nullptr, m->elevation.p, m->variance.p,
+                                                           m->counter.p + 1);
+    count_launch(2);
+  }
+  {
+    ProfScope ps(PROF_ELEV_FUSE);
+    k_elev_clamp_var<<<((cells + 3) / 4 + 255) / 256, 256, 0, st>>>(m->variance.p, cells);
+    count_launch(1);
+  }
+  MR_CUDA(cudaGetLastError());
+  return MRSLAM_OK;
+}
+
+static int elev_batch(mrslam_elev_t* h, const mrslam_elev_frame_t* frames, int nframes, float resolution, int length, bool async) {
+  if (getenv("MRSLAM_ELEV_PIPELINED")) return elev_batch_pipelined(h, frames, nframes, resolution, length, async);  // round-1 path (A/B)
+  REQ(h);
+  Elev* m = E(h);
+  REQ_INIT(m);
+  if (nframes < 0 || (nframes > 0 && !frames)) {
+    set_error("process_fuse_device_batch: bad arguments");
+    return MRSLAM_ERR_ARG;
+  }
+  std::lock_guard<std::mutex> lk2(m->mu);
+  std::lock_guard<std::mutex> lk(rt().mu);
+  MR_CHECK(m->join());
+  if (nframes == 0) return MRSLAM_OK;
+  for (int f = 0; f < nframes; f++)
+    if (frames[f].n < 0 || (frames[f].n > 0 && (!frames[f].d_x || !frames[f].d_y || !frames[f].d_z))) {
+      set_error("process_fuse_device_batch: bad frame %d", f);
+      return MRSLAM_ERR_ARG;
+    }
+  MR_CHECK(m->ensure_pipeline(1));
+  MR_CHECK(m->counter.reserve(2));
+  cudaStream_t st = async ? m->bstream : rt().stream;
+  if (async) {
+    MR_CUDA(cudaEventRecord(m->ev_start, rt().stream));  // inputs and the map state are ordered on the library stream
+    MR_CUDA(cudaStreamWaitEvent(st, m->ev_start, 0));
+  }
+  // groups of <= ELEV_GROUP frames; a Move that jumps by a whole map length (clear-all) starts a new group after its fill
+  int f0 = 0;
+  while (f0 < nframes) {
+    int f1 = f0;
+    // dry-run the Moves on the geometry (restored afterwards) to find the end of the group: a clear-all move ends it
+    const ElevGeom g0 = m->g;
+    const float sz0 = m->sensor_z;
+    bool first_is_clear_all = false;
+    while (f1 < nframes && f1 - f0 < ELEV_GROUP) {
+      if (frames[f1].do_move) {
+        MovePlan mp;
+        plan_move(m, frames[f1].position, resolution, length, mp);
+        if (mp.clear_all) {
+          first_is_clear_all = f1 == f0;
+          break;
+        }
+      }
+      f1++;
+    }
+    m->g = g0;
+    m->sensor_z = sz0;
+    if (first_is_clear_all) {
+      MovePlan real;
+      plan_move(m, frames[f0].position, resolution, length, real);
+      MR_CHECK(apply_move_clears(m, real, length, st));
+      mrslam_elev_frame_t F = frames[f0];  // the frame itself is replayed without its (already applied) move
+      F.do_move = 0;
+      MR_CHECK(elev_group_onepass(m, &F, 1, resolution, length, st));
+      f0++;
+      continue;
+    }
+    MR_CHECK(elev_group_onepass(m, frames + f0, f1 - f0, resolution, length, st));
+    f0 = f1;
+  }
   if (async) {
     MR_CUDA(cudaEventRecord(m->ev_done, st));
     m->pending_join = true;

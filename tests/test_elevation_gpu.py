@@ -194,6 +194,53 @@ def test_pipelined_batch_equals_per_frame_sequence(gpu):
     assert np.array_equal(a.get_map()["elevation"], c.get_map()["elevation"])
 
 
+@pytest.mark.parametrize("L,res,nframes,rows", [(60, 0.2, 70, None), (201, 0.15, 9, None), (120, 0.25, 12, (30, 95))])
+def test_onepass_replay_with_moves_equals_per_frame_sequence(gpu, L, res, nframes, rows):
+    """One-pass replay of a whole group of frames (one sort + one run walk with in-run frame-end clamps and Move clear masks) ==
+    the per-frame sequence Move, process_fuse_device -- with Moves that wipe cells holding points of earlier frames of the same
+    batch, a jump of more than a map length in the middle (clear-all), more than 64 frames (two groups), frames without a Move,
+    an empty frame, and (third case) a map restricted to a block of storage rows.  Elevation, variance and the count bit for bit."""
+    import torch
+    a = elevation.ElevationMap()
+    a.Init_GPU_elevationmap(L, res, 2.5, 0.2)
+    b = elevation.ElevationMap()
+    b.Init_GPU_elevationmap(L, res, 2.5, 0.2)
+    if rows:
+        a.set_owned_rows(*rows)
+        b.set_owned_rows(*rows)
+    rng = np.random.default_rng(11)
+    frames, keep, total = [], [], 0
+    base = [frame(f, "vlp16") for f in range(4)]
+    pos = np.zeros(3, np.float32)
+    for f in range(nframes):
+        pose, x, y, z, args = base[f % 4]
+        n = len(x) if f % 7 != 5 else 0
+        # a random walk of a few cells per frame (wraps the ring buffer several times), one long jump, some frames without a Move
+        step = rng.integers(-6, 7, 2) * res
+        if f == nframes // 2:
+            step = np.array([-(L + 5) * res, 0.0])
+        pos = (pos + np.array([step[0], step[1], 0.0])).astype(np.float32)
+        T = np.array(args[0], np.float32).copy()
+        T[0, 3], T[1, 3] = pos[0] + 0.3, pos[1] - 0.2           # the scan moves with the robot
+        args_f = (T,) + tuple(args[1:])
+        do_move = f % 5 != 4
+        d = [torch.from_numpy(t).cuda() for t in (x, y, z)]
+        keep.append(d)
+        if do_move:
+            a.Move(pos, res, L)
+        total += a.process_fuse_device(d[0], d[1], d[2], n, *args_f, near_filter=(f % 3 != 0))
+        frames.append(elevation.ElevationMap.make_frame(d[0], d[1], d[2], n, *args_f, near_filter=(f % 3 != 0), position=pos if do_move else None))
+    torch.cuda.synchronize()
+    b.fused_total(reset=True)
+    b.process_fuse_device_batch(frames, res, L)
+    assert b.fused_total(reset=True) == total and total > 0
+    ma, mb = a.get_map(), b.get_map()
+    for key in ("elevation", "variance", "intensity", "R"):
+        assert np.array_equal(ma[key], mb[key]), key
+    assert all(np.array_equal(u, v) for u, v in zip(a.state(), b.state()))
+    assert (ma["elevation"] != -10).sum() > 50
+
+
 def test_empty_and_invalid_inputs(gpu):
     g = elevation.ElevationMap()
     with pytest.raises(Exception):
