@@ -31,7 +31,7 @@ void launch_mapfeature(const float* elevation, const float* variance, const floa
                        float* traver_map, int L, float res, int sx, int sy, float* o_elev, float* o_var, int* o_R, int* o_G, int* o_B,
                        float* o_rough, float* o_slope, float* o_traver, float* o_int, cudaStream_t st);
 void launch_raytracing(float* elevation, const float* variance, const float* traver, float* lowest, int L, int sx, int sy, float sensor_z,
-                       float obstacle_thr, cudaStream_t st);
+                       float obstacle_thr, int* list, int* count, cudaStream_t st);
 
 struct ElevGeom {
   int L;
@@ -1273,8 +1273,9 @@ int mrslam_elev_raytracing(mrslam_elev_t* h, int length) {
   std::lock_guard<std::mutex> lk2(m->mu);
   std::lock_guard<std::mutex> lk(rt().mu);
   MR_CHECK(m->join());
+  MR_CHECK(m->feat_i.reserve((size_t)m->cells() + 4));  // obstacle list + its counter (the Map_feature int staging is free here)
   launch_raytracing(m->elevation.p, m->variance.p, m->traver.p, m->lowest.p, m->g.L, m->g.sx, m->g.sy, m->sensor_z, m->obstacle_thr,
-                    rt().stream);
+                    m->feat_i.p, m->feat_i.p + m->cells(), rt().stream);
   MR_CUDA(cudaGetLastError());
   MR_CUDA(cudaStreamSynchronize(rt().stream));  // the reference synchronises here as well
   return MRSLAM_OK;

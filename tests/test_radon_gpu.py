@@ -78,6 +78,48 @@ def test_radon_vs_reference_kernel(gpu):
     assert e_emu < 2e-3 and e_exact < 5e-3
 
 
+def test_radon_mode_gap_on_the_matcher(gpu):
+    """What the Radon-mode difference means for the MATCHER (VERDICT r1 task 10): 256 scan pairs, sinograms from (i) the
+    reference's own hardware-texture kernel (libradon_ref.so, forward.cu unmodified) and (ii) the product default
+    (texture-weight emulation + fast trig) and (iii) exact bilinear; TIRING + fast_corr of scan j against scan 0 in each mode.
+    Reported: max |delta dist| and the number of yaw (angle) flips; asserted: the product default never flips the matched
+    angle where the correlation peak is unambiguous and moves `dist` by < 2e-3 (the loop threshold is 0.3-0.5 wide)."""
+    from oracle import ref
+    from mr_slam_b200 import synth
+    if not ref.available("radon"):
+        pytest.skip("oracle/_ref not present")
+    n_base, reps = 16, 16
+    base = [synth.make_scan(synth.pose_matrix(3.0 * np.cos(0.7 * i), 2.0 * np.sin(1.3 * i), 0.0, 0.2 * i), "vlp16", scan_id=300 + i) +
+            np.array([0, 0, 1.8], np.float32) for i in range(n_base)]
+    scans = []
+    for j in range(n_base * reps):
+        b = base[j % n_base]
+        yaw = 2 * np.pi * (j // n_base) / reps + 0.013 * j
+        c, s = np.float32(np.cos(yaw)), np.float32(np.sin(yaw))
+        scans.append(np.stack([c * b[:, 0] - s * b[:, 1], s * b[:, 0] + c * b[:, 1], b[:, 2]], 1).astype(np.float32))
+    bev = ring.scans_to_bev_device(torch.from_numpy(np.stack(scans)).cuda())
+    bev_h = bev.cpu().numpy()
+    sino_ref = ref.radon_forward(bev_h, ANG, 120, 1.0)                                            # (i) reference kernel on this GPU
+    sino_emu = ParallelBeam(120, ANG, interp="texture", fast_trig=True).forward(bev).cpu().numpy()   # (ii) product default
+    sino_ex = ParallelBeam(120, ANG, interp="exact", fast_trig=False).forward(bev).cpu().numpy()     # (iii) exact bilinear
+    res = {}
+    for name, sino in (("ref", sino_ref), ("default", sino_emu), ("exact", sino_ex)):
+        tir = ring.tiring(torch.from_numpy(np.ascontiguousarray(sino[:, None])).cuda())
+        d, a, corr = ring.fast_corr_batch(tir[0], tir, want_corr=True)
+        res[name] = (d.cpu().numpy(), a.cpu().numpy(), corr.cpu().numpy())
+    d0, a0, c0 = res["ref"]
+    top2 = np.sort(c0, axis=1)[:, -2:]
+    clear = (top2[:, 1] - top2[:, 0]) > 1e-3 * top2[:, 1]            # pairs whose correlation peak is not a near-tie
+    out = {}
+    for name in ("default", "exact"):
+        d, a, _ = res[name]
+        out[name] = (float(np.abs(d - d0).max()), int((a != a0).sum()), int(((a != a0) & clear).sum()))
+    print("matcher gap vs the reference Radon kernel over %d pairs: default max|ddist| %.2e, angle flips %d (%d on unambiguous peaks); "
+          "exact-bilinear max|ddist| %.2e, angle flips %d (%d unambiguous)" % ((len(scans),) + out["default"] + out["exact"]))
+    assert out["default"][0] < 2e-3 and out["default"][2] == 0
+    assert out["exact"][0] < 5e-3
+
+
 def test_tiring_and_fast_corr_vs_reference_python(gpu):
     z = np.load(os.path.join(GOLDEN, "ring_fixture.npz"))
     tir = ring.tiring(torch.from_numpy(z["sino"]).cuda())
