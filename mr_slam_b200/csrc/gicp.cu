@@ -28,7 +28,7 @@ struct Cloud {
   DevBuf<unsigned long long> skeys;
   DevBuf<double> cov;
   DevBuf<int> knn_ids;  // [npad*k] neighbour lists (scratch between k_knn_search and k_cov)
-  DevBuf<unsigned char> knn_fb;  // [ceil(ntiles/4)] blocks k_knn_search_v2 hands back to k_knn_search
+  DevBuf<unsigned char> knn_fb;  // [ntiles] tiles k_knn_search_v2 hands back to k_knn_search
   bool cov_valid = false;
   bool built = false;   // spatial structures (psort / tb / sb) are produced lazily, batched with the other clouds of a call
   DevBuf<float> raw;    // staging of host input
@@ -207,11 +207,12 @@ static int dispatch_knn(int k, const KnnParams* d_params, int nproblems, int max
   dim3 grid((max_tiles + 3) / 4, nproblems);
   {
     ProfScope ps(PROF_KNN_SEARCH);
-    const bool v2 = k < KP && !getenv("MRSLAM_KNN_V1");
+    const bool v2 = k < KP && getenv("MRSLAM_KNN_V2");  // opt-in until the round-2 GPU comparison is in (gpurun_out/r2f)
     if (v2) {
       // k <= 15: staged lane-per-query-list kernel; the (rare) blocks it flags are redone by the general kernel
-      if (scratch_stats_enabled()) k_knn_search_v2<true><<<grid, 128, 0, rt().stream>>>(d_params);
-      else k_knn_search_v2<false><<<grid, 128, 0, rt().stream>>>(d_params);
+      const dim3 grid2(max_tiles, nproblems);  // one warp per query tile
+      if (scratch_stats_enabled()) k_knn_search_v2<true><<<grid2, 32, 0, rt().stream>>>(d_params);
+      else k_knn_search_v2<false><<<grid2, 32, 0, rt().stream>>>(d_params);
       count_launch(1);
     }
     if (scratch_stats_enabled()) k_knn_search<true><<<grid, 128, 0, rt().stream>>>(d_params, v2 ? 1 : 0);
@@ -488,7 +489,7 @@ static int compute_covariances(Gicp** hs, int n, int which = 3) {
     Cloud* c = todo[order[i]];
     MR_CHECK(c->cov.reserve((size_t)std::max(c->npad, 1) * 6));
     MR_CHECK(c->knn_ids.reserve((size_t)std::max(c->npad, 1) * ks[order[i]]));
-    MR_CHECK(c->knn_fb.reserve((size_t)c->ntiles / 4 + 2));
+    MR_CHECK(c->knn_fb.reserve((size_t)c->ntiles + 4));
     KnnParams p;
     p.fb = c->knn_fb.p;
     p.n = c->n; p.ids = c->knn_ids.p;
@@ -930,7 +931,7 @@ int mrslam_cloud_knn(mrslam_cloud_t* h, int k, int* idx_out, float* sqd_out) {
     return MRSLAM_ERR_ARG;
   }
   MR_CHECK(c->knn_ids.reserve((size_t)std::max(c->npad, 1) * k));
-  MR_CHECK(c->knn_fb.reserve((size_t)c->ntiles / 4 + 2));
+  MR_CHECK(c->knn_fb.reserve((size_t)c->ntiles + 4));
   KnnParams p;
   p.fb = c->knn_fb.p;
   p.n = c->n; p.ids = c->knn_ids.p;
@@ -979,7 +980,7 @@ int mrslam_ringpp_build_neighbors(const float* xyz, int n, int stride_floats, in
     MR_CHECK(di.reserve((size_t)n * k));
     MR_CHECK(dout.reserve((size_t)n * 15));
     MR_CHECK(c->knn_ids.reserve((size_t)std::max(c->npad, 1) * k));
-    MR_CHECK(c->knn_fb.reserve((size_t)c->ntiles / 4 + 2));
+    MR_CHECK(c->knn_fb.reserve((size_t)c->ntiles + 4));
     KnnParams p;
     p.fb = c->knn_fb.p;
     p.n = c->n; p.ids = c->knn_ids.p;

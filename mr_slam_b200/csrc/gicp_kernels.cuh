@@ -434,7 +434,7 @@ struct KnnParams {
   int* knn_idx;     // optional test hook, original order [n*k]
   float* knn_sqd;   // optional
   unsigned long long* stat_pairs;  // optional: number of (query,candidate) distance evaluations
-  unsigned char* fb;  // [ceil(ntiles/4)] per-block flag written by k_knn_search_v2: 1 = this block must be redone by k_knn_search
+  unsigned char* fb;  // [ntiles] per-tile flag written by k_knn_search_v2: 1 = this tile must be redone by k_knn_search
 };
 
 constexpr int SGROUP = MR_SGROUP;  // super-tile box tests kept in flight together (SGROUP x 32 boxes)
@@ -580,10 +580,12 @@ template <bool STATS>
 __global__ void __launch_bounds__(128, 8) k_knn_search(const KnnParams* __restrict__ plist, int only_flagged) {
   __shared__ int s_list[4][KCAND];
   const KnnParams P = plist[blockIdx.y];
-  if (only_flagged && (blockIdx.x * 4 >= P.ntiles || !P.fb[blockIdx.x])) return;  // second pass behind k_knn_search_v2
+  // second pass behind k_knn_search_v2: only the tiles it flagged (one flag per tile; warp-uniform exit further down)
+  if (only_flagged && blockIdx.x * 4 >= P.ntiles) return;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int qt = blockIdx.x * 4 + wib;
   if (qt >= P.ntiles) return;  // warp-uniform; no block-level barrier in this kernel
+  if (only_flagged && !P.fb[qt]) return;
   const float4 qmine = P.psort[(size_t)qt * TILE + lane];
   const int k = P.k;
   unsigned long long tiles_done = 0, inserts = 0;
@@ -708,19 +710,26 @@ __global__ void __launch_bounds__(128, 8) k_knn_search(const KnnParams* __restri
 //   * distance evaluation is cheapest WARP-PER-QUERY (one candidate point per lane), but a visit does not have to touch the
 //     list: qualifiers (key < the query's current k-th key) are ballot-compacted into a per-query buffer in shared memory as
 //     16-bit (staged tile, lane) ids, at a cost that does not depend on how many there are.
-// One block = four consecutive query tiles (128 queries).  Their candidate tiles -- every tile whose box is within
-// R = max over the block's queries of the own-tile k-th distance of the block's bounding box -- are found ONCE per block and
-// staged in shared memory 32 tiles at a time by 1-D bulk-async copies (cp.async.bulk, completion on an mbarrier), while the
-// lanes compute which staged tiles their own query needs (point-to-box test against the query's own k-th distance).
+// The candidate tiles of a query tile -- every tile whose box is within R = max over its queries of the own-tile k-th distance
+// of the tile's box -- are found once per warp and staged in shared memory 32 tiles at a time by 1-D bulk-async copies
+// (cp.async.bulk, completion on an mbarrier), while the lanes compute which staged tiles their own query needs
+// (point-to-box test against the query's own k-th distance).
 // Exactness: a tile is skipped for a query only if its box is provably farther than the query's current k-th key, and a
 // candidate is dropped only if its key is not below that key, so the final list is the exact kNN under (distance, index).
-// Blocks with more than V2_MAXC candidate tiles are flagged in P.fb and redone by k_knn_search.
+// Tiles with more than V2_MAXC candidate tiles are flagged in P.fb and redone by k_knn_search.
 // ---------------------------------------------------------------------------------------------
 constexpr int KP = 16;
-constexpr int V2_CH = 32;
-constexpr int V2_MAXC = 256;
-constexpr int V2_CAP = 64;
-constexpr int V2_BSTRIDE = V2_CAP + 2;  // 66 u16 = 33 words per row: lane q reading row q is bank-conflict free
+#ifndef MR_V2_CH
+#define MR_V2_CH 24
+#endif
+#ifndef MR_V2_CAP
+#define MR_V2_CAP 32
+#endif
+constexpr int V2_CH = MR_V2_CH;    // candidate tiles staged at a time (<= 32: one bit each in a lane's need mask); 24 tiles = 12 KB
+constexpr int V2_MAXC = 128;       // candidate tiles a query tile may have; more -> k_knn_search redoes the tile
+constexpr int V2_CAP = MR_V2_CAP;  // buffered qualifiers per query between merges (a visit adds at most 32)
+constexpr int V2_BSTRIDE = V2_CAP + 2;  // u16 per row, an ODD number of 32-bit words: lane q reading row q is bank-conflict free
+static_assert(V2_CH <= 32 && V2_CAP >= 32 && (V2_BSTRIDE / 2) % 2 == 1 && V2_BSTRIDE * 2 >= 15 * 4, "kNN v2 shared-memory layout");
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
@@ -785,50 +794,54 @@ __device__ __forceinline__ void key_merge16(u64 (&L)[KP], const u64 (&B)[KP]) {
       if ((i & kk) == 0) key_ce(L[i], L[i | kk]);
 }
 
+// One warp = one block = one query tile (32 queries); nothing is shared between warps, so there is no block-level barrier.
+// Steps: (1) own tile -> shared; every lane sorts its own 32 distances into its register list (two batches of 16);
+// (2) the warp collects the candidate tiles: boxes within R_w = largest own-tile k-th distance of its queries of the tile's box;
+// (3) per chunk of <= V2_CH candidates: the tiles are staged by 1-D bulk-async copies while every lane computes which of
+// them ITS query needs (point-to-box test against its own k-th distance) and which of those is nearest;
+// (4) phase 1: warp-per-query scan of only the NEAREST needed tile of every query, then one lane-per-query merge -- the k-th
+// distances are now close to final -- (5) phase 2: the need masks are recomputed with the tight distances, the remaining
+// tiles are scanned and merged.  The first version of this kernel (one scan with the loose own-tile distance; round-2 profile
+// r2c) buffered 19.6 qualifiers per query and, because a merge costs what the FULLEST buffer of the warp needs, spent 57 % of
+// its 751 warp-instructions per query in merge rounds; the two-phase order cuts qualifiers and rounds.
 template <bool STATS>
-__global__ void __launch_bounds__(128, 4) k_knn_search_v2(const KnnParams* __restrict__ plist) {
+__global__ void __launch_bounds__(32) k_knn_search_v2(const KnnParams* __restrict__ plist) {
   __shared__ __align__(128) float4 s_stage[V2_CH * TILE];  // candidate tiles of the current chunk (bulk-copy destination)
-  __shared__ __align__(16) float4 s_q[4][TILE];            // the block's own four tiles
-  __shared__ __align__(16) float4 s_box[V2_MAXC][2];       // candidate boxes (min xyz, max xyz)
+  __shared__ __align__(16) float4 s_q[TILE];               // own tile
+  __shared__ __align__(16) float4 s_box[V2_CH][2];         // boxes of the staged tiles (min xyz, max xyz)
   __shared__ int s_cand[V2_MAXC];                          // candidate tile ids
-  __shared__ __align__(16) unsigned short s_buf[4][TILE][V2_BSTRIDE];  // per query: buffered qualifiers (staged slot * 32 + lane)
+  __shared__ __align__(16) unsigned short s_buf[TILE][V2_BSTRIDE];  // per query: buffered qualifiers (staged slot * 32 + lane)
   __shared__ __align__(8) unsigned long long s_mbar;
-  __shared__ float s_wbox[4][6];
-  __shared__ float s_wR[4];
-  __shared__ int s_ncand;
 
   const KnnParams P = plist[blockIdx.y];
-  const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
-  const int qt0 = blockIdx.x * 4;
-  if (qt0 >= P.ntiles) return;  // block-uniform
-  const int qt = qt0 + wib;
-  const bool wvalid = qt < P.ntiles;
+  const int lane = threadIdx.x;
+  const int qt = blockIdx.x;
+  if (qt >= P.ntiles) return;
   const int k = P.k, ntp = P.ntiles_pad, nsp = P.nsuper_pad;
   const unsigned lt = (1u << lane) - 1u;
-  if (tid == 0) {
+  if (lane == 0) {
     mbar_init(&s_mbar, 1);
-    s_ncand = 0;
     fence_mbar_init();
   }
-  // ---- own tile -> shared; lane-per-query initial list from its 32 points (two batches of 16) ----
-  const float4 qmine = wvalid ? P.psort[(size_t)qt * TILE + lane] : make_float4(PAD_COORD, PAD_COORD, PAD_COORD, __int_as_float(PAD_IDX));
-  s_q[wib][lane] = qmine;
+  // ---- (1) own tile -> shared; lane-per-query initial list from its 32 points ----
+  const float4 qmine = P.psort[(size_t)qt * TILE + lane];
+  s_q[lane] = qmine;
   __syncwarp();
   const float qx = qmine.x, qy = qmine.y, qz = qmine.z;
   const int qidx = __float_as_int(qmine.w);
-  const bool qvalid = wvalid && qidx != PAD_IDX;
+  const bool qvalid = qidx != PAD_IDX;
   // The list always holds 16 keys: KP - k minimal sentinels (key 0) in front, so that the k-th best is L[KP-1] whatever k is
   // and every index into L stays a compile-time constant.  (A real key 0 -- point 0 at distance 0 -- is identical to a
   // sentinel, so it does not matter which of the two copies ends up in front.)
   u64 L[KP];
 #pragma unroll
   for (int i = 0; i < KP; i++) L[i] = (i < KP - k) ? 0ull : KEY_NONE;
-#pragma unroll
+#pragma unroll 1
   for (int h = 0; h < 2; h++) {
     u64 Bt[KP];
 #pragma unroll
     for (int j = 0; j < KP; j++) {
-      const float4 c = s_q[wib][h * KP + j];
+      const float4 c = s_q[h * KP + j];
       Bt[j] = make_key(dist2(qx, qy, qz, c.x, c.y, c.z), __float_as_int(c.w));
     }
     key_sort16(Bt);
@@ -837,166 +850,184 @@ __global__ void __launch_bounds__(128, 4) k_knn_search_v2(const KnnParams* __res
   float tau_d = key_dist(L[KP - 1]);
   unsigned long long st_visits = 0, st_quals = 0, st_rounds = 0, st_oflow = 0;
 
-  // ---- block-wide candidate tiles: box within R of the block's box, R = largest own-tile k-th distance of the block ----
+  // ---- (2) candidate tiles of this warp ----
+  int ncand = 0;
   {
     const float Rw = warp_max(qvalid ? tau_d : 0.0f);
-    if (lane == 0) s_wR[wib] = Rw;
-    if (lane < 6) s_wbox[wib][lane] = wvalid ? P.tb[(size_t)lane * ntp + qt] : (lane < 3 ? FLT_MAX : -FLT_MAX);
-  }
-  __syncthreads();
-  float a[6], Rblk;
-  {
+    float a[6];
 #pragma unroll
-    for (int c = 0; c < 3; c++) {
-      a[c] = fminf(fminf(s_wbox[0][c], s_wbox[1][c]), fminf(s_wbox[2][c], s_wbox[3][c]));
-      a[3 + c] = fmaxf(fmaxf(s_wbox[0][3 + c], s_wbox[1][3 + c]), fmaxf(s_wbox[2][3 + c], s_wbox[3][3 + c]));
-    }
-    Rblk = fmaxf(fmaxf(s_wR[0], s_wR[1]), fmaxf(s_wR[2], s_wR[3]));
-  }
+    for (int c = 0; c < 6; c++) a[c] = P.tb[(size_t)c * ntp + qt];
 #pragma unroll 1
-  for (int s0 = wib * 32; s0 < P.nsuper; s0 += 128) {
-    const int sidx = s0 + lane;
-    const float bs = (sidx < P.nsuper) ? box_box_dist2(a, P.sb, nsp, sidx) : INFINITY;
-    unsigned ms = __ballot_sync(FULL, bs * CULL_SAFETY <= Rblk);
-    while (ms) {
-      const int js = __ffs(ms) - 1;
-      ms &= ms - 1;
-      const int t = (s0 + js) * 32 + lane;
-      float b6[6];
-#pragma unroll
-      for (int c = 0; c < 6; c++) b6[c] = P.tb[(size_t)c * ntp + t];  // t < ntiles_pad always
-      const float gx = fmaxf(0.0f, fmaxf(b6[0] - a[3], a[0] - b6[3])), gy = fmaxf(0.0f, fmaxf(b6[1] - a[4], a[1] - b6[4])),
-                  gz = fmaxf(0.0f, fmaxf(b6[2] - a[5], a[2] - b6[5]));
-      const bool pass = t < P.ntiles && (gx * gx + gy * gy + gz * gz) * CULL_SAFETY <= Rblk;
-      const unsigned mt = __ballot_sync(FULL, pass);
-      if (mt) {
-        int base = 0;
-        if (lane == 0) base = atomicAdd(&s_ncand, __popc(mt));
-        base = __shfl_sync(FULL, base, 0);
-        const int pos = base + __popc(mt & lt);
-        if (pass && pos < V2_MAXC) {
-          s_cand[pos] = t;
-          s_box[pos][0] = make_float4(b6[0], b6[1], b6[2], 0.0f);
-          s_box[pos][1] = make_float4(b6[3], b6[4], b6[5], 0.0f);
-        }
+    for (int s0 = 0; s0 < P.nsuper; s0 += 32) {
+      const int sidx = s0 + lane;
+      const float bs = (sidx < P.nsuper) ? box_box_dist2(a, P.sb, nsp, sidx) : INFINITY;
+      unsigned ms = __ballot_sync(FULL, bs * CULL_SAFETY <= Rw);
+      while (ms) {
+        const int js = __ffs(ms) - 1;
+        ms &= ms - 1;
+        const int t = (s0 + js) * 32 + lane;
+        const bool pass = t < P.ntiles && t != qt && box_box_dist2(a, P.tb, ntp, t) * CULL_SAFETY <= Rw;
+        const unsigned mt = __ballot_sync(FULL, pass);
+        const int pos = ncand + __popc(mt & lt);
+        if (pass && pos < V2_MAXC) s_cand[pos] = t;
+        ncand += __popc(mt);
       }
     }
   }
-  __syncthreads();
-  const int ncand = s_ncand;
-  if (ncand > V2_MAXC) {  // block-uniform: too many candidates for the staged scheme (huge R: sparse outliers, n < k)
-    if (tid == 0) {
-      P.fb[blockIdx.x] = 1;
-      if (STATS && P.stat_pairs) atomicAdd(P.stat_pairs + 4, 1ull << 32);  // high word: blocks handed to k_knn_search
+  if (ncand > V2_MAXC) {  // warp-uniform: too many candidates for the staged scheme (huge R: sparse outliers, n < k)
+    if (lane == 0) {
+      P.fb[qt] = 1;
+      if (STATS && P.stat_pairs) atomicAdd(P.stat_pairs + 4, 1ull << 32);  // high word: tiles handed to k_knn_search
     }
     return;
   }
-  if (tid == 0) P.fb[blockIdx.x] = 0;
+  if (lane == 0) P.fb[qt] = 0;
+  __syncwarp();
 
-  // ---- chunks of V2_CH staged tiles: warp-per-query scan into the buffers, lane-per-query merge into the lists ----
+  // lane-per-query merge of the buffered qualifiers, 16 per round (the staged tiles are resident)
   int cnt = 0;  // buffered qualifiers of MY query
+  auto merge_buffers = [&]() {
+    const int rounds = (__reduce_max_sync(FULL, cnt) + KP - 1) / KP;
+#pragma unroll 1
+    for (int r = 0; r < rounds; r++) {
+      u64 Bt[KP];
+      const unsigned* rowq = reinterpret_cast<const unsigned*>(&s_buf[lane][r * KP]);
+#pragma unroll
+      for (int j2 = 0; j2 < KP / 2; j2++) {
+        const unsigned two = rowq[j2];
+#pragma unroll
+        for (int hh = 0; hh < 2; hh++) {
+          const int j = 2 * j2 + hh;
+          const unsigned id = hh ? (two >> 16) : (two & 0xffffu);
+          u64 key = KEY_NONE;
+          if (r * KP + j < cnt) {
+            const float4 c = s_stage[id];
+            key = make_key(dist2(qx, qy, qz, c.x, c.y, c.z), __float_as_int(c.w));
+          }
+          Bt[j] = key;
+        }
+      }
+      key_sort16(Bt);
+      key_merge16(L, Bt);
+      if (STATS) st_rounds++;
+    }
+    cnt = 0;
+    tau_d = key_dist(L[KP - 1]);
+    __syncwarp();
+  };
+  // warp-per-query scan of the tiles in `need` (bit i = staged slot i) of every query; qualifiers go to the buffers.  Returns
+  // false when a buffer would overflow: the caller merges and calls again (the unvisited tiles stay in `need`).
+  auto scan = [&](unsigned& need) -> bool {
+#pragma unroll 1
+    for (int qi = 0; qi < TILE; qi++) {
+      unsigned m = __shfl_sync(FULL, need, qi);
+      if (!m) continue;
+      const float ox = __shfl_sync(FULL, qx, qi), oy = __shfl_sync(FULL, qy, qi), oz = __shfl_sync(FULL, qz, qi);
+      const u64 otau = __shfl_sync(FULL, L[KP - 1], qi);
+      int ocnt = __shfl_sync(FULL, cnt, qi);
+      unsigned short* row = &s_buf[qi][0];
+      bool overflow = false;
+      while (m) {
+        const int i = __ffs(m) - 1;
+        const float4 c = s_stage[i * TILE + lane];
+        const u64 ckey = make_key(dist2(ox, oy, oz, c.x, c.y, c.z), __float_as_int(c.w));
+        const bool pass = ckey < otau;
+        const unsigned bal = __ballot_sync(FULL, pass);
+        const int np = __popc(bal);
+        if (ocnt + np > V2_CAP) {  // warp-uniform
+          overflow = true;
+          break;
+        }
+        if (pass) row[ocnt + __popc(bal & lt)] = (unsigned short)(i * TILE + lane);
+        ocnt += np;
+        m &= m - 1;
+        if (STATS) st_visits++, st_quals += np;
+      }
+      if (lane == qi) {
+        cnt = ocnt;
+        need = m;
+      }
+      if (overflow) return false;
+    }
+    __syncwarp();
+    return true;
+  };
+
+  // ---- (3)-(5) chunks of V2_CH staged tiles ----
   unsigned phase = 0;
 #pragma unroll 1
   for (int c0 = 0; c0 < ncand; c0 += V2_CH) {
     const int nch = min(V2_CH, ncand - c0);
-    __syncthreads();  // every warp is done with the previous chunk
-    if (wib == 0) {
-      if (lane == 0) mbar_arrive_expect_tx(&s_mbar, (unsigned)nch * TILE * 16u);
-      __syncwarp();
-      if (lane < nch) bulk_load_1d(&s_stage[lane * TILE], P.psort + (size_t)s_cand[c0 + lane] * TILE, TILE * 16u, &s_mbar);
+    __syncwarp();
+    if (lane == 0) mbar_arrive_expect_tx(&s_mbar, (unsigned)nch * TILE * 16u);
+    __syncwarp();
+    int myt = -1;
+    if (lane < nch) {
+      myt = s_cand[c0 + lane];
+      bulk_load_1d(&s_stage[lane * TILE], P.psort + (size_t)myt * TILE, TILE * 16u, &s_mbar);
+      s_box[lane][0] = make_float4(P.tb[myt], P.tb[(size_t)ntp + myt], P.tb[(size_t)2 * ntp + myt], 0.0f);
+      s_box[lane][1] = make_float4(P.tb[(size_t)3 * ntp + myt], P.tb[(size_t)4 * ntp + myt], P.tb[(size_t)5 * ntp + myt], 0.0f);
     }
-    // while the copies fly: which staged tiles does MY query need?  (point-to-box distance against my current k-th distance)
+    __syncwarp();
+    // which staged tiles does MY query need (point-to-box distance against my current k-th distance), and which is nearest?
     unsigned need = 0;
+    int nearest = -1;
+    float nearest_d = INFINITY;
 #pragma unroll 4
     for (int i = 0; i < nch; i++) {
-      const float4 bmn = s_box[c0 + i][0], bmx = s_box[c0 + i][1];
+      const float4 bmn = s_box[i][0], bmx = s_box[i][1];
       const float gx = fmaxf(0.0f, fmaxf(bmn.x - qx, qx - bmx.x)), gy = fmaxf(0.0f, fmaxf(bmn.y - qy, qy - bmx.y)),
                   gz = fmaxf(0.0f, fmaxf(bmn.z - qz, qz - bmx.z));
-      const bool nd = (gx * gx + gy * gy + gz * gz) * CULL_SAFETY <= tau_d && s_cand[c0 + i] != qt;
-      need |= nd ? (1u << i) : 0u;
+      const float bd = gx * gx + gy * gy + gz * gz;
+      if (bd * CULL_SAFETY <= tau_d) {
+        need |= 1u << i;
+        if (bd < nearest_d) {
+          nearest_d = bd;
+          nearest = i;
+        }
+      }
     }
     if (!qvalid) need = 0;
     mbar_wait(&s_mbar, phase);
     phase ^= 1u;
-
-    int qi = 0;
+    // phase 1: only the nearest needed tile of every query (at most 32 qualifiers each: cannot overflow)
+    unsigned first = (need && nearest >= 0) ? (1u << nearest) : 0u;
+    need &= ~first;
+    scan(first);
+    merge_buffers();
+    // phase 2: the other tiles, against the tightened k-th distances
+    if (need) {
+      unsigned keep = 0;
+      unsigned m = need;
+      while (m) {
+        const int i = __ffs(m) - 1;
+        m &= m - 1;
+        const float4 bmn = s_box[i][0], bmx = s_box[i][1];
+        const float gx = fmaxf(0.0f, fmaxf(bmn.x - qx, qx - bmx.x)), gy = fmaxf(0.0f, fmaxf(bmn.y - qy, qy - bmx.y)),
+                    gz = fmaxf(0.0f, fmaxf(bmn.z - qz, qz - bmx.z));
+        if ((gx * gx + gy * gy + gz * gz) * CULL_SAFETY <= tau_d) keep |= 1u << i;
+      }
+      need = keep;
+    }
 #pragma unroll 1
     while (true) {
-      bool overflow = false;
-#pragma unroll 1
-      for (; qi < TILE; qi++) {
-        unsigned m = __shfl_sync(FULL, need, qi);
-        if (!m) continue;
-        const float ox = __shfl_sync(FULL, qx, qi), oy = __shfl_sync(FULL, qy, qi), oz = __shfl_sync(FULL, qz, qi);
-        const u64 otau = __shfl_sync(FULL, L[KP - 1], qi);
-        int ocnt = __shfl_sync(FULL, cnt, qi);
-        unsigned short* row = &s_buf[wib][qi][0];
-        while (m) {
-          const int i = __ffs(m) - 1;
-          const float4 c = s_stage[i * TILE + lane];
-          const u64 ckey = make_key(dist2(ox, oy, oz, c.x, c.y, c.z), __float_as_int(c.w));
-          const bool pass = ckey < otau;
-          const unsigned bal = __ballot_sync(FULL, pass);
-          const int np = __popc(bal);
-          if (ocnt + np > V2_CAP) {  // warp-uniform: merge what is buffered first, then come back to this tile
-            overflow = true;
-            break;
-          }
-          if (pass) row[ocnt + __popc(bal & lt)] = (unsigned short)(i * TILE + lane);
-          ocnt += np;
-          m &= m - 1;
-          if (STATS) st_visits++, st_quals += np;
-        }
-        if (lane == qi) {
-          cnt = ocnt;
-          need = m;  // non-zero only after an overflow: the tiles of this query still to visit
-        }
-        if (overflow) break;
-      }
-      __syncwarp();
-      // ---- lane-per-query merge of the buffered qualifiers, 16 per round (the staged tiles are still resident) ----
-      const int rounds = (__reduce_max_sync(FULL, cnt) + KP - 1) / KP;
-#pragma unroll 1
-      for (int r = 0; r < rounds; r++) {
-        u64 Bt[KP];
-        const unsigned* rowq = reinterpret_cast<const unsigned*>(&s_buf[wib][lane][r * KP]);
-#pragma unroll
-        for (int j2 = 0; j2 < KP / 2; j2++) {
-          const unsigned two = rowq[j2];
-#pragma unroll
-          for (int hh = 0; hh < 2; hh++) {
-            const int j = 2 * j2 + hh;
-            const unsigned id = hh ? (two >> 16) : (two & 0xffffu);
-            u64 key = KEY_NONE;
-            if (r * KP + j < cnt) {
-              const float4 c = s_stage[id];
-              key = make_key(dist2(qx, qy, qz, c.x, c.y, c.z), __float_as_int(c.w));
-            }
-            Bt[j] = key;
-          }
-        }
-        key_sort16(Bt);
-        key_merge16(L, Bt);
-        if (STATS) st_rounds++;
-      }
-      cnt = 0;
-      tau_d = key_dist(L[KP - 1]);
-      __syncwarp();
-      if (!overflow) break;
+      const bool done = scan(need);
+      merge_buffers();
+      if (done) break;
       if (STATS) st_oflow++;
     }
   }
 
   // ---- results: neighbour j of my query is L[KP - k + j]; transpose through shared memory for coalesced stores ----
   __syncwarp();
-  int* s_out = reinterpret_cast<int*>(&s_buf[wib][0][0]);  // 32 x k ints <= 1920 B of this warp's 4224 B buffer
+  int* s_out = reinterpret_cast<int*>(&s_buf[0][0]);  // 32 x k ints <= 1920 B of the 4224 B buffer
 #pragma unroll
   for (int i = 0; i < KP; i++) {
     const int j = i - (KP - k);
     if (j >= 0) s_out[lane * k + j] = key_idx(L[i]);
   }
   __syncwarp();
-  if (wvalid) {
+  {
     int* dst = P.ids + (size_t)qt * TILE * k;
     for (int e = lane; e < TILE * k; e += 32) dst[e] = s_out[e];
   }
@@ -1012,8 +1043,9 @@ __global__ void __launch_bounds__(128, 4) k_knn_search_v2(const KnnParams* __res
       }
     }
   }
-  if (STATS && P.stat_pairs && wvalid) {
+  if (STATS && P.stat_pairs) {
     st_visits = __shfl_sync(FULL, st_visits, 0);
+    st_quals = __shfl_sync(FULL, st_quals, 0);
     if (lane == 0) {
       atomicAdd(P.stat_pairs, st_visits * 32ull + 1024ull);  // (query, candidate) distance evaluations of this warp (32 x 32 own tile incl.)
       atomicAdd(P.stat_pairs + 2, st_quals);
