@@ -230,6 +230,11 @@ int mrslam_elev_set_owned_rows(mrslam_elev_t*, int row_lo, int row_hi);
 int mrslam_elev_rows_copy(mrslam_elev_t*, int plane, int storage_row, int n_rows, void* d_buf, int to_map);
 /* Raytracing(length)   :1301   obstacle clean-up along the sensor rays (G_Raytracing :706-889) + reset of map_lowest */
 int mrslam_elev_raytracing(mrslam_elev_t*, int length);
+/* Stable LSD radix sort of (u32 key, u32 value) pairs by key bits [0, bits) with the library's own kernels (the sort behind the
+ * elevation replay, csrc/radix_sort.cuh; replaces cub::DeviceRadixSort there): keys equal to drop_key are removed when use_drop != 0
+ * (how invalid points leave the fuse).  Host arrays in and out; *n_out = number of pairs kept.  Utility / test entry point. */
+int mrslam_sort_pairs_u32(const unsigned* keys, const unsigned* vals, int n, int bits, unsigned drop_key, int use_drop,
+                          unsigned* keys_out, unsigned* vals_out, int* n_out);
 /* read back the hidden map (any pointer may be NULL); length*length entries each, storage (ring-buffer) order */
 int mrslam_elev_get_map(mrslam_elev_t*, float* elevation, float* variance, float* intensity, int* R, int* G, int* B,
                         float* lowest);

@@ -139,6 +139,7 @@ def _declare(L):
         L.mrslam_voxelfeat_features.argtypes = [fp, i, i, i, ip, fp, fp]
         L.mrslam_voxelfeat_transform.argtypes = [fp, i, i, i, i, i, i, i, fp]
         L.mrslam_voxelocc_bev_device.argtypes = [fp, C.c_void_p, i, i, i, i, i, fp]
+        L.mrslam_sort_pairs_u32.argtypes = [fp, fp, i, i, C.c_uint, i, fp, fp, C.POINTER(C.c_int)]
         L.mrslam_ring_scans_to_bev_device.argtypes = [fp, C.c_void_p, i, i, f, f, i, i, i, i, fp]
     if hasattr(L, "mrslam_radon_forward"):
         L.mrslam_radon_forward.argtypes = [fp, i, i, i, fp, i, i, f, i, i, fp]

@@ -51,6 +51,7 @@ extern thread_local int g_status;
 struct Runtime {
   int device = -1;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;  // host -> device uploads of input clouds: they overlap kernels already queued on `stream`
   int sm_count = 148;
   std::atomic<unsigned long long> launches{0};
   std::mutex mu;  // serialises host-side drivers that share the stream

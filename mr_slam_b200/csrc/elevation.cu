@@ -17,12 +17,12 @@
 // Arithmetic: built with -fmad=false; every fused multiply-add below is explicit and is the
 // contraction nvcc applies to the reference kernels (t=a*b; t=fma(c,d,t) ... left to right), so the
 // cell indices are bit-identical to the reference's and to the CPU oracle's.
-#include <cub/device/device_radix_sort.cuh>
 
 #include <algorithm>
 #include <cmath>
 
 #include "common.cuh"
+#include "radix_sort.cuh"
 
 namespace mrslam {
 
@@ -209,10 +209,10 @@ __global__ void k_elev_process_batch(const BatchFrame* __restrict__ frames, int 
 struct BatchOffsets {
   int off[ELEV_GROUP];
 };
-__global__ void k_elev_gather_batch(const int* __restrict__ order, int n, BatchOffsets bo, const float* __restrict__ ph,
+__global__ void k_elev_gather_batch(const int* __restrict__ order, const int* __restrict__ d_n, BatchOffsets bo, const float* __restrict__ ph,
                                     const float* __restrict__ pv, float2* __restrict__ hv, unsigned char* __restrict__ fr) {
   int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n) return;
+  if (j >= *d_n) return;  // the sort dropped the invalid points: the count of the rest lives on the device
   const int v = order[j];
   const int f = v >> 24, pi = bo.off[f] + (v & 0xffffff);
   hv[j] = make_float2(ph[pi], pv[pi]);
@@ -248,11 +248,11 @@ __global__ void k_elev_keys(const int* __restrict__ idx, const float* __restrict
 }
 
 // gather the per-point inputs into sorted (cell, point-index) order so that the run walk below reads contiguous memory
-__global__ void k_elev_gather(const int* __restrict__ order, int n, const float* __restrict__ ph, const float* __restrict__ pv,
+__global__ void k_elev_gather(const int* __restrict__ order, const int* __restrict__ d_n, const float* __restrict__ ph, const float* __restrict__ pv,
                               const int* __restrict__ cR, const int* __restrict__ cG, const int* __restrict__ cB,
                               const float* __restrict__ inten, float2* __restrict__ hv, int4* __restrict__ col) {
   int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n) return;
+  if (j >= *d_n) return;  // the sort dropped the invalid points; the count of the rest lives on the device
   const int pi = order[j];
   hv[j] = make_float2(ph[pi], pv[pi]);
   if (col) col[j] = make_int4(cR[pi], cG[pi], cB[pi], __float_as_int(inten[pi]));
@@ -273,11 +273,12 @@ __device__ __forceinline__ bool elev_mahal_gt5(float h, float e, float v) {
   return d / sqrtf(v) > 5.f;
 }
 
-__global__ void k_elev_fuse_segments(const int* __restrict__ keys, int n, int cells, const float2* __restrict__ hv,
+__global__ void k_elev_fuse_segments(const int* __restrict__ keys, const int* __restrict__ d_n, int cells, const float2* __restrict__ hv,
                                      const int4* __restrict__ col, float* __restrict__ elevation, float* __restrict__ variance,
                                      float* __restrict__ intensity, int* __restrict__ R, int* __restrict__ G, int* __restrict__ B,
                                      unsigned long long* n_fused) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = *d_n;
   if (i >= n) return;
   const int c = keys[i];
   if (c >= cells) return;
@@ -361,11 +362,12 @@ __global__ void k_elev_fuse_segments(const int* __restrict__ keys, int n, int ce
 // per storage row / column, one bit per frame whose Move cleared it (k_elev_clear_tab has already applied the clears), so a
 // run only applies the points of frames >= the last clear of its cell.  Result: exactly the state the per-frame sequence
 // Move, Process_points, Fuse leaves, with one sort and one walk for the whole group.
-__global__ void k_elev_fuse_runs_batch(const int* __restrict__ keys, int n, int cells, int L, const float2* __restrict__ hv,
+__global__ void k_elev_fuse_runs_batch(const int* __restrict__ keys, const int* __restrict__ d_n, int cells, int L, const float2* __restrict__ hv,
                                        const unsigned char* __restrict__ fr, const unsigned long long* __restrict__ rowclr,
                                        const unsigned long long* __restrict__ colclr, float* __restrict__ elevation,
                                        float* __restrict__ variance, unsigned long long* n_fused) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = *d_n;
   if (i >= n) return;
   const int c = keys[i];
   if (c >= cells) return;
@@ -468,14 +470,9 @@ struct Elev {
   DevBuf<int> pidx, pR, pG, pB, keys, keys_alt, vals, vals_alt;
   DevBuf<float2> ghv;
   DevBuf<int4> gcol;
-  DevBuf<unsigned char> cubtmp;
   DevBuf<unsigned long long> counter;
   DevBuf<float> feat;   // Map_feature staging: 6 float planes
   DevBuf<int> feat_i;   // ... and 3 int planes
-  // second set of sorted-stream buffers + an auxiliary stream: the batched entry point overlaps process+sort+gather of frame
-  // f+1 (aux stream) with the run walk of frame f (library stream)
-  DevBuf<int> keys2, keys_alt2, vals2, vals_alt2;
-  DevBuf<float2> ghv2;
   // one-pass replay of a group of frames: frame table, clear table, per-row / per-column clear masks (pinned staging + device)
   DevBuf<BatchFrame> d_frames;
   PinBuf<BatchFrame> h_frames;
@@ -484,9 +481,9 @@ struct Elev {
   DevBuf<unsigned long long> d_clr;
   PinBuf<unsigned long long> h_clr;
   DevBuf<unsigned char> gfr;
+  RadixScratch rsort;
   StageFence batch_fence;
-  cudaStream_t aux = nullptr;
-  cudaEvent_t ev_start = nullptr, ev_a[2] = {nullptr, nullptr}, ev_b[2] = {nullptr, nullptr};
+  cudaEvent_t ev_start = nullptr;
   // asynchronous replay: the map-writing half runs on `bstream` instead of the library stream, so that an unrelated batch
   // (a loop-closure storm) can use the library stream meanwhile; every other entry point joins first
   cudaStream_t bstream = nullptr;
@@ -517,22 +514,19 @@ struct Elev {
   void release() {
     for (DevBuf<float>* b : {&elevation, &variance, &intensity, &lowest, &traver, &px, &py, &pz, &pvar, &pxt, &pyt, &pzt, &pint, &ph}) b->release();
     for (DevBuf<int>* b : {&R, &G, &B, &pidx, &pR, &pG, &pB, &keys, &keys_alt, &vals, &vals_alt}) b->release();
-    for (DevBuf<int>* b : {&keys2, &keys_alt2, &vals2, &vals_alt2}) b->release();
-    ghv2.release();
-    cubtmp.release();
     counter.release();
     ghv.release();
     gcol.release();
     feat.release();
     feat_i.release();
     d_frames.release(); h_frames.release(); d_ctab.release(); h_ctab.release(); d_clr.release(); h_clr.release(); gfr.release();
+    rsort.hist.release(); rsort.chunk.release(); rsort.count.release();
     if (bstream) cudaStreamSynchronize(bstream);
-    if (aux) cudaStreamDestroy(aux);
     if (bstream) cudaStreamDestroy(bstream);
-    for (cudaEvent_t e : {ev_start, ev_a[0], ev_a[1], ev_b[0], ev_b[1], ev_done})
+    for (cudaEvent_t e : {ev_start, ev_done})
       if (e) cudaEventDestroy(e);
-    aux = bstream = nullptr;
-    ev_start = ev_a[0] = ev_a[1] = ev_b[0] = ev_b[1] = ev_done = nullptr;
+    bstream = nullptr;
+    ev_start = ev_done = nullptr;
     pending_join = false;
   }
   int reserve_batch(size_t total, int nframes) {
@@ -547,13 +541,10 @@ struct Elev {
     return MRSLAM_OK;
   }
   int ensure_pipeline(int n) {
-    size_t m = std::max(n, 1);
-    MR_CHECK(keys2.reserve(m)); MR_CHECK(keys_alt2.reserve(m)); MR_CHECK(vals2.reserve(m)); MR_CHECK(vals_alt2.reserve(m));
-    MR_CHECK(ghv2.reserve(m));
-    if (!aux) {
-      MR_CUDA(cudaStreamCreateWithFlags(&aux, cudaStreamNonBlocking));
+    (void)n;
+    if (!bstream) {
       MR_CUDA(cudaStreamCreateWithFlags(&bstream, cudaStreamNonBlocking));
-      for (cudaEvent_t* e : {&ev_start, &ev_a[0], &ev_a[1], &ev_b[0], &ev_b[1], &ev_done}) MR_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+      for (cudaEvent_t* e : {&ev_start, &ev_done}) MR_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     }
     return MRSLAM_OK;
   }
@@ -568,14 +559,15 @@ static int fuse_sorted(Elev* m, int n, const float* d_h, const float* d_v, const
   if (n > 0) {
     int bits = 1;
     while ((1ll << bits) <= cells) bits++;
-    cub::DoubleBuffer<int> dk(m->keys.p, m->keys_alt.p), dv(m->vals.p, m->vals_alt.p);
-    size_t tmp = 0;
-    MR_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp, dk, dv, n, 0, bits, st));
-    MR_CHECK(m->cubtmp.reserve(tmp));
-    MR_CUDA(cub::DeviceRadixSort::SortPairs(m->cubtmp.p, tmp, dk, dv, n, 0, bits, st));
+    // stable sort by cell with the library's own radix sort (csrc/radix_sort.cuh); invalid points (key == cells) are dropped in
+    // its first pass, the number of valid ones stays on the device
+    unsigned *ks = nullptr, *vs = nullptr;
+    const int* d_nv = nullptr;
+    MR_CHECK(radix_sort_pairs(m->rsort, (unsigned*)m->keys.p, (unsigned*)m->vals.p, (unsigned*)m->keys_alt.p, (unsigned*)m->vals_alt.p, n, nullptr, 0,
+                              ((bits + 7) / 8) * 8, (unsigned)cells, 1, st, &ks, &vs, &d_nv));
     if (n_fused) MR_CUDA(cudaMemsetAsync(m->counter.p, 0, sizeof(unsigned long long), st));
-    k_elev_gather<<<(n + 255) / 256, 256, 0, st>>>(dv.Current(), n, d_h, d_v, d_R, d_G, d_B, d_I, m->ghv.p, d_R ? m->gcol.p : nullptr);
-    k_elev_fuse_segments<<<(n + 127) / 128, 128, 0, st>>>(dk.Current(), n, cells, m->ghv.p, d_R ? m->gcol.p : nullptr, m->elevation.p,
+    k_elev_gather<<<(n + 255) / 256, 256, 0, st>>>((const int*)vs, d_nv, d_h, d_v, d_R, d_G, d_B, d_I, m->ghv.p, d_R ? m->gcol.p : nullptr);
+    k_elev_fuse_segments<<<(n + 127) / 128, 128, 0, st>>>((const int*)ks, d_nv, cells, m->ghv.p, d_R ? m->gcol.p : nullptr, m->elevation.p,
                                                          m->variance.p, m->intensity.p, m->R.p, m->G.p, m->B.p,
                                                          n_fused ? m->counter.p : m->counter.p + 1);
     count_launch(2);
@@ -874,90 +866,6 @@ int mrslam_elev_process_fuse_device(mrslam_elev_t* h, const float* d_x, const fl
   return fuse_sorted(m, n, m->pzt.p, m->pvar.p, nullptr, nullptr, nullptr, nullptr, n_fused);
 }
 
-// Many frames in one call (map replay / catching up after a loop closure): Move + Process_points + Fuse per frame, exactly
-// the per-frame sequence, with the map-independent half of frame f+1 (process, sort by cell, gather; aux stream) running
-// under the run walk of frame f (library stream).  `lowest` is only touched by the process kernels (aux stream, in frame
-// order); elevation / variance / colour only by clear, fuse and clamp (library stream, in frame order).
-static int elev_batch_pipelined(mrslam_elev_t* h, const mrslam_elev_frame_t* frames, int nframes, float resolution, int length, bool async) {
-  REQ(h);
-  Elev* m = E(h);
-  REQ_INIT(m);
-  if (nframes < 0 || (nframes > 0 && !frames)) {
-    set_error("process_fuse_device_batch: bad arguments");
-    return MRSLAM_ERR_ARG;
-  }
-  std::lock_guard<std::mutex> lk2(m->mu);
-  std::lock_guard<std::mutex> lk(rt().mu);
-  MR_CHECK(m->join());
-  if (nframes == 0) return MRSLAM_OK;
-  int max_n = 0;
-  for (int f = 0; f < nframes; f++) {
-    if (frames[f].n < 0 || (frames[f].n > 0 && (!frames[f].d_x || !frames[f].d_y || !frames[f].d_z))) {
-      set_error("process_fuse_device_batch: bad frame %d", f);
-      return MRSLAM_ERR_ARG;
-    }
-    max_n = std::max(max_n, frames[f].n);
-  }
-  MR_CHECK(m->reserve_points(max_n));
-  MR_CHECK(m->ensure_pipeline(max_n));
-  cudaStream_t st = async ? m->bstream : rt().stream, aux = m->aux;
-  const int cells = m->cells();
-  int bits = 1;
-  while ((1ll << bits) <= cells) bits++;
-  size_t tmp = 0;
-  {
-    cub::DoubleBuffer<int> dk(m->keys.p, m->keys_alt.p), dv(m->vals.p, m->vals_alt.p);
-    MR_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp, dk, dv, std::max(max_n, 1), 0, bits, aux));
-  }
-  MR_CHECK(m->cubtmp.reserve(tmp));
-  ProfScope ps(PROF_ELEV_FUSE);  // (spans only the enqueue when the batch is asynchronous)
-  MR_CUDA(cudaEventRecord(m->ev_start, rt().stream));  // inputs and the map state are ordered on the library stream
-  MR_CUDA(cudaStreamWaitEvent(aux, m->ev_start, 0));
-  if (async) MR_CUDA(cudaStreamWaitEvent(st, m->ev_start, 0));
-  for (int f = 0; f < nframes; f++) {
-    const mrslam_elev_frame_t& F = frames[f];
-    const int s = f & 1, n = F.n;
-    if (F.do_move) MR_CHECK(move_locked(m, F.position, resolution, length, nullptr, nullptr, nullptr, st));  // clears -> map stream
-    int* keys = s ? m->keys2.p : m->keys.p;
-    int* keys_alt = s ? m->keys_alt2.p : m->keys_alt.p;
-    int* vals = s ? m->vals2.p : m->vals.p;
-    int* vals_alt = s ? m->vals_alt2.p : m->vals_alt.p;
-    float2* ghv = s ? m->ghv2.p : m->ghv.p;
-    const int* keys_sorted = keys;
-    // ---- aux stream: everything of frame f that does not read the map
-    if (f >= 2) MR_CUDA(cudaStreamWaitEvent(aux, m->ev_b[s], 0));  // set s is free again once frame f-2 has been fused
-    if (n > 0) {
-      ProcParams P;
-      fill_proc(P, F.T16, F.lower, F.upper, F.min_r, F.beam_a, F.beam_c, F.sJ, F.rotVar, F.CSBT, F.PCBM, F.BrBS, F.near_filter);
-      k_elev_process<<<(n + 255) / 256, 256, 0, aux>>>(F.d_x, F.d_y, F.d_z, n, P, m->g, m->lowest.p, nullptr, m->pvar.p, nullptr, nullptr,
-                                                      m->pzt.p, keys, vals);
-      cub::DoubleBuffer<int> dk(keys, keys_alt), dv(vals, vals_alt);
-      size_t t2 = tmp;
-      MR_CUDA(cub::DeviceRadixSort::SortPairs(m->cubtmp.p, t2, dk, dv, n, 0, bits, aux));
-      keys_sorted = dk.Current();
-      k_elev_gather<<<(n + 255) / 256, 256, 0, aux>>>(dv.Current(), n, m->pzt.p, m->pvar.p, nullptr, nullptr, nullptr, nullptr, ghv, nullptr);
-      count_launch(2);
-    }
-    MR_CUDA(cudaEventRecord(m->ev_a[s], aux));
-    // ---- library stream: the run walk and the clamp, in frame order
-    MR_CUDA(cudaStreamWaitEvent(st, m->ev_a[s], 0));
-    if (n > 0) {
-      k_elev_fuse_segments<<<(n + 127) / 128, 128, 0, st>>>(keys_sorted, n, cells, ghv, nullptr, m->elevation.p, m->variance.p,
-                                                           m->intensity.p, m->R.p, m->G.p, m->B.p, m->counter.p + 1);
-      count_launch(1);
-    }
-    k_elev_clamp_var<<<((cells + 3) / 4 + 255) / 256, 256, 0, st>>>(m->variance.p, cells);
-    count_launch(1);
-    MR_CUDA(cudaEventRecord(m->ev_b[s], st));
-  }
-  MR_CUDA(cudaGetLastError());
-  if (async) {
-    MR_CUDA(cudaEventRecord(m->ev_done, st));
-    m->pending_join = true;
-  }
-  return MRSLAM_OK;
-}
-
 // The whole replay in one pass per group of <= 64 frames: host-side Move plans (geometry per frame, strips to clear, one bit per
 // frame in per-row / per-column clear masks) -> one clear launch, one process launch over all frames, ONE stable sort by cell of
 // all points (the concatenation is in (frame, point) order, so is every run afterwards), one gather, one run walk that applies the
@@ -1033,13 +941,14 @@ static int elev_group_onepass(Elev* m, const mrslam_elev_frame_t* frames, int nf
     ProfScope ps(PROF_ELEV_FUSE);
     int bits = 1;
     while ((1ll << bits) <= cells) bits++;
-    cub::DoubleBuffer<int> dk(m->keys.p, m->keys_alt.p), dv(m->vals.p, m->vals_alt.p);
-    size_t tmp = 0;
-    MR_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp, dk, dv, n, 0, bits, st));
-    MR_CHECK(m->cubtmp.reserve(tmp));
-    MR_CUDA(cub::DeviceRadixSort::SortPairs(m->cubtmp.p, tmp, dk, dv, n, 0, bits, st));
-    k_elev_gather_batch<<<(n + 255) / 256, 256, 0, st>>>(dv.Current(), n, bo, m->pzt.p, m->pvar.p, m->ghv.p, m->gfr.p);
-    k_elev_fuse_runs_batch<<<(n + 127) / 128, 128, 0, st>>>(dk.Current(), n, cells, L, m->ghv.p, m->gfr.p, any_move ? m->d_clr.p : nullptr,
+    // own stable radix sort (csrc/radix_sort.cuh): the first pass drops the invalid points (key == cells: filtered, outside the
+    // map, or in another GPU's rows of a tile-sharded grid), the count of the rest stays on the device
+    unsigned *ks = nullptr, *vs = nullptr;
+    const int* d_nv = nullptr;
+    MR_CHECK(radix_sort_pairs(m->rsort, (unsigned*)m->keys.p, (unsigned*)m->vals.p, (unsigned*)m->keys_alt.p, (unsigned*)m->vals_alt.p, n, nullptr, 0,
+                              ((bits + 7) / 8) * 8, (unsigned)cells, 1, st, &ks, &vs, &d_nv));
+    k_elev_gather_batch<<<(n + 255) / 256, 256, 0, st>>>((const int*)vs, d_nv, bo, m->pzt.p, m->pvar.p, m->ghv.p, m->gfr.p);
+    k_elev_fuse_runs_batch<<<(n + 127) / 128, 128, 0, st>>>((const int*)ks, d_nv, cells, L, m->ghv.p, m->gfr.p, any_move ? m->d_clr.p : nullptr,
                                                            any_move ? m->d_clr.p + L : nullptr, m->elevation.p, m->variance.p,
                                                            m->counter.p + 1);
     count_launch(2);
@@ -1054,7 +963,6 @@ static int elev_group_onepass(Elev* m, const mrslam_elev_frame_t* frames, int nf
 }
 
 static int elev_batch(mrslam_elev_t* h, const mrslam_elev_frame_t* frames, int nframes, float resolution, int length, bool async) {
-  if (getenv("MRSLAM_ELEV_PIPELINED")) return elev_batch_pipelined(h, frames, nframes, resolution, length, async);  // round-1 path (A/B)
   REQ(h);
   Elev* m = E(h);
   REQ_INIT(m);
@@ -1329,6 +1237,41 @@ int mrslam_elev_get_state(mrslam_elev_t* h, float* central2, int* start2) {
   central2[1] = m->g.cy;
   start2[0] = m->g.sx;
   start2[1] = m->g.sy;
+  return MRSLAM_OK;
+}
+
+// Stable radix sort of (key, value) pairs by key bits [0, bits) with the hot path's own kernels (csrc/radix_sort.cuh): host arrays
+// in, host arrays out; keys equal to drop_key are removed when use_drop != 0.  A test / utility entry point -- the elevation
+// replay calls the same code on device-resident keys.
+int mrslam_sort_pairs_u32(const unsigned* keys, const unsigned* vals, int n, int bits, unsigned drop_key, int use_drop, unsigned* keys_out,
+                          unsigned* vals_out, int* n_out) {
+  MR_CHECK(ensure_init());
+  if (n < 0 || bits < 1 || bits > 32 || (n > 0 && (!keys || !vals || !keys_out || !vals_out)) || !n_out) {
+    set_error("sort_pairs_u32: bad arguments");
+    return MRSLAM_ERR_ARG;
+  }
+  std::lock_guard<std::mutex> lk(rt().mu);
+  cudaStream_t st = rt().stream;
+  static RadixScratch S;
+  static DevBuf<unsigned> ka, va, kb, vb;
+  const size_t cap = std::max(n, 1);
+  MR_CHECK(ka.reserve(cap)); MR_CHECK(va.reserve(cap)); MR_CHECK(kb.reserve(cap)); MR_CHECK(vb.reserve(cap));
+  if (n > 0) {
+    MR_CUDA(cudaMemcpyAsync(ka.p, keys, sizeof(unsigned) * (size_t)n, cudaMemcpyHostToDevice, st));
+    MR_CUDA(cudaMemcpyAsync(va.p, vals, sizeof(unsigned) * (size_t)n, cudaMemcpyHostToDevice, st));
+  }
+  unsigned *ks = nullptr, *vs = nullptr;
+  const int* d_n = nullptr;
+  MR_CHECK(radix_sort_pairs(S, ka.p, va.p, kb.p, vb.p, n, nullptr, 0, ((bits + 7) / 8) * 8, drop_key, use_drop, st, &ks, &vs, &d_n));
+  int m = 0;
+  MR_CUDA(cudaMemcpyAsync(&m, d_n, sizeof(int), cudaMemcpyDeviceToHost, st));
+  MR_CUDA(cudaStreamSynchronize(st));
+  if (m > 0) {
+    MR_CUDA(cudaMemcpyAsync(keys_out, ks, sizeof(unsigned) * (size_t)m, cudaMemcpyDeviceToHost, st));
+    MR_CUDA(cudaMemcpyAsync(vals_out, vs, sizeof(unsigned) * (size_t)m, cudaMemcpyDeviceToHost, st));
+    MR_CUDA(cudaStreamSynchronize(st));
+  }
+  *n_out = m;
   return MRSLAM_OK;
 }
 }

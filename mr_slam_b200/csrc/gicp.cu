@@ -32,6 +32,10 @@ struct Cloud {
   bool cov_valid = false;
   bool built = false;   // spatial structures (psort / tb / sb) are produced lazily, batched with the other clouds of a call
   DevBuf<float> raw;    // staging of host input
+  // uploads run on the runtime's copy stream so that they overlap kernels already queued on the library stream (the target
+  // clouds of a batch go up while the source clouds' kNN runs): ev_raw_free = the staging buffer is allocated and no longer read
+  // (library-stream order), ev_up = the upload has landed (copy-stream order)
+  cudaEvent_t ev_raw_free = nullptr, ev_up = nullptr;
   int refs = 1;
 
   // stage 1 (at setInput time): points into porig (device).  The Morton sort etc. is deferred to build_clouds().
@@ -77,15 +81,33 @@ struct Cloud {
       return MRSLAM_ERR_ARG;
     }
     size_t nf = (size_t)n_ * stride;
+    const float* before = raw.p;
     MR_CHECK(raw.reserve(std::max<size_t>(nf, 1)));
     if (n_ > 0) {
+      cudaStream_t up = rt().copy_stream, st = rt().stream;
+      if (!ev_up) {
+        MR_CUDA(cudaEventCreateWithFlags(&ev_up, cudaEventDisableTiming));
+        MR_CUDA(cudaEventCreateWithFlags(&ev_raw_free, cudaEventDisableTiming));
+        before = nullptr;
+      }
+      // a (re)allocated staging buffer exists in library-stream order only; otherwise ev_raw_free was recorded behind the
+      // last kernel that read the buffer (a previous life of this pooled cloud), long complete by now
+      if (raw.p != before) MR_CUDA(cudaEventRecord(ev_raw_free, st));
+      MR_CUDA(cudaStreamWaitEvent(up, ev_raw_free, 0));
       size_t bytes = ((size_t)(n_ - 1) * stride + 3) * sizeof(float);
-      MR_CUDA(cudaMemcpyAsync(raw.p, xyz, bytes, cudaMemcpyHostToDevice, rt().stream));
+      MR_CUDA(cudaMemcpyAsync(raw.p, xyz, bytes, cudaMemcpyHostToDevice, up));
+      MR_CUDA(cudaEventRecord(ev_up, up));
+      MR_CUDA(cudaStreamWaitEvent(st, ev_up, 0));
     }
-    return set_from_device_raw(raw.p, n_, stride);
+    int rc = set_from_device_raw(raw.p, n_, stride);
+    if (rc == MRSLAM_OK && n_ > 0) MR_CUDA(cudaEventRecord(ev_raw_free, rt().stream));  // packed: the staging buffer is free again
+    return rc;
   }
 
   void release() {
+    if (ev_up) cudaEventDestroy(ev_up);
+    if (ev_raw_free) cudaEventDestroy(ev_raw_free);
+    ev_up = ev_raw_free = nullptr;
     porig.release(); psort.release(); tb.release(); sb.release(); qp.release(); skeys.release(); cov.release(); knn_ids.release(); knn_fb.release(); raw.release();
   }
 };
@@ -215,8 +237,10 @@ static int dispatch_knn(int k, const KnnParams* d_params, int nproblems, int max
       else k_knn_search_v2<false><<<grid2, 32, 0, rt().stream>>>(d_params);
       count_launch(1);
     }
-    if (scratch_stats_enabled()) k_knn_search<true><<<grid, 128, 0, rt().stream>>>(d_params, v2 ? 1 : 0);
-    else k_knn_search<false><<<grid, 128, 0, rt().stream>>>(d_params, v2 ? 1 : 0);
+    static const int knn_wpb = getenv("MRSLAM_KNN_WPB") ? std::max(1, std::min(4, atoi(getenv("MRSLAM_KNN_WPB")))) : 4;
+    const dim3 g1((max_tiles + knn_wpb - 1) / knn_wpb, nproblems);
+    if (scratch_stats_enabled()) k_knn_search<true><<<g1, 32 * knn_wpb, 0, rt().stream>>>(d_params, v2 ? 1 : 0);
+    else k_knn_search<false><<<g1, 32 * knn_wpb, 0, rt().stream>>>(d_params, v2 ? 1 : 0);
   }
   count_launch(1);
   if (with_cov) {
@@ -566,7 +590,9 @@ static int run_linearize(Gicp** hs, const std::vector<int>& ids) {
     dim3 grid((maxt + 3) / 4, na);
     {
       ProfScope ps(PROF_NN1_SEARCH);
-      k_nn1_search<MODE_LINEARIZE><<<grid, 128, 0, st>>>(S.d_pairs.p, S.d_active.p, S.d_T.p, 0.0, S.stats ? S.d_stat.p : nullptr);
+      static const int nn1_wpb = getenv("MRSLAM_NN1_WPB") ? std::max(1, std::min(4, atoi(getenv("MRSLAM_NN1_WPB")))) : 4;
+      const dim3 g1((maxt + nn1_wpb - 1) / nn1_wpb, na);
+      k_nn1_search<MODE_LINEARIZE><<<g1, 32 * nn1_wpb, 0, st>>>(S.d_pairs.p, S.d_active.p, S.d_T.p, 0.0, S.stats ? S.d_stat.p : nullptr);
     }
     {
       ProfScope ps(PROF_LINEARIZE);

@@ -581,9 +581,9 @@ __global__ void __launch_bounds__(128, 8) k_knn_search(const KnnParams* __restri
   __shared__ int s_list[4][KCAND];
   const KnnParams P = plist[blockIdx.y];
   // second pass behind k_knn_search_v2: only the tiles it flagged (one flag per tile; warp-uniform exit further down)
-  if (only_flagged && blockIdx.x * 4 >= P.ntiles) return;
+  if (only_flagged && blockIdx.x * (blockDim.x >> 5) >= P.ntiles) return;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int qt = blockIdx.x * 4 + wib;
+  const int qt = blockIdx.x * (blockDim.x >> 5) + wib;  // 4 warps per block, or 1 (no block-level step in this kernel)
   if (qt >= P.ntiles) return;  // warp-uniform; no block-level barrier in this kernel
   if (only_flagged && !P.fb[qt]) return;
   const float4 qmine = P.psort[(size_t)qt * TILE + lane];
@@ -1296,8 +1296,11 @@ __global__ void __launch_bounds__(128) k_nn1_search(const PairParams* __restrict
   __shared__ float4 s_tile[4][TILE];
   __shared__ u64 s_cand[4][CAND];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int qt = blockIdx.x * 4 + wib;
-  if (blockIdx.x * 4 >= P.src_ntiles) return;  // block-uniform
+  // MODE_LINEARIZE has no block-level step and may be launched with ONE warp per block (a block's slot is then freed when
+  // its warp is done instead of when the slowest of four is); MODE_FITNESS reduces over the four warps of a block
+  const int wpb = blockDim.x >> 5;
+  const int qt = blockIdx.x * wpb + wib;
+  if (blockIdx.x * wpb >= P.src_ntiles) return;  // block-uniform
   const bool wvalid = qt < P.src_ntiles;
   const double* Td = Tbuf + (size_t)pid * 12;
   float res_d = INFINITY;

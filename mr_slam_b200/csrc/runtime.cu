@@ -93,6 +93,11 @@ static int init_device(int device) {
     R.stream = nullptr;
   }
   MR_CUDA(cudaStreamCreateWithFlags(&R.stream, cudaStreamNonBlocking));
+  if (R.copy_stream) {
+    cudaStreamDestroy(R.copy_stream);
+    R.copy_stream = nullptr;
+  }
+  MR_CUDA(cudaStreamCreateWithFlags(&R.copy_stream, cudaStreamNonBlocking));
   cudaMemPool_t pool;
   MR_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
   unsigned long long thresh = ~0ull;  // keep freed blocks cached: handles are created per loop-closure check

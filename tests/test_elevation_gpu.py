@@ -241,6 +241,27 @@ def test_onepass_replay_with_moves_equals_per_frame_sequence(gpu, L, res, nframe
     assert (ma["elevation"] != -10).sum() > 50
 
 
+@pytest.mark.parametrize("n,bits", [(0, 21), (1, 21), (2047, 8), (2048, 21), (2049, 24), (100003, 21), (1 << 20, 24), (3000000, 21)])
+def test_own_radix_sort_is_a_stable_sort_with_drop(gpu, n, bits):
+    """csrc/radix_sort.cuh (the sort of the elevation replay, device-side counts, sentinel drop in the first pass) against numpy's
+    stable argsort: same keys, same values in the same order -- i.e. equal keys keep their input order -- and the dropped sentinel."""
+    import ctypes as C
+    from mr_slam_b200._lib import check, lib, ptr
+    rng = np.random.default_rng(n + bits)
+    hi = (1 << bits) - 1
+    keys = rng.integers(0, max(hi // 7, 2), n, dtype=np.uint32) if n % 2 else rng.integers(0, hi, n, dtype=np.uint32)   # many / few duplicates
+    drop = np.uint32(hi)
+    keys[rng.random(n) < 0.3] = drop
+    vals = np.arange(n, dtype=np.uint32)
+    for use_drop in (1, 0):
+        ko, vo, m = np.zeros(max(n, 1), np.uint32), np.zeros(max(n, 1), np.uint32), C.c_int(-1)
+        check(lib().mrslam_sort_pairs_u32(ptr(keys) if n else None, ptr(vals) if n else None, n, bits, int(drop), use_drop, ptr(ko), ptr(vo), C.byref(m)))
+        keep = keys != drop if use_drop else np.ones(n, bool)
+        order = np.argsort(keys[keep], kind="stable")
+        assert m.value == int(keep.sum())
+        assert np.array_equal(ko[:m.value], keys[keep][order]) and np.array_equal(vo[:m.value], vals[keep][order])
+
+
 def test_empty_and_invalid_inputs(gpu):
     g = elevation.ElevationMap()
     with pytest.raises(Exception):
