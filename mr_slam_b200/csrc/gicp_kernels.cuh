@@ -341,6 +341,68 @@ __device__ __forceinline__ void sym_eig3(const double A[9], double w[3], double 
   for (int i = 0; i < 9; i++) V[i] = V2[i];
 }
 
+// PLANE regularisation (fast_gicp_impl.hpp:273-293: SVD of the 3x3 covariance, singular values replaced by (1, 1, 1e-3)) needs
+// only the direction n of the SMALLEST eigenvalue: U diag(1,1,1e-3) U^T = I - (1 - 1e-3) n n^T.  Instead of a full Jacobi
+// eigen-decomposition (the round-1 k_cov spent ~2500 double-precision instructions per point in it), the smallest root of the
+// characteristic polynomial of the trace-normalised matrix is found by Newton's iteration from 0 (monotone from below for a
+// positive semi-definite matrix) and n is the largest cross product of two rows of (B - lambda I).  Only +, -, *, /, sqrt in a
+// fixed order, so the CUDA kernel and the CPU oracle produce the same bits.  Where the two smallest eigenvalues coincide the
+// direction inside their plane is arbitrary -- as it is for the reference's JacobiSVD.
+__device__ __forceinline__ void plane_regularize(const double a[6] /* xx xy xz yy yz zz */, double out[6]) {
+  const double tr = a[0] + a[3] + a[5];
+  double n0 = 0.0, n1 = 0.0, n2 = 1.0;
+  if (tr > 0.0) {
+    const double inv = 1.0 / tr;
+    const double b00 = a[0] * inv, b01 = a[1] * inv, b02 = a[2] * inv, b11 = a[3] * inv, b12 = a[4] * inv, b22 = a[5] * inv;
+    const double c2 = b00 + b11 + b22;
+    const double m01 = b00 * b11 - b01 * b01, m02 = b00 * b22 - b02 * b02, m12 = b11 * b22 - b12 * b12;
+    const double c1 = m01 + m02 + m12;
+    const double c0 = b00 * m12 - b01 * (b01 * b22 - b12 * b02) + b02 * (b01 * b12 - b11 * b02);
+    double l = 0.0;
+    for (int it = 0; it < 12; it++) {
+      const double q = ((l - c2) * l + c1) * l - c0;
+      const double dq = (3.0 * l - 2.0 * c2) * l + c1;
+      if (!(dq > 0.0)) break;
+      const double step = q / dq;
+      if (step == 0.0 || !(step == step)) break;
+      l = l - step;
+    }
+    const double r00 = b00 - l, r11 = b11 - l, r22 = b22 - l;
+    // rows of B - l I: (r00 b01 b02), (b01 r11 b12), (b02 b12 r22); the null direction is orthogonal to all of them
+    const double x0 = b01 * b12 - b02 * r11, x1 = b02 * b01 - r00 * b12, x2 = r00 * r11 - b01 * b01;      // row0 x row1
+    const double y0 = b01 * r22 - b02 * b12, y1 = b02 * b02 - r00 * r22, y2 = r00 * b12 - b01 * b02;      // row0 x row2
+    const double z0 = r11 * r22 - b12 * b12, z1 = b12 * b02 - b01 * r22, z2 = b01 * b12 - r11 * b02;      // row1 x row2
+    const double nx = x0 * x0 + x1 * x1 + x2 * x2, ny = y0 * y0 + y1 * y1 + y2 * y2, nz = z0 * z0 + z1 * z1 + z2 * z2;
+    double v0 = x0, v1 = x1, v2 = x2, nn = nx;
+    if (ny > nn) { v0 = y0; v1 = y1; v2 = y2; nn = ny; }
+    if (nz > nn) { v0 = z0; v1 = z1; v2 = z2; nn = nz; }
+    if (nn > 0.0) {
+      const double s = 1.0 / sqrt(nn);
+      n0 = v0 * s; n1 = v1 * s; n2 = v2 * s;
+    } else {
+      // rank <= 1 exactly (all points on one line): any direction orthogonal to the line; the line is the largest row
+      double u0 = r00, u1 = b01, u2 = b02, un = r00 * r00 + b01 * b01 + b02 * b02;
+      const double w1 = b01 * b01 + r11 * r11 + b12 * b12, w2 = b02 * b02 + b12 * b12 + r22 * r22;
+      if (w1 > un) { u0 = b01; u1 = r11; u2 = b12; un = w1; }
+      if (w2 > un) { u0 = b02; u1 = b12; u2 = r22; un = w2; }
+      if (un > 0.0) {
+        // cross with the coordinate axis the line is least aligned with
+        const double a0 = fabs(u0), a1 = fabs(u1), a2 = fabs(u2);
+        double e0 = 1.0, e1 = 0.0, e2 = 0.0;
+        if (a1 < a0 && a1 <= a2) { e0 = 0.0; e1 = 1.0; }
+        else if (a2 < a0 && a2 < a1) { e0 = 0.0; e2 = 1.0; }
+        const double t0 = u1 * e2 - u2 * e1, t1 = u2 * e0 - u0 * e2, t2 = u0 * e1 - u1 * e0;
+        const double s = 1.0 / sqrt(t0 * t0 + t1 * t1 + t2 * t2);
+        n0 = t0 * s; n1 = t1 * s; n2 = t2 * s;
+      }
+    }
+  }
+  const double g = 1.0 - 1e-3;
+  const double g0 = g * n0, g1 = g * n1, g2 = g * n2;
+  out[0] = 1.0 - g0 * n0; out[1] = 0.0 - g0 * n1; out[2] = 0.0 - g0 * n2;
+  out[3] = 1.0 - g1 * n1; out[4] = 0.0 - g1 * n2; out[5] = 1.0 - g2 * n2;
+}
+
 // inverse of a 3x3 given row-major a[9]; same expression order as the oracle's inverse3
 __device__ __forceinline__ void inverse3(const double a[9], double r[9]) {
   double c00 = a[4] * a[8] - a[5] * a[7];
@@ -1119,12 +1181,15 @@ __global__ void __launch_bounds__(128) k_cov(const KnnParams* __restrict__ plist
 #pragma unroll
     for (int a = 0; a < 9; a++) Cn[a] = Ci[a] / nrm;
     inverse3(Cn, out);
+  } else if (P.reg == MRSLAM_REG_PLANE) {
+    const double c6[6] = {C[0], C[1], C[2], C[4], C[5], C[8]};
+    double o6[6];
+    plane_regularize(c6, o6);
+    out[0] = o6[0]; out[1] = o6[1]; out[2] = o6[2]; out[4] = o6[3]; out[5] = o6[4]; out[8] = o6[5];
   } else {
     double w[3], V[9], vals[3];
     sym_eig3(C, w, V);
-    if (P.reg == MRSLAM_REG_PLANE) {
-      vals[0] = 1.0; vals[1] = 1.0; vals[2] = 1e-3;
-    } else if (P.reg == MRSLAM_REG_MIN_EIG) {
+    if (P.reg == MRSLAM_REG_MIN_EIG) {
       vals[0] = fmax(w[0], 1e-3); vals[1] = fmax(w[1], 1e-3); vals[2] = fmax(w[2], 1e-3);
     } else {
       vals[0] = fmax(w[0] / w[0], 1e-3); vals[1] = fmax(w[1] / w[0], 1e-3); vals[2] = fmax(w[2] / w[0], 1e-3);
