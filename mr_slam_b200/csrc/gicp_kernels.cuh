@@ -655,11 +655,19 @@ __global__ void __launch_bounds__(128, 8) k_knn_search(const KnnParams* __restri
   int ncand = 0;
   if (shared_ok) {
     const int ntp = P.ntiles_pad, nsp = P.nsuper_pad;
+    // B: an upper bound of every query's k-th neighbour distance.  The k tile points closest to a query IN CURVE ORDER (a window of
+    // k consecutive positions around it) are k candidates already, so the farthest of them bounds the query's k-th distance; the
+    // Hilbert order keeps such a window much tighter than the whole tile (round 1 used the largest pairwise distance of all 32
+    // points, which put 6 % of the tiles over the 64-candidate limit and onto the per-query path below).
     float B = 0.0f;
+    {
+      const int w0 = max(0, min(lane - k / 2, TILE - k));  // window [w0, w0 + k) contains this lane (k <= 32)
 #pragma unroll 4
-    for (int j = 0; j < TILE; j++) {
-      const float px = __shfl_sync(FULL, qmine.x, j), py = __shfl_sync(FULL, qmine.y, j), pz = __shfl_sync(FULL, qmine.z, j);
-      B = fmaxf(B, dist2(qmine.x, qmine.y, qmine.z, px, py, pz));
+      for (int j = 0; j < TILE; j++) {
+        const float px = __shfl_sync(FULL, qmine.x, j), py = __shfl_sync(FULL, qmine.y, j), pz = __shfl_sync(FULL, qmine.z, j);
+        const float d = dist2(qmine.x, qmine.y, qmine.z, px, py, pz);
+        if (j >= w0 && j < w0 + k) B = fmaxf(B, d);
+      }
     }
     B = warp_max(B);
     float a[6];
