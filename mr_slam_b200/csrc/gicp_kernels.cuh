@@ -364,8 +364,9 @@ __device__ __forceinline__ void plane_regularize(const double a[6] /* xx xy xz y
       const double dq = (3.0 * l - 2.0 * c2) * l + c1;
       if (!(dq > 0.0)) break;
       const double step = q / dq;
-      if (step == 0.0 || !(step == step)) break;
+      if (!(step == step)) break;
       l = l - step;
+      if (fabs(step) <= fabs(l) * 1e-15) break;  // converged to the last bits (typically after 4-6 of the 12 steps)
     }
     const double r00 = b00 - l, r11 = b11 - l, r22 = b22 - l;
     // rows of B - l I: (r00 b01 b02), (b01 r11 b12), (b02 b12 r22); the null direction is orthogonal to all of them
@@ -1138,36 +1139,73 @@ __global__ void __launch_bounds__(128) k_cov(const KnnParams* __restrict__ plist
   if (__float_as_int(P.psort[s].w) == PAD_IDX) return;
   const int k = P.k;
   const int* ids = P.ids + (size_t)s * k;
-  // fast_gicp_impl.hpp:256-261.  (Issuing the neighbour gathers eight at a time was measured and does not help: the kernel is
-  // bound by its double-precision arithmetic -- Jacobi sweeps -- not by the latency of the 2 x k gathers.)
+  // fast_gicp_impl.hpp:256-261.  r2: the ncu profile of round 1 blamed the double-precision Jacobi, but replacing it (below) moved the
+  // kernel by 10 % only -- the two passes over the k neighbours are what costs: 2 x k dependent 16-byte gathers per point, issued one
+  // at a time.  For k <= 16 (the nodes use 15) the neighbours are fetched ONCE, all loads in flight together, and both passes run
+  // from registers, in the same summation order as before (so the results do not change by a bit).
   double mean[3] = {0.0, 0.0, 0.0};
-#pragma unroll 1
-  for (int j = 0; j < k; j++) {
-    const int id = ids[j];
-    if (id != PAD_IDX) {
-      const float4 p = P.porig[id];
-      mean[0] += (double)p.x;
-      mean[1] += (double)p.y;
-      mean[2] += (double)p.z;
-    }
-  }
-  const double dk = (double)k;
-  mean[0] /= dk; mean[1] /= dk; mean[2] /= dk;
   double C[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-#pragma unroll 1
-  for (int j = 0; j < k; j++) {
-    const int id = ids[j];
-    double dd[3];
-    if (id != PAD_IDX) {
-      const float4 p = P.porig[id];
-      dd[0] = (double)p.x - mean[0]; dd[1] = (double)p.y - mean[1]; dd[2] = (double)p.z - mean[2];
-    } else {
-      dd[0] = 0.0 - mean[0]; dd[1] = 0.0 - mean[1]; dd[2] = 0.0 - mean[2];
+  const double dk = (double)k;
+  if (k <= 16) {
+    int id[16];
+#pragma unroll
+    for (int j = 0; j < 16; j++) id[j] = j < k ? ids[j] : PAD_IDX;
+    float px[16], py[16], pz[16];
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+      float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (id[j] != PAD_IDX) p = P.porig[id[j]];
+      px[j] = p.x; py[j] = p.y; pz[j] = p.z;
     }
 #pragma unroll
-    for (int a = 0; a < 3; a++)
+    for (int j = 0; j < 16; j++)
+      if (j < k && id[j] != PAD_IDX) {
+        mean[0] += (double)px[j];
+        mean[1] += (double)py[j];
+        mean[2] += (double)pz[j];
+      }
+    mean[0] /= dk; mean[1] /= dk; mean[2] /= dk;
 #pragma unroll
-      for (int b = 0; b < 3; b++) C[3 * a + b] += dd[a] * dd[b];
+    for (int j = 0; j < 16; j++)
+      if (j < k) {
+        double dd[3];
+        if (id[j] != PAD_IDX) {
+          dd[0] = (double)px[j] - mean[0]; dd[1] = (double)py[j] - mean[1]; dd[2] = (double)pz[j] - mean[2];
+        } else {
+          dd[0] = 0.0 - mean[0]; dd[1] = 0.0 - mean[1]; dd[2] = 0.0 - mean[2];
+        }
+#pragma unroll
+        for (int a = 0; a < 3; a++)
+#pragma unroll
+          for (int b = 0; b < 3; b++) C[3 * a + b] += dd[a] * dd[b];
+      }
+  } else {
+#pragma unroll 1
+    for (int j = 0; j < k; j++) {
+      const int id = ids[j];
+      if (id != PAD_IDX) {
+        const float4 p = P.porig[id];
+        mean[0] += (double)p.x;
+        mean[1] += (double)p.y;
+        mean[2] += (double)p.z;
+      }
+    }
+    mean[0] /= dk; mean[1] /= dk; mean[2] /= dk;
+#pragma unroll 1
+    for (int j = 0; j < k; j++) {
+      const int id = ids[j];
+      double dd[3];
+      if (id != PAD_IDX) {
+        const float4 p = P.porig[id];
+        dd[0] = (double)p.x - mean[0]; dd[1] = (double)p.y - mean[1]; dd[2] = (double)p.z - mean[2];
+      } else {
+        dd[0] = 0.0 - mean[0]; dd[1] = 0.0 - mean[1]; dd[2] = 0.0 - mean[2];
+      }
+#pragma unroll
+      for (int a = 0; a < 3; a++)
+#pragma unroll
+        for (int b = 0; b < 3; b++) C[3 * a + b] += dd[a] * dd[b];
+    }
   }
 #pragma unroll
   for (int a = 0; a < 9; a++) C[a] /= dk;

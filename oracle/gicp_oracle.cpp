@@ -277,8 +277,9 @@ inline void plane_regularize(const double a[6] /* xx xy xz yy yz zz */, double o
       const double dq = (3.0 * l - 2.0 * c2) * l + c1;
       if (!(dq > 0.0)) break;
       const double step = q / dq;
-      if (step == 0.0 || !(step == step)) break;
+      if (!(step == step)) break;
       l = l - step;
+      if (std::fabs(step) <= std::fabs(l) * 1e-15) break;  // converged to the last bits (typically after 4-6 of the 12 steps)
     }
     const double r00 = b00 - l, r11 = b11 - l, r22 = b22 - l;
     // rows of B - l I: (r00 b01 b02), (b01 r11 b12), (b02 b12 r22); the null direction is orthogonal to all of them
