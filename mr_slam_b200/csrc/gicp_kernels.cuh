@@ -1209,12 +1209,23 @@ __global__ void __launch_bounds__(128) k_cov(const KnnParams* __restrict__ plist
   }
 #pragma unroll
   for (int a = 0; a < 9; a++) C[a] /= dk;
+  // the raw covariance (symmetric by construction: 6 unique numbers); k_cov_regularize turns it into the regularised one in
+  // place.  Two kernels because they want opposite things: this one keeps 16 gathers in flight per thread and needs ~130
+  // registers for it; the regularisation is a chain of dependent double-precision divisions and wants every warp slot of the SM.
+  double* co = P.cov + (size_t)s * 6;
+  co[0] = C[0]; co[1] = C[1]; co[2] = C[2]; co[3] = C[4]; co[4] = C[5]; co[5] = C[8];
+}
 
+// regularisation of the covariances written by k_cov, in place (fast_gicp_impl.hpp:264-293); grid = (ceil(npad/256), n_clouds)
+__global__ void __launch_bounds__(256) k_cov_regularize(const KnnParams* __restrict__ plist) {
+  const KnnParams P = plist[blockIdx.y];
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (P.reg == MRSLAM_REG_NONE || s >= P.ntiles * TILE) return;
+  if (__float_as_int(P.psort[s].w) == PAD_IDX) return;
+  double* co = P.cov + (size_t)s * 6;
+  const double C[9] = {co[0], co[1], co[2], co[1], co[3], co[4], co[2], co[4], co[5]};
   double out[9];
-  if (P.reg == MRSLAM_REG_NONE) {
-#pragma unroll
-    for (int a = 0; a < 9; a++) out[a] = C[a];
-  } else if (P.reg == MRSLAM_REG_FROBENIUS) {
+  if (P.reg == MRSLAM_REG_FROBENIUS) {
     double Cl[9], Ci[9], Cn[9];
 #pragma unroll
     for (int a = 0; a < 9; a++) Cl[a] = C[a];
@@ -1246,7 +1257,6 @@ __global__ void __launch_bounds__(128) k_cov(const KnnParams* __restrict__ plist
       for (int b = a; b < 3; b++)
         out[3 * a + b] = V[3 * a] * vals[0] * V[3 * b] + V[3 * a + 1] * vals[1] * V[3 * b + 1] + V[3 * a + 2] * vals[2] * V[3 * b + 2];
   }
-  double* co = P.cov + (size_t)s * 6;
   co[0] = out[0]; co[1] = out[1]; co[2] = out[2]; co[3] = out[4]; co[4] = out[5]; co[5] = out[8];
 }
 
@@ -1276,6 +1286,10 @@ struct PairParams {
 };
 
 enum { MODE_LINEARIZE = 0, MODE_FITNESS = 1 };
+#ifndef MR_NN1_WPQ
+#define MR_NN1_WPQ 1
+#endif
+constexpr int NN1_STAGE = 16;  // candidate tiles staged in shared memory per warp (8 KB); later ones are read from L2
 
 // Warp-cooperative exact NN-1 of ONE query (all lanes hold the same query); the 32 lanes evaluate the 32 points of a
 // candidate tile in parallel.  (key0,pos0) is a known candidate (seed) or (KEY_NONE,-1).  Returns the best (key,pos).
@@ -1406,6 +1420,10 @@ __global__ void __launch_bounds__(128) k_nn1_search(const PairParams* __restrict
   __shared__ double s_red[4][2];
   __shared__ float4 s_tile[4][TILE];
   __shared__ u64 s_cand[4][CAND];
+#if MR_NN1_WPQ
+  __shared__ __align__(16) float4 s_pts[4][NN1_STAGE][TILE];  // the first NN1_STAGE candidate tiles of the warp, staged once
+  __shared__ float s_cbox[4][CAND][6];                        // candidate boxes (for the per-lane need test)
+#endif
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   // MODE_LINEARIZE has no block-level step and may be launched with ONE warp per block (a block's slot is then freed when
   // its warp is done instead of when the slowest of four is); MODE_FITNESS reduces over the four warps of a block
@@ -1514,13 +1532,27 @@ __global__ void __launch_bounds__(128) k_nn1_search(const PairParams* __restrict
             const int js = __ffs(ms) - 1;
             ms &= ms - 1;
             const int t = (g0 + js) * 32 + lane;
+#if MR_NN1_WPQ
+            float tbx[6];
+#pragma unroll
+            for (int c6 = 0; c6 < 6; c6++) tbx[c6] = P.tgt_tb[(size_t)c6 * ntp + t];  // t < ntiles_pad always
+            const float gx_ = fmaxf(0.0f, fmaxf(tbx[0] - wb[3], wb[0] - tbx[3])), gy_ = fmaxf(0.0f, fmaxf(tbx[1] - wb[4], wb[1] - tbx[4])),
+                        gz_ = fmaxf(0.0f, fmaxf(tbx[2] - wb[5], wb[2] - tbx[5]));
+            const float bt = gx_ * gx_ + gy_ * gy_ + gz_ * gz_;
+#else
             const float bt = box_box_dist2(wb, P.tgt_tb, ntp, t);
+#endif
             const bool pass = t < P.tgt_ntiles && bt * CULL_SAFETY <= R0;
             const unsigned mt = __ballot_sync(FULL, pass);
             if (pass) {
               const int pos = cnt + __popc(mt & lt);
-              if (pos < CAND) s_cand[wib][pos] = ((u64)__float_as_uint(bt) << 32) | (unsigned)t;
-              else dropped = fminf(dropped, bt);
+              if (pos < CAND) {
+                s_cand[wib][pos] = ((u64)__float_as_uint(bt) << 32) | (unsigned)t;
+#if MR_NN1_WPQ
+#pragma unroll
+                for (int c6 = 0; c6 < 6; c6++) s_cbox[wib][pos][c6] = tbx[c6];
+#endif
+              } else dropped = fminf(dropped, bt);
             }
             cnt += __popc(mt);
           }
@@ -1529,6 +1561,63 @@ __global__ void __launch_bounds__(128) k_nn1_search(const PairParams* __restrict
         const float dropped_min = overflow ? warp_min(dropped) : INFINITY;
         const int n = min(cnt, CAND);
         __syncwarp();
+#if MR_NN1_WPQ
+        // r2: every coherent lane needs only the one to three candidate tiles whose box lies within ITS OWN seed distance, so the
+        // shared lane-per-query walk of round 1 (every lane scans every tile of the warp's list: 11.7 tiles x 32 points, of which
+        // one in six (lane, tile) pairs could matter) is replaced by: stage the tiles once, let every lane mark the tiles it
+        // needs, then serve the (query, tile) pairs one at a time with the whole warp (one point per lane, warp arg-min).
+        const int nst = min(n, NN1_STAGE);
+        for (int c = 0; c < nst; c++) s_pts[wib][c][lane] = P.tgt_sort[(size_t)(unsigned)(s_cand[wib][c] & 0xffffffffull) * TILE + lane];
+        unsigned need0 = 0, need1 = 0;
+        {
+          const float bestd = key_dist(bkey);
+#pragma unroll 2
+          for (int c = 0; c < n; c++) {
+            const float* bx = s_cbox[wib][c];
+            const float gx = fmaxf(0.0f, fmaxf(bx[0] - qx, qx - bx[3])), gy = fmaxf(0.0f, fmaxf(bx[1] - qy, qy - bx[4])),
+                        gz = fmaxf(0.0f, fmaxf(bx[2] - qz, qz - bx[5]));
+            const bool nd = coherent && (gx * gx + gy * gy + gz * gz) * CULL_SAFETY <= fminf(bestd, cap);
+            if (c < 32) need0 |= nd ? (1u << c) : 0u;
+            else need1 |= nd ? (1u << (c - 32)) : 0u;
+          }
+        }
+        __syncwarp();
+        unsigned todo = __ballot_sync(FULL, (need0 | need1) != 0u);
+        while (todo) {
+          const int qi = __ffs(todo) - 1;
+          todo &= todo - 1;
+          unsigned m0 = __shfl_sync(FULL, need0, qi), m1 = __shfl_sync(FULL, need1, qi);
+          const float ox = __shfl_sync(FULL, qx, qi), oy = __shfl_sync(FULL, qy, qi), oz = __shfl_sync(FULL, qz, qi);
+          u64 obest = __shfl_sync(FULL, bkey, qi);
+          int obp = __shfl_sync(FULL, bp, qi);
+          while (m0 | m1) {
+            int c;
+            if (m0) {
+              c = __ffs(m0) - 1;
+              m0 &= m0 - 1;
+            } else {
+              c = 32 + __ffs(m1) - 1;
+              m1 &= m1 - 1;
+            }
+            const int t = (int)(unsigned)(s_cand[wib][c] & 0xffffffffull);
+            const float4 c4 = c < NN1_STAGE ? s_pts[wib][c][lane] : P.tgt_sort[(size_t)t * TILE + lane];
+            const float d = dist2(ox, oy, oz, c4.x, c4.y, c4.z);
+            const unsigned hi = __float_as_uint(d), idx = (unsigned)__float_as_int(c4.w);
+            const unsigned mhi = __reduce_min_sync(FULL, hi);
+            const unsigned mlo = __reduce_min_sync(FULL, hi == mhi ? idx : 0xffffffffu);
+            const u64 cmin = ((u64)mhi << 32) | mlo;
+            if (cmin < obest) {
+              obest = cmin;
+              obp = t * TILE + (__ffs(__ballot_sync(FULL, hi == mhi && idx == mlo)) - 1);
+            }
+            tiles_done++;
+          }
+          if (lane == qi) {
+            bkey = obest;
+            bp = obp;
+          }
+        }
+#else
         u64 e0 = lane < n ? s_cand[wib][lane] : KEY_NONE;
         u64 e1 = lane + 32 < n ? s_cand[wib][lane + 32] : KEY_NONE;
         // nearest-first walk: stop as soon as the nearest remaining tile is farther than every coherent best
@@ -1545,6 +1634,7 @@ __global__ void __launch_bounds__(128) k_nn1_search(const PairParams* __restrict
           if (__uint_as_float(mhi) * CULL_SAFETY > fminf(R, cap)) break;
           scan_tile((int)mlo);
         }
+#endif
         // with an overflowing candidate list some tiles at distance >= dropped_min were never looked at:
         // coherent lanes whose best is not provably closer go to phase B
         if (overflow) {

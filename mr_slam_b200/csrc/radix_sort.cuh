@@ -36,11 +36,15 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const unsigned* __restri
   if (base < n) {
 #pragma unroll
     for (int i = 0; i < RS_ITEMS; i++) {
+      // warp-aggregated: neighbouring points land in the same few digits (cells of one scan line), which would serialise
+      // per-element shared-memory atomics; one atomic per group of equal digits in the warp instead
       const int e = base + i * RS_THREADS + threadIdx.x;
-      if (e < n) {
-        const unsigned k = keys[e];
-        if (!(use_drop && k == drop_key)) atomicAdd(&s_h[(k >> shift) & 0xffu], 1u);
-      }
+      bool live = e < n;
+      unsigned k = live ? keys[e] : 0u;
+      if (use_drop && k == drop_key) live = false;
+      const unsigned d = (k >> shift) & 0xffu;
+      const unsigned grp = __match_any_sync(FULL, live ? d : (256u + (threadIdx.x & 31u)));
+      if (live && (grp & ((1u << (threadIdx.x & 31)) - 1u)) == 0) atomicAdd(&s_h[d], (unsigned)__popc(grp));
     }
   }
   __syncthreads();

@@ -8,3 +8,6 @@ timeout 300 python scripts/time_next_rows.py > $O/next_rows.json 2> $O/next_rows
 bash scripts/ncu_all.sh $O
 timeout 300 python bench.py --workload ring --steps 10 --warmup 3 > $O/bench_ring.json 2> $O/bench_ring.err; echo "ring rc=$?"
 timeout 400 python bench.py --workload tiled --steps 5 --warmup 3 > $O/bench_tiled.json 2> $O/bench_tiled.err; echo "tiled rc=$?"
+# NN-1: per-lane need masks + warp-per-pair visits (default) vs the round-1 shared lane-per-query walk (variant)
+echo "== nn1 wpq (default)"; timeout 300 python scripts/prof_gicp.py 8 2 2>&1 | grep -E "per-kernel|nn1 pair evals" | tail -2
+echo "== nn1 lpq (variant)"; MRSLAM_LIB=$PWD/build/variants/libmrslam_nn1lpq.so timeout 300 python scripts/prof_gicp.py 8 2 2>&1 | grep -E "per-kernel|nn1 pair evals" | tail -2
