@@ -1286,8 +1286,10 @@ struct PairParams {
 };
 
 enum { MODE_LINEARIZE = 0, MODE_FITNESS = 1 };
+// r2 experiment (per-lane need masks + one warp-wide visit per (query, tile) pair): exact, but 72.6 us per pair-pass against 38.5 us
+// for the shared walk -- a query needs 4.1 tiles on average, not the 1-2 the idea counted on (132 visits per warp-pass).  Off.
 #ifndef MR_NN1_WPQ
-#define MR_NN1_WPQ 1
+#define MR_NN1_WPQ 0
 #endif
 constexpr int NN1_STAGE = 16;  // candidate tiles staged in shared memory per warp (8 KB); later ones are read from L2
 

@@ -177,7 +177,10 @@ __global__ void __launch_bounds__(256) k_ring_tiring(const float* __restrict__ s
   __syncthreads();
   const float scale = (float)(1.0 / sqrt((double)A));
   float* o = out + ((size_t)item * C + c) * A * D * 2;
-  for (int idx = threadIdx.x; idx < A * D; idx += blockDim.x) {
+  // r2: the output frequencies of one image are split over gridDim.z blocks (each stages the whole image: 58 KB, L2 hits), so a
+  // batch of 256 images gives 1024 blocks instead of 256 on 148 SMs
+  const int per = (A + gridDim.z - 1) / gridDim.z, k0 = blockIdx.z * per, k1 = min(A, k0 + per);
+  for (int idx = k0 * D + threadIdx.x; idx < k1 * D; idx += blockDim.x) {
     const int k = idx / D, d = idx - k * D;
     float re = 0.f, im = 0.f;
     int ph = 0;
@@ -194,15 +197,22 @@ __global__ void __launch_bounds__(256) k_ring_tiring(const float* __restrict__ s
 }
 
 // fast_corr(query, db[j]) for every j: grid = n_db, block = 256.  corr[t] = sum_{c,d} | 1/sqrt(A) sum_k q*conj(b) e^{+2 pi i k t/A} |
+// fast_corr (util.py:362-374), split over detector columns: block (j, z) forms the product a * conj(b) of database descriptor j
+// for ITS slice of the detector axis only (r2: the whole 2 x A x D product took 115 KB of shared memory = one 8-warp block per
+// SM; a slice of D / FC_SPLIT columns takes 29 KB, so seven blocks are resident), inverse-DFTs it along the angle axis and adds
+// its part of sum_d |.| to corr[j][t]; k_ring_corr_argmax then applies fftshift + max.
+constexpr int FC_SPLIT = 4;
 __global__ void __launch_bounds__(256) k_ring_fast_corr(const float* __restrict__ q, const float* __restrict__ db, int C, int A, int D,
-                                                       float* __restrict__ dist, int* __restrict__ angle, float* __restrict__ corr_out) {
+                                                       float* __restrict__ corr_acc /* [n_db][A], zeroed */) {
   extern __shared__ float sm[];
+  const int Ds = (D + FC_SPLIT - 1) / FC_SPLIT;
   float* tw_c = sm;            // A
   float* tw_s = sm + A;        // A
-  float* corr = sm + 2 * A;    // A (accumulated with atomics in shared memory)
-  float* pr = sm + 3 * A;      // A * D   product real (one channel at a time)
-  float* pi = pr + A * D;      // A * D
-  const int j = blockIdx.x;
+  float* corr = sm + 2 * A;    // A
+  float* pr = sm + 3 * A;      // A * Ds   product real (one channel at a time)
+  float* pi = pr + A * Ds;     // A * Ds
+  const int j = blockIdx.x, d0 = blockIdx.y * Ds, dn = min(Ds, D - d0);
+  if (dn <= 0) return;
   for (int i = threadIdx.x; i < A; i += blockDim.x) {
     double sv, cv;
     sincospi(2.0 * (double)i / (double)A, &sv, &cv);
@@ -215,18 +225,20 @@ __global__ void __launch_bounds__(256) k_ring_fast_corr(const float* __restrict_
     __syncthreads();
     const float* qa = q + (size_t)c * A * D * 2;
     const float* ba = db + ((size_t)j * C + c) * A * D * 2;
-    for (int i = threadIdx.x; i < A * D; i += blockDim.x) {
-      const float ar = qa[2 * i], ai = qa[2 * i + 1], br = ba[2 * i], bi = -ba[2 * i + 1];
-      pr[i] = ar * br - ai * bi;
-      pi[i] = fmaf(ar, bi, ai * br);
+    for (int i = threadIdx.x; i < A * dn; i += blockDim.x) {
+      const int a = i / dn, d = i - a * dn;
+      const size_t g = (size_t)a * D + d0 + d;
+      const float ar = qa[2 * g], ai = qa[2 * g + 1], br = ba[2 * g], bi = -ba[2 * g + 1];
+      pr[a * Ds + d] = ar * br - ai * bi;
+      pi[a * Ds + d] = fmaf(ar, bi, ai * br);
     }
     __syncthreads();
-    for (int idx = threadIdx.x; idx < A * D; idx += blockDim.x) {
-      const int t = idx / D, d = idx - t * D;
+    for (int idx = threadIdx.x; idx < A * dn; idx += blockDim.x) {
+      const int t = idx / dn, d = idx - t * dn;
       float re = 0.f, im = 0.f;
       int ph = 0;
       for (int k = 0; k < A; k++) {
-        const float xr = pr[k * D + d], xi = pi[k * D + d];
+        const float xr = pr[k * Ds + d], xi = pi[k * Ds + d];
         re += xr * tw_c[ph] - xi * tw_s[ph];
         im += fmaf(xr, tw_s[ph], xi * tw_c[ph]);
         ph += t;
@@ -236,29 +248,43 @@ __global__ void __launch_bounds__(256) k_ring_fast_corr(const float* __restrict_
     }
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    // fftshift1d (util.py:306-337): roll by ceil(A/2); then max / argmax (first maximum)
-    const int nsh = (A + 1) / 2;
-    int am = 0;
-    float best = corr[nsh % A];
-    for (int i = 1; i < A; i++) {
-      const float v = corr[(i + nsh) % A];
-      if (v > best) {
-        best = v;
-        am = i;
-      }
+  for (int i = threadIdx.x; i < A; i += blockDim.x) atomicAdd(&corr_acc[(size_t)j * A + i], corr[i]);
+}
+
+// fftshift1d (util.py:306-337): roll by ceil(A/2); then max / argmax (first maximum); one warp per database descriptor
+__global__ void k_ring_corr_argmax(const float* __restrict__ corr_acc, int n_db, int A, int D, float* __restrict__ dist, int* __restrict__ angle,
+                                   float* __restrict__ corr_out) {
+  const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (j >= n_db) return;
+  const float* corr = corr_acc + (size_t)j * A;
+  const int nsh = (A + 1) / 2;
+  float best = -INFINITY;
+  int am = 0;
+  for (int i = lane; i < A; i += 32) {
+    const float v = corr[(i + nsh) % A];
+    if (corr_out) corr_out[(size_t)j * A + i] = v;
+    if (v > best) {  // (first maximum of this lane's positions: they are visited in increasing order)
+      best = v;
+      am = i;
     }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(FULL, best, o);
+    const int oa = __shfl_xor_sync(FULL, am, o);
+    if (ob > best || (ob == best && oa < am)) {
+      best = ob;
+      am = oa;
+    }
+  }
+  if (lane == 0) {
     dist[j] = 1.0f - best / (float)(0.15 * A * D);
     angle[j] = -am + A / 2;
-  }
-  if (corr_out) {
-    const int nsh = (A + 1) / 2;
-    for (int i = threadIdx.x; i < A; i += blockDim.x) corr_out[(size_t)j * A + i] = corr[(i + nsh) % A];
   }
 }
 
 struct RadonScratch {
-  DevBuf<float> stats, sino, shifts;
+  DevBuf<float> stats, sino, shifts, corr;
   DevBuf<double> disco;
 };
 static RadonScratch& rs() {
@@ -295,7 +321,7 @@ static int tiring_launch(const float* d_sino, int items, int C, int A, int D, fl
     return MRSLAM_ERR_ARG;
   }
   MR_CUDA(cudaFuncSetAttribute(k_ring_tiring, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_ring_tiring<<<dim3(C, items), 256, smem, st>>>(d_sino, S.stats.p, C, A, D, d_tiring);
+  k_ring_tiring<<<dim3(C, items, 4), 256, smem, st>>>(d_sino, S.stats.p, C, A, D, d_tiring);
   count_launch(2);
   MR_CUDA(cudaGetLastError());
   return MRSLAM_OK;
@@ -484,13 +510,18 @@ int mrslam_ring_fast_corr(const float* d_query, const float* d_db, int n_db, int
   MR_CHECK(ensure_init());
   if (n_db <= 0) return MRSLAM_OK;
   std::lock_guard<std::mutex> lk(rt().mu);
-  size_t smem = ((size_t)3 * n_angles + 2 * (size_t)n_angles * det_count) * sizeof(float);
+  const int Ds = (det_count + FC_SPLIT - 1) / FC_SPLIT;
+  size_t smem = ((size_t)3 * n_angles + 2 * (size_t)n_angles * Ds) * sizeof(float);
   if (smem > 200 * 1024) {
     set_error("ring_fast_corr: descriptor %dx%d does not fit shared memory", n_angles, det_count);
     return MRSLAM_ERR_ARG;
   }
+  MR_CHECK(rs().corr.reserve((size_t)n_db * n_angles));
+  MR_CUDA(cudaMemsetAsync(rs().corr.p, 0, sizeof(float) * (size_t)n_db * n_angles, rt().stream));
   MR_CUDA(cudaFuncSetAttribute(k_ring_fast_corr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_ring_fast_corr<<<n_db, 256, smem, rt().stream>>>(d_query, d_db, channels, n_angles, det_count, d_dist, d_angle, d_corr_opt);
+  k_ring_fast_corr<<<dim3(n_db, FC_SPLIT), 256, smem, rt().stream>>>(d_query, d_db, channels, n_angles, det_count, rs().corr.p);
+  k_ring_corr_argmax<<<(n_db + 3) / 4, 128, 0, rt().stream>>>(rs().corr.p, n_db, n_angles, det_count, d_dist, d_angle, d_corr_opt);
+  count_launch(2);
   count_launch(1);
   MR_CUDA(cudaGetLastError());
   return MRSLAM_OK;

@@ -191,14 +191,13 @@ class TiledElevationMap:
         self.row_lo, self.row_hi = self.bounds[self.rank], self.bounds[self.rank + 1]
         if self.world > 1 and min(b - a for a, b in zip(self.bounds[:-1], self.bounds[1:])) < self.halo:
             raise ValueError("tiles must be at least `halo` rows high")
+        self.stream = None
         if sync is None and str(device).startswith("cuda"):
-            # rows_to_device / rows_from_device enqueue D2D copies on the LIBRARY stream while torch.cat / the collectives run
-            # on torch's and NCCL's streams: without an explicit order a gather could read half-written rows
+            # rows_to_device / rows_from_device enqueue D2D copies on the LIBRARY stream.  The torch ops and the collectives of the
+            # exchange are issued with that same stream as torch's current stream, so everything is ordered by the stream itself --
+            # no host synchronisation (the first version synchronised the device three times per exchange: 0.6 ms at 4000^2).
             from ._lib import lib
-
-            def sync():
-                lib().mrslam_device_synchronize()
-                torch.cuda.synchronize()
+            self.stream = torch.cuda.ExternalStream(lib().mrslam_stream())
         self.sync = sync if sync is not None else (lambda: None)
         emap.set_owned_rows(self.row_lo, self.row_hi)
 
@@ -219,10 +218,18 @@ class TiledElevationMap:
         for start, cnt, off in self._spans(row, t.shape[0]):
             self.m.rows_from_device(plane, start, cnt, t[off:off + cnt])
 
+    def _on_stream(self):
+        import contextlib
+        return torch.cuda.stream(self.stream) if self.stream is not None else contextlib.nullcontext()
+
     def exchange_halo(self, plane="elevation"):
         """fetch the `halo` storage rows above and below the own block from the neighbouring tiles into this replica"""
         if self.world == 1:
             return
+        with self._on_stream():
+            self._exchange_halo(plane)
+
+    def _exchange_halo(self, plane):
         h = self.halo
         dtype = torch.int32 if plane in ("R", "G", "B") else torch.float32
         mine = torch.cat([self._rows(plane, self.row_lo, h, dtype), self._rows(plane, self.row_hi - h, h, dtype)])   # top, bottom
@@ -248,6 +255,13 @@ class TiledElevationMap:
 
     def gather_full(self, planes=("elevation", "variance")):
         """assemble whole planes on every rank from the owned blocks (all_gather of padded blocks); returns {plane: tensor [L*L]}"""
+        with self._on_stream():
+            res = self._gather_full(planes)
+        if self.stream is not None:
+            self.stream.synchronize()     # the caller reads the result on its own stream / the host
+        return res
+
+    def _gather_full(self, planes):
         res = {}
         hmax = max(b - a for a, b in zip(self.bounds[:-1], self.bounds[1:]))
         for plane in planes:
