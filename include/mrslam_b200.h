@@ -201,8 +201,10 @@ typedef struct mrslam_elev_frame {
   int near_filter;
 } mrslam_elev_frame_t;
 /* nframes frames in call order (map replay, or the frames queued while a loop closure was processed): same results as
- * nframes x (Move, process_fuse_device); internally the map-independent half of frame f+1 (transform, sensor variance, sort by
- * cell) overlaps the per-cell recurrence of frame f on a second stream.  No host synchronisation; counts go to fused_total. */
+ * nframes x (Move, process_fuse_device), bit for bit, but fused in ONE pass per group of <= 64 frames: the Moves are planned on
+ * the host, all frames are processed by one launch, all their points are sorted by cell once (library's own stable radix sort,
+ * invalid points dropped in its first pass), and one run walk applies the per-frame clamps and the Moves' clears in order.
+ * No host synchronisation; counts go to fused_total. */
 int mrslam_elev_process_fuse_device_batch(mrslam_elev_t*, const mrslam_elev_frame_t* frames, int nframes, float resolution, int length);
 /* The same replay with its map-writing half on the map's own stream instead of mrslam_stream(): the call returns after the
  * enqueue and an unrelated batch (a loop-closure storm on the library stream) runs concurrently with it.  Inputs must be

@@ -247,8 +247,6 @@ static int dispatch_knn(int k, const KnnParams* d_params, int nproblems, int max
     ProfScope ps(PROF_COV);
     k_cov<<<dim3((max_tiles * TILE + 127) / 128, nproblems), 128, 0, rt().stream>>>(d_params);
     count_launch(1);
-    k_cov_regularize<<<dim3((max_tiles * TILE + 255) / 256, nproblems), 256, 0, rt().stream>>>(d_params);  // no-op blocks for REG_NONE clouds
-    count_launch(1);
   }
   MR_CUDA(cudaGetLastError());
   return MRSLAM_OK;

@@ -1131,6 +1131,45 @@ __global__ void __launch_bounds__(32) k_knn_search_v2(const KnnParams* __restric
 // 5x slower here: with 32 neighbouring queries almost every scanned candidate enters SOME lane's list, so the whole warp
 // executes the O(k) register insertion for nearly every candidate.  The warp-shuffle k-min above stays the kNN kernel.)
 
+// regularisation of a neighbourhood covariance (fast_gicp_impl.hpp:264-293); C symmetric 3x3 row-major, out: upper triangle valid
+__device__ __forceinline__ void regularize_cov(int reg, const double C[9], double out[9]) {
+  if (reg == MRSLAM_REG_NONE) {
+#pragma unroll
+    for (int a = 0; a < 9; a++) out[a] = C[a];
+  } else if (reg == MRSLAM_REG_FROBENIUS) {
+    double Cl[9], Ci[9], Cn[9];
+#pragma unroll
+    for (int a = 0; a < 9; a++) Cl[a] = C[a];
+    Cl[0] += 1e-3; Cl[4] += 1e-3; Cl[8] += 1e-3;
+    inverse3(Cl, Ci);
+    double nrm = 0.0;
+#pragma unroll
+    for (int a = 0; a < 9; a++) nrm += Ci[a] * Ci[a];
+    nrm = sqrt(nrm);
+#pragma unroll
+    for (int a = 0; a < 9; a++) Cn[a] = Ci[a] / nrm;
+    inverse3(Cn, out);
+  } else if (reg == MRSLAM_REG_PLANE) {
+    const double c6[6] = {C[0], C[1], C[2], C[4], C[5], C[8]};
+    double o6[6];
+    plane_regularize(c6, o6);
+    out[0] = o6[0]; out[1] = o6[1]; out[2] = o6[2]; out[4] = o6[3]; out[5] = o6[4]; out[8] = o6[5];
+  } else {
+    double w[3], V[9], vals[3];
+    sym_eig3(C, w, V);
+    if (reg == MRSLAM_REG_MIN_EIG) {
+      vals[0] = fmax(w[0], 1e-3); vals[1] = fmax(w[1], 1e-3); vals[2] = fmax(w[2], 1e-3);
+    } else {
+      vals[0] = fmax(w[0] / w[0], 1e-3); vals[1] = fmax(w[1] / w[0], 1e-3); vals[2] = fmax(w[2] / w[0], 1e-3);
+    }
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+#pragma unroll
+      for (int b = a; b < 3; b++)
+        out[3 * a + b] = V[3 * a] * vals[0] * V[3 * b] + V[3 * a + 1] * vals[1] * V[3 * b + 1] + V[3 * a + 2] * vals[2] * V[3 * b + 2];
+  }
+}
+
 // covariance of the k neighbours (double), one thread per SORTED point; grid = (ceil(npad/128), n_clouds)
 __global__ void __launch_bounds__(128) k_cov(const KnnParams* __restrict__ plist) {
   const KnnParams P = plist[blockIdx.y];
@@ -1209,56 +1248,14 @@ __global__ void __launch_bounds__(128) k_cov(const KnnParams* __restrict__ plist
   }
 #pragma unroll
   for (int a = 0; a < 9; a++) C[a] /= dk;
-  // the raw covariance (symmetric by construction: 6 unique numbers); k_cov_regularize turns it into the regularised one in
-  // place.  Two kernels because they want opposite things: this one keeps 16 gathers in flight per thread and needs ~130
-  // registers for it; the regularisation is a chain of dependent double-precision divisions and wants every warp slot of the SM.
-  double* co = P.cov + (size_t)s * 6;
-  co[0] = C[0]; co[1] = C[1]; co[2] = C[2]; co[3] = C[4]; co[4] = C[5]; co[5] = C[8];
-}
-
-// regularisation of the covariances written by k_cov, in place (fast_gicp_impl.hpp:264-293); grid = (ceil(npad/256), n_clouds)
-__global__ void __launch_bounds__(256) k_cov_regularize(const KnnParams* __restrict__ plist) {
-  const KnnParams P = plist[blockIdx.y];
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (P.reg == MRSLAM_REG_NONE || s >= P.ntiles * TILE) return;
-  if (__float_as_int(P.psort[s].w) == PAD_IDX) return;
-  double* co = P.cov + (size_t)s * 6;
-  const double C[9] = {co[0], co[1], co[2], co[1], co[3], co[4], co[2], co[4], co[5]};
+  // (r2: splitting the regularisation into a second, high-occupancy kernel was measured and lost -- 0.285 vs 0.254 ms per 16
+  // clouds: the extra 96 B/pt round trip costs more than the occupancy gains)
   double out[9];
-  if (P.reg == MRSLAM_REG_FROBENIUS) {
-    double Cl[9], Ci[9], Cn[9];
-#pragma unroll
-    for (int a = 0; a < 9; a++) Cl[a] = C[a];
-    Cl[0] += 1e-3; Cl[4] += 1e-3; Cl[8] += 1e-3;
-    inverse3(Cl, Ci);
-    double nrm = 0.0;
-#pragma unroll
-    for (int a = 0; a < 9; a++) nrm += Ci[a] * Ci[a];
-    nrm = sqrt(nrm);
-#pragma unroll
-    for (int a = 0; a < 9; a++) Cn[a] = Ci[a] / nrm;
-    inverse3(Cn, out);
-  } else if (P.reg == MRSLAM_REG_PLANE) {
-    const double c6[6] = {C[0], C[1], C[2], C[4], C[5], C[8]};
-    double o6[6];
-    plane_regularize(c6, o6);
-    out[0] = o6[0]; out[1] = o6[1]; out[2] = o6[2]; out[4] = o6[3]; out[5] = o6[4]; out[8] = o6[5];
-  } else {
-    double w[3], V[9], vals[3];
-    sym_eig3(C, w, V);
-    if (P.reg == MRSLAM_REG_MIN_EIG) {
-      vals[0] = fmax(w[0], 1e-3); vals[1] = fmax(w[1], 1e-3); vals[2] = fmax(w[2], 1e-3);
-    } else {
-      vals[0] = fmax(w[0] / w[0], 1e-3); vals[1] = fmax(w[1] / w[0], 1e-3); vals[2] = fmax(w[2] / w[0], 1e-3);
-    }
-#pragma unroll
-    for (int a = 0; a < 3; a++)
-#pragma unroll
-      for (int b = a; b < 3; b++)
-        out[3 * a + b] = V[3 * a] * vals[0] * V[3 * b] + V[3 * a + 1] * vals[1] * V[3 * b + 1] + V[3 * a + 2] * vals[2] * V[3 * b + 2];
-  }
+  regularize_cov(P.reg, C, out);
+  double* co = P.cov + (size_t)s * 6;
   co[0] = out[0]; co[1] = out[1]; co[2] = out[2]; co[3] = out[4]; co[4] = out[5]; co[5] = out[8];
 }
+
 
 // ---------------------------------------------------------------------------------------------
 // NN-1 correspondence search (warp per query tile), then Mahalanobis + J^T M J / J^T M e / cost as a
