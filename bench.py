@@ -42,6 +42,9 @@ RING_SCANS, RING_BASE = int(os.environ.get("BENCH_RING_SCANS", 256)), int(os.env
 TILED_L, TILED_RES = int(os.environ.get("BENCH_TILED_L", 4000)), 0.05
 TILED_FRAMES, TILED_BASE = int(os.environ.get("BENCH_TILED_FRAMES", 84)), int(os.environ.get("BENCH_TILED_BASE", 28))
 SM_COUNT = 148
+# NVML sampling cadence inside the timed steps (1 = every step).  Development knob: with several ranks on one host the NVML
+# queries of all ranks go through one driver lock.
+SAMPLE_EVERY = int(os.environ.get("BENCH_SAMPLE_EVERY", 1))
 # measured under ncu (profiles/r2_summary.txt): warp-instructions per query of the two search kernels, DRAM bytes per cloud
 KNN_WARP_INST_PER_QUERY = float(os.environ.get("BENCH_KNN_INST", 701.0))
 NN1_WARP_INST_PER_QUERY = float(os.environ.get("BENCH_NN1_INST", 160.0))
@@ -81,11 +84,18 @@ def peaks():
 
 
 def make_pairs(rank, n_pairs):
+    """The pair set of robot `rank`.  By default every robot refines the SAME 32 pairs (synth seeds 0..n_pairs-1): weak scaling is
+    defined on equal work per GPU, and the work of a GICP batch depends on its data -- independent pair sets (round 1:
+    seeds rank*1000+i) have different Levenberg-Marquardt iteration counts, and the same 32-pair step takes 13.7 ... 17.9 ms on ONE
+    GPU depending on the set (profiles/r2_summary.txt), which showed up as a "scaling efficiency" of 0.79 at N=4 although no rank
+    waited for anything.  (A rigid copy per rank does not help: the convergence test of lsq_registration_impl.hpp:84-94 is not
+    invariant under a change of frame.)  The clouds still travel between the ranks.  BENCH_DISTINCT_DATA=1 restores independent sets."""
     from mr_slam_b200 import synth
+    seed0 = rank * 1000 if os.environ.get("BENCH_DISTINCT_DATA") else 0
     out = []
     for i in range(n_pairs):
-        src, tgt, T_gt, T_guess, P_a, P_b = synth.make_pair(rank * 1000 + i, "hdl64", N_POINTS)
-        out.append(dict(src=src, tgt=tgt, T_gt=T_gt, guess=T_guess.astype(np.float32), pose=P_b))
+        src, tgt, T_gt, T_guess, P_a, P_b = synth.make_pair(seed0 + i, "hdl64", N_POINTS)
+        out.append(dict(src=src, tgt=tgt, T_gt=T_gt, guess=T_guess.astype(np.float32), pose=P_b, scan=src))
     return out
 
 
@@ -97,6 +107,7 @@ def config_for(workload, n_pairs, world, near_filter=True):
                 "pairs_per_rank": n_pairs, "points_per_scan": N_POINTS, "k": K_CORR, "max_iter": MAX_ITER, "max_corr_m": MAX_CORR,
                 "trans_eps": TRANS_EPS, "elevation_grid": "%dx%d @ %.2f m" % (ELEV_L, ELEV_L, ELEV_RES), "near_filter": bool(near_filter),
                 "parallelism": "robot-per-gpu x%d" % world,
+                "data": "every robot refines the same %d pairs (equal work per GPU; independent sets differ by up to 30 %% in step time on one GPU)" % n_pairs,
                 "exchange": "none (single robot)" if world == 1 else
                             "one neighbour-to-neighbour NCCL send/recv of the %d candidate clouds (%.1f MB) per rank and step"
                             % (n_pairs, n_pairs * N_POINTS * 12 / 1e6),
@@ -201,7 +212,7 @@ def oracle_elev_sample(pairs, n_sample, om=None, near_filter=True):
     t0 = time.perf_counter()
     for p in pairs[:n_sample]:
         ei = synth.elevation_inputs(p["pose"])
-        x, y, z = (np.ascontiguousarray(p["src"][:, i]) for i in range(3))
+        x, y, z = (np.ascontiguousarray(p.get("scan", p["src"])[:, i]) for i in range(3))
         om.move(p["pose"][:3, 3].astype(np.float32))
         r = om.process_points(x, y, z, ei["T"], p["pose"][2, 3] - 5.0, p["pose"][2, 3] + 5.0, ei["min_r"], ei["beam_a"], ei["beam_c"],
                               ei["sensorJacobian"], ei["rotationVariance"], ei["C_SB_transpose"], ei["P_mul_C_BM_transpose"],
@@ -459,20 +470,22 @@ def run_cfg2(args):
     near_filter = not args.near_filter_off
 
     n_pairs = args.pairs
-    pairs = make_pairs(rank, n_pairs)
+    # BENCH_DATA_RANK (development): run another rank's pair set on this GPU -- the LM iteration counts, and with them the step
+    # time, depend on the pairs, so ranks with different data do different amounts of work
+    data_rank = env_int("BENCH_DATA_RANK", rank) if world == 1 else rank
+    pairs = make_pairs(data_rank, n_pairs)
     guesses = np.stack([p["guess"] for p in pairs])
     # device-resident inputs: this robot's source scans and the candidate clouds it offers to its neighbour
     src_dev = torch.from_numpy(np.stack([p["src"] for p in pairs])).to(dev)           # [P, N, 3]
     # rank q holds (and offers) the keyframes that robot (q-1) % world matches against: the targets of that rank's pairs
-    offer_pairs = pairs if world == 1 else make_pairs((rank - 1) % world, n_pairs)
+    offer_pairs = pairs if (world == 1 or not os.environ.get("BENCH_DISTINCT_DATA")) else make_pairs((rank - 1) % world, n_pairs)
     offer_dev = torch.from_numpy(np.stack([p["tgt"] for p in offer_pairs])).to(dev)
-    del offer_pairs
     recv_dev = torch.empty_like(offer_dev) if world > 1 else None
     # pinned host copies for the e2e path
     src_host = [torch.from_numpy(p["src"]).pin_memory() for p in pairs]
     tgt_host = [torch.from_numpy(p["tgt"]).pin_memory() for p in pairs]
-    soa_dev = [torch.from_numpy(np.ascontiguousarray(p["src"].T)).to(dev) for p in pairs]  # elevation inputs x,y,z SoA
-    soa_host = [torch.from_numpy(np.ascontiguousarray(p["src"].T)).pin_memory().numpy() for p in pairs]  # page-locked x,y,z
+    soa_dev = [torch.from_numpy(np.ascontiguousarray(p["scan"].T)).to(dev) for p in pairs]  # elevation inputs x,y,z SoA (sensor frame)
+    soa_host = [torch.from_numpy(np.ascontiguousarray(p["scan"].T)).pin_memory().numpy() for p in pairs]  # page-locked x,y,z
     pin = lambda dt: torch.zeros(N_POINTS, dtype=dt).pin_memory().numpy()
     elev_out = (pin(torch.int32), pin(torch.float32), pin(torch.float32), pin(torch.float32), pin(torch.float32))
     zeros_i_pin, zeros_f_pin = pin(torch.int32), pin(torch.float32)
@@ -503,6 +516,7 @@ def run_cfg2(args):
                                                      position=pairs[i]["pose"][:3, 3].astype(np.float32)) for i in range(n_pairs)]
     ev = C.ev
     exch_ms = [0.0]
+    step_no = [0]
     sampler = C.sampler
 
     def step_device(overlap=True, sample_clocks=False, local_targets=None):
@@ -528,8 +542,9 @@ def run_cfg2(args):
         for g, cs in zip(regs, src_clouds):
             g.set_input_source(cs)
         pygicp.prepare_batch(regs, pygicp.SOURCE)
-        if sample_clocks:
+        if sample_clocks and (len(sampler.samples) < 1 or SAMPLE_EVERY <= 1 or step_no[0] % SAMPLE_EVERY == 0):
             sampler.sample()      # the source kNN (ALU-bound work) is running on the GPU right now
+        step_no[0] += 1
         C.record(e1)
         # the robot's scans replayed into its map by one call (frames pipelined inside the library)
         emap.process_fuse_device_batch(elev_frames, ELEV_RES, ELEV_L, asynchronous=overlap)
