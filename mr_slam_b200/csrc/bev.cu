@@ -13,12 +13,12 @@
 //     each run in point order (exactly the reference's sequential semantics).
 // Points whose voxel index falls outside the grid (x == 1.0 exactly, |z| > max_height for the polar variant)
 // make the reference write out of bounds; they are skipped here (documented in DESIGN.md).
-#include <cub/device/device_radix_sort.cuh>
 
 #include <algorithm>
 #include <vector>
 
 #include "common.cuh"
+#include "radix_sort.cuh"
 
 namespace mrslam {
 
@@ -285,7 +285,7 @@ __global__ void k_voxelfeat_bev(const float* __restrict__ pt, VoxCfg c, int feat
 struct BevScratch {
   DevBuf<float> pts, out;
   DevBuf<int> a, b, keys, keys_alt, vals, vals_alt, layer;
-  DevBuf<unsigned char> cubtmp;
+  RadixScratch rsort;
   DevBuf<long long> offsets;
 };
 static BevScratch& bs() {
@@ -296,13 +296,13 @@ static BevScratch& bs() {
 static int sort_pairs(BevScratch& S, int n, int maxkey, const int** keys_out, const int** vals_out) {
   int bits = 1;
   while ((1ll << bits) <= maxkey) bits++;
-  cub::DoubleBuffer<int> dk(S.keys.p, S.keys_alt.p), dv(S.vals.p, S.vals_alt.p);
-  size_t tmp = 0;
-  MR_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp, dk, dv, n, 0, bits, rt().stream));
-  MR_CHECK(S.cubtmp.reserve(tmp));
-  MR_CUDA(cub::DeviceRadixSort::SortPairs(S.cubtmp.p, tmp, dk, dv, n, 0, bits, rt().stream));
-  *keys_out = dk.Current();
-  *vals_out = dv.Current();
+  // the library's own stable radix sort (csrc/radix_sort.cuh)
+  unsigned *ks = nullptr, *vs = nullptr;
+  const int* d_n = nullptr;
+  MR_CHECK(radix_sort_pairs(S.rsort, (unsigned*)S.keys.p, (unsigned*)S.vals.p, (unsigned*)S.keys_alt.p, (unsigned*)S.vals_alt.p, n, nullptr, 0,
+                            ((bits + 7) / 8) * 8, 0u, 0, rt().stream, &ks, &vs, &d_n));
+  *keys_out = (const int*)ks;
+  *vals_out = (const int*)vs;
   return MRSLAM_OK;
 }
 

@@ -18,7 +18,6 @@
 // Kernels: k_kf_transform (all keyframes of a merge in one launch, blockIdx.y = keyframe) -> k_kf_minmax -> k_kf_keys ->
 // CUB radix sort (library) -> k_kf_heads + CUB exclusive scan -> k_kf_centroids (one thread per voxel run).  HBM bound:
 // 16 B/pt in, 16 B/pt staged, 8 B/pt per sort pass, 16 B per output voxel.
-#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
 #include <algorithm>
@@ -28,6 +27,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "radix_sort.cuh"
 
 namespace mrslam {
 
@@ -189,6 +189,7 @@ struct KfScratch {
   DevBuf<int> valid, keys, keys_alt, vals, vals_alt, head, pos;
   DevBuf<unsigned> mm;
   DevBuf<unsigned char> tmp;
+  RadixScratch rsort;
   DevBuf<float> staging;  // host inputs
   DevBuf<unsigned char> bytes;
 };
@@ -313,13 +314,17 @@ int mrslam_keyframe_merge(const float* const* clouds, const int* n, int stride_f
   g.mul[2] = div_b[0] * div_b[1];
   k_kf_keys<<<(N + 255) / 256, 256, 0, st>>>(S.cat.p, S.valid.p, N, g, S.keys.p, S.vals.p);
   count_launch(1);
-  cub::DoubleBuffer<int> dk(S.keys.p, S.keys_alt.p), dv(S.vals.p, S.vals_alt.p);
-  MR_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk, dv, N, 0, 31, st));
+  // stable sort by voxel key with the library's own radix sort (csrc/radix_sort.cuh); the head scan stays a library scan
+  unsigned *ks = nullptr, *vs = nullptr;
+  const int* d_ns = nullptr;
+  MR_CHECK(radix_sort_pairs(S.rsort, (unsigned*)S.keys.p, (unsigned*)S.vals.p, (unsigned*)S.keys_alt.p, (unsigned*)S.vals_alt.p, N, nullptr, 0, 32, 0u, 0,
+                            st, &ks, &vs, &d_ns));
+  const int* keys_sorted = (const int*)ks;
+  const int* vals_sorted = (const int*)vs;
   size_t scan_bytes = 0;
   MR_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, S.head.p, S.pos.p, N, st));
   MR_CHECK(S.tmp.reserve(std::max(tmp_bytes, scan_bytes)));
-  MR_CUDA(cub::DeviceRadixSort::SortPairs(S.tmp.p, tmp_bytes, dk, dv, N, 0, 31, st));
-  k_kf_heads<<<(N + 255) / 256, 256, 0, st>>>(dk.Current(), N, S.head.p);
+  k_kf_heads<<<(N + 255) / 256, 256, 0, st>>>(keys_sorted, N, S.head.p);
   MR_CUDA(cub::DeviceScan::ExclusiveSum(S.tmp.p, scan_bytes, S.head.p, S.pos.p, N, st));
   count_launch(1);
   // number of voxels = pos[N-1] + head[N-1]
@@ -332,7 +337,7 @@ int mrslam_keyframe_merge(const float* const* clouds, const int* n, int stride_f
     set_error("keyframe_merge: output needs %d points, capacity %d", result, capacity);
     return MRSLAM_ERR_ARG;
   }
-  k_kf_centroids<<<(N + 127) / 128, 128, 0, st>>>(dk.Current(), dv.Current(), S.head.p, S.pos.p, N, S.cat.p, reinterpret_cast<float4*>(d_out_xyzi));
+  k_kf_centroids<<<(N + 127) / 128, 128, 0, st>>>(keys_sorted, vals_sorted, S.head.p, S.pos.p, N, S.cat.p, reinterpret_cast<float4*>(d_out_xyzi));
   count_launch(1);
   MR_CUDA(cudaGetLastError());
   *n_out = result;

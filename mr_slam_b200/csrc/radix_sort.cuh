@@ -25,7 +25,7 @@ struct RadixScratch {
 __device__ __forceinline__ int rs_count(const int* d_n, int n_max) { return d_n ? min(*d_n, n_max) : n_max; }
 
 // per-block digit histogram; hist[d * nblk + b]
-__global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const unsigned* __restrict__ keys, const int* __restrict__ d_n, int n_max, int nblk,
+static __global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const unsigned* __restrict__ keys, const int* __restrict__ d_n, int n_max, int nblk,
                                                         int shift, unsigned drop_key, int use_drop, unsigned* __restrict__ hist) {
   __shared__ unsigned s_h[RS_BINS];
   const int n = rs_count(d_n, n_max);
@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const unsigned* __restri
 }
 
 // exclusive scan inside chunks of RS_SCAN_CHUNK consecutive table entries (digit-major order = output order); chunk totals out
-__global__ void __launch_bounds__(RS_SCAN_CHUNK) k_rs_scan_chunks(unsigned* __restrict__ hist, int total, unsigned* __restrict__ chunk) {
+static __global__ void __launch_bounds__(RS_SCAN_CHUNK) k_rs_scan_chunks(unsigned* __restrict__ hist, int total, unsigned* __restrict__ chunk) {
   __shared__ unsigned s_w[RS_SCAN_CHUNK / 32];
   const int e = blockIdx.x * RS_SCAN_CHUNK + threadIdx.x;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(RS_SCAN_CHUNK) k_rs_scan_chunks(unsigned* __re
 }
 
 // exclusive scan of the chunk totals by one block (any number of chunks: serial over tiles of 1024); grand total -> *d_n_out
-__global__ void __launch_bounds__(1024) k_rs_scan_totals(unsigned* __restrict__ chunk, int nchunks, int* __restrict__ d_n_out) {
+static __global__ void __launch_bounds__(1024) k_rs_scan_totals(unsigned* __restrict__ chunk, int nchunks, int* __restrict__ d_n_out) {
   __shared__ unsigned s_w[32];
   __shared__ unsigned s_carry;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(1024) k_rs_scan_totals(unsigned* __restrict__ 
 
 // stable scatter: destination = offset of (digit, block) + rank of the element among the block's elements of that digit that
 // precede it.  Warp w owns elements [w*256, w*256+256) of the tile, visited 32 at a time in order.
-__global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const unsigned* __restrict__ keys, const unsigned* __restrict__ vals,
+static __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const unsigned* __restrict__ keys, const unsigned* __restrict__ vals,
                                                            const int* __restrict__ d_n, int n_max, int nblk, int shift, unsigned drop_key,
                                                            int use_drop, const unsigned* __restrict__ hist, const unsigned* __restrict__ chunk,
                                                            unsigned* __restrict__ keys_out, unsigned* __restrict__ vals_out) {
