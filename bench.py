@@ -588,15 +588,15 @@ def run_cfg2(args):
         per-point outputs of Process_points never leave the GPU)."""
         e0, e1 = ev(), ev()
         C.record(e0)
-        with torch.cuda.stream(copy_stream):
+        regs = new_regs()
+        for i, g in enumerate(regs):
+            g.set_input_source(src_host[i].numpy())       # uploads on the library's copy stream, first in the PCIe queue:
+        pygicp.prepare_batch(regs, pygicp.SOURCE)         # ... the source kNN can start as soon as they have landed
+        with torch.cuda.stream(copy_stream):              # the elevation scans and the target clouds go up under it
             for i in range(n_pairs):
                 stage_soa[i].copy_(soa_pin_t[i], non_blocking=True)
             up = torch.cuda.Event()
             up.record()
-        regs = new_regs()
-        for i, g in enumerate(regs):
-            g.set_input_source(src_host[i].numpy())
-        pygicp.prepare_batch(regs, pygicp.SOURCE)
         for i, g in enumerate(regs):
             g.set_input_target(tgt_host[i].numpy())
         lib_stream.wait_event(up)

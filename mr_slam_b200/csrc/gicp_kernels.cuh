@@ -1699,7 +1699,10 @@ __global__ void __launch_bounds__(128) k_nn1_search(const PairParams* __restrict
 }
 
 // Mahalanobis + linearisation terms, one thread per SORTED source point.  grid = (ceil(src_ntiles/4), n_active)
-__global__ void __launch_bounds__(128) k_linearize(const PairParams* __restrict__ plist, const int* __restrict__ active,
+#ifndef MR_LIN_MINBLK
+#define MR_LIN_MINBLK 1
+#endif
+__global__ void __launch_bounds__(128, MR_LIN_MINBLK) k_linearize(const PairParams* __restrict__ plist, const int* __restrict__ active,
                                                    const double* __restrict__ Tbuf) {
   const int pid = active[blockIdx.y];
   const PairParams P = plist[pid];

@@ -2,7 +2,7 @@
 First launch of every kernel name: duration, DRAM bytes and throughput, SM / issue utilisation, occupancy, registers, instructions."""
 import csv, io, subprocess, sys, collections
 rep = sys.argv[1]
-want = {"gpu__time_duration.sum": "dur_us", "dram__bytes_read.sum": "dram_rd_MB", "dram__bytes_write.sum": "dram_wr_MB",
+want = {"gpu__time_duration.sum": "dur_us", "dram__bytes_read.sum": "dram_rd_MB", "dram__bytes_write.sum": "dram_wr_MB", "dram__bytes.sum.per_second": "dram_GBps",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed": "dram_pct", "sm__throughput.avg.pct_of_peak_sustained_elapsed": "sm_pct",
         "smsp__issue_active.avg.pct_of_peak_sustained_active": "issue_pct", "sm__warps_active.avg.pct_of_peak_sustained_active": "occ_pct",
         "launch__registers_per_thread": "regs", "smsp__inst_executed.sum": "warp_inst", "launch__grid_size": "grid", "launch__block_size": "block",
@@ -26,9 +26,10 @@ for r in rows[2:]:
         except ValueError: continue
         u = units[c]
         if m == "gpu__time_duration.sum": v = v / 1e3 if u in ("ns", "nsecond") else (v * 1e3 if u in ("ms", "msecond") else v)
-        if m.startswith("dram__bytes"): v = {"byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3}.get(u, 1e-6) * v
+        if m == "dram__bytes.sum.per_second": v = {"byte/s": 1e-9, "Kbyte/s": 1e-6, "Mbyte/s": 1e-3, "Gbyte/s": 1.0, "Tbyte/s": 1e3}.get(u, 1e-9) * v
+        elif m.startswith("dram__bytes"): v = {"byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3}.get(u, 1e-6) * v
         a[want[m]] = v
-keys = ["dur_us", "dram_rd_MB", "dram_wr_MB", "dram_pct", "sm_pct", "issue_pct", "occ_pct", "fp64_pct", "regs", "warp_inst", "grid", "block", "n"]
+keys = ["dur_us", "dram_GBps", "dram_pct", "sm_pct", "issue_pct", "occ_pct", "fp64_pct", "regs", "warp_inst", "grid", "block", "n"]
 print("%-34s" % "kernel" + "".join("%12s" % k for k in keys))
 for name, a in seen.items():
     print("%-34s" % name[:34] + "".join(("%12.4g" % a[k]) if isinstance(a.get(k), float) else ("%12s" % a.get(k, "-")) for k in keys))
