@@ -529,7 +529,19 @@ struct Elev {
     ev_start = ev_done = nullptr;
     pending_join = false;
   }
-  int reserve_batch(size_t total, int nframes) {
+  // Returns (through *grew) whether any device buffer was (re)allocated: DevBuf allocates in LIBRARY-stream order, so a replay
+  // that runs on the map's own stream must be ordered behind the library stream once after a growth (never in steady state).
+  int reserve_batch(size_t total, int nframes, bool* grew) {
+    const size_t caps0 = pzt.cap + pvar.cap + keys.cap + keys_alt.cap + vals.cap + vals_alt.cap + ghv.cap + gfr.cap + counter.cap + d_frames.cap +
+                         d_ctab.cap + d_clr.cap + rsort.hist.cap + rsort.chunk.cap + rsort.count.cap;
+    MR_CHECK(reserve_batch_(total, nframes));
+    MR_CHECK(radix_reserve(rsort, (int)std::max<size_t>(total, 1)));
+    const size_t caps1 = pzt.cap + pvar.cap + keys.cap + keys_alt.cap + vals.cap + vals_alt.cap + ghv.cap + gfr.cap + counter.cap + d_frames.cap +
+                         d_ctab.cap + d_clr.cap + rsort.hist.cap + rsort.chunk.cap + rsort.count.cap;
+    *grew = caps1 != caps0;
+    return MRSLAM_OK;
+  }
+  int reserve_batch_(size_t total, int nframes) {
     size_t t = std::max<size_t>(total, 1);
     MR_CHECK(pzt.reserve(t)); MR_CHECK(pvar.reserve(t));
     MR_CHECK(keys.reserve(t)); MR_CHECK(keys_alt.reserve(t)); MR_CHECK(vals.reserve(t)); MR_CHECK(vals_alt.reserve(t));
@@ -885,7 +897,12 @@ static int elev_group_onepass(Elev* m, const mrslam_elev_frame_t* frames, int nf
     return MRSLAM_ERR_ARG;
   }
   MR_CHECK(m->batch_fence.wait());
-  MR_CHECK(m->reserve_batch(total, nframes));
+  bool grew = false;
+  MR_CHECK(m->reserve_batch(total, nframes, &grew));
+  if (grew && st != rt().stream) {  // fresh allocations exist in library-stream order only
+    MR_CUDA(cudaEventRecord(m->ev_start, rt().stream));
+    MR_CUDA(cudaStreamWaitEvent(st, m->ev_start, 0));
+  }
   unsigned long long* rowclr = m->h_clr.p;
   unsigned long long* colclr = m->h_clr.p + L;
   memset(m->h_clr.p, 0, sizeof(unsigned long long) * 2 * (size_t)L);

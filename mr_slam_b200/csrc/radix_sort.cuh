@@ -177,6 +177,16 @@ static __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const unsigned
     }
 }
 
+// scratch for up to n_max elements (allocations are ordered on the library stream, see DevBuf)
+inline int radix_reserve(RadixScratch& S, int n_max) {
+  const int nblk = std::max(1, (n_max + RS_TILE - 1) / RS_TILE);
+  const int total = RS_BINS * nblk;
+  MR_CHECK(S.hist.reserve((size_t)total));
+  MR_CHECK(S.chunk.reserve((size_t)((total + RS_SCAN_CHUNK - 1) / RS_SCAN_CHUNK)));
+  MR_CHECK(S.count.reserve(2));
+  return MRSLAM_OK;
+}
+
 // Sorts by key bits [begin_bit, end_bit).  n_max = capacity (grid size); d_n_in = element count on the device (null: n_max).
 // Elements whose key equals drop_key are removed in the first pass when use_drop != 0.  Buffers a = input, b = scratch; the
 // sorted pairs end up in *keys_sorted / *vals_sorted (one of the two buffers) and their count in *d_n_sorted (device).
@@ -186,9 +196,7 @@ inline int radix_sort_pairs(RadixScratch& S, unsigned* keys_a, unsigned* vals_a,
   const int nblk = std::max(1, (n_max + RS_TILE - 1) / RS_TILE);
   const int total = RS_BINS * nblk;
   const int nchunks = (total + RS_SCAN_CHUNK - 1) / RS_SCAN_CHUNK;
-  MR_CHECK(S.hist.reserve((size_t)total));
-  MR_CHECK(S.chunk.reserve((size_t)nchunks));
-  MR_CHECK(S.count.reserve(2));
+  MR_CHECK(radix_reserve(S, n_max));
   const int* d_n = d_n_in;
   unsigned *ki = keys_a, *vi = vals_a, *ko = keys_b, *vo = vals_b;
   int pass = 0;
