@@ -62,14 +62,14 @@ __device__ __forceinline__ bool cell_of(const ElevGeom& g, float px, float py, i
   return ix >= 0 && ix < g.L && iy >= 0 && iy < g.L;
 }
 
-__device__ __forceinline__ float atomic_min_float(float* addr, float val) {
-  int* ai = (int*)addr;
-  int old = *ai, assumed;
-  do {
-    assumed = old;
-    old = atomicCAS(ai, assumed, __float_as_int(fminf(val, __int_as_float(assumed))));
-  } while (assumed != old);
-  return __int_as_float(old);
+// atomic minimum of a float with ONE hardware atomic instead of a compare-and-swap loop (dozens of points of a scan line land in
+// the same cell: the CAS loop of round 1 retried under that contention and made the process kernel latency-bound, 14 points/ns):
+// non-negative floats order like signed integers, negative floats like unsigned integers in reverse.
+__device__ __forceinline__ void atomic_min_float(float* addr, float val) {
+  if (!(val == val)) return;      // NaN never wins (the CAS form kept the old value)
+  if (val == 0.0f) val = 0.0f;    // -0.0 would read as INT_MIN below
+  if (val >= 0.0f) atomicMin(reinterpret_cast<int*>(addr), __float_as_int(val));
+  else atomicMax(reinterpret_cast<unsigned*>(addr), __float_as_uint(val));
 }
 
 __global__ void k_elev_fill(float* elevation, float* variance, float* intensity, float* lowest, float* traver, int* R, int* G, int* B,
@@ -193,7 +193,13 @@ constexpr int ELEV_GROUP = 64;  // frames per group: one bit per frame in the cl
 __global__ void k_elev_process_batch(const BatchFrame* __restrict__ frames, int cells, float* __restrict__ lowest, float* __restrict__ ph,
                                      float* __restrict__ pv, int* __restrict__ keys, int* __restrict__ vals) {
   const int f = blockIdx.y;
-  const BatchFrame& F = frames[f];
+  __shared__ BatchFrame F;  // the frame's geometry and sensor model: once per block into shared memory
+  {
+    const unsigned* src = reinterpret_cast<const unsigned*>(frames + f);
+    unsigned* dst = reinterpret_cast<unsigned*>(&F);
+    for (int w = threadIdx.x; w < (int)(sizeof(BatchFrame) / sizeof(unsigned)); w += blockDim.x) dst[w] = src[w];
+  }
+  __syncthreads();
   const int n = F.n, off = F.off;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     int mi;
