@@ -326,19 +326,21 @@ __global__ void k_elev_fuse_segments(const int* __restrict__ keys, const int* __
         colour = cc.x != 0 && cc.y != 0 && cc.z != 0 && __int_as_float(cc.w) != 0.f;
       }
       bool wc = false;
+      // fused estimate first: its divisions overlap the Mahalanobis test instead of waiting for it (see k_elev_fuse_runs_batch)
+      const float ne = fmaf(v, h, hvv * e) / (v + hvv);
+      const float nv = (hvv * v) / (hvv + v);
+      const bool far = elev_mahal_gt5(h, e, v);
       if (e == -10.f) {
         e = h;
         v = hvv;
         wc = colour;
-      } else if (elev_mahal_gt5(h, e, v)) {
+      } else if (far) {
         if (e < h) {
           e = h;
           v = hvv;
           wc = colour;
         }
       } else {
-        const float ne = fmaf(v, h, hvv * e) / (v + hvv);
-        const float nv = (hvv * v) / (hvv + v);
         e = ne;
         v = nv;
         wc = colour;
@@ -416,17 +418,20 @@ __global__ void k_elev_fuse_runs_batch(const int* __restrict__ keys, const int* 
         prev_f = f;
       }
       const float h = m4[u].x, hvv = m4[u].y;
+      // the fused estimate is computed BEFORE the Mahalanobis test is known: its two divisions then overlap the rsqrt + compare
+      // of the test instead of waiting for it (the loop is one dependent chain per cell; this shortens the chain, not the work)
+      const float ne = fmaf(v, h, hvv * e) / (v + hvv);
+      const float nv = (hvv * v) / (hvv + v);
+      const bool far = elev_mahal_gt5(h, e, v);
       if (e == -10.f) {
         e = h;
         v = hvv;
-      } else if (elev_mahal_gt5(h, e, v)) {
+      } else if (far) {
         if (e < h) {
           e = h;
           v = hvv;
         }
       } else {
-        const float ne = fmaf(v, h, hvv * e) / (v + hvv);
-        const float nv = (hvv * v) / (hvv + v);
         e = ne;
         v = nv;
       }
