@@ -66,10 +66,19 @@ __device__ __forceinline__ bool cell_of(const ElevGeom& g, float px, float py, i
 // the same cell: the CAS loop of round 1 retried under that contention and made the process kernel latency-bound, 14 points/ns):
 // non-negative floats order like signed integers, negative floats like unsigned integers in reverse.
 __device__ __forceinline__ void atomic_min_float(float* addr, float val) {
+#ifdef MR_ELEV_CAS_MIN  // the round-1 form, kept for A/B measurements
+  int* ai = (int*)addr;
+  int old = *ai, assumed;
+  do {
+    assumed = old;
+    old = atomicCAS(ai, assumed, __float_as_int(fminf(val, __int_as_float(assumed))));
+  } while (assumed != old);
+#else
   if (!(val == val)) return;      // NaN never wins (the CAS form kept the old value)
   if (val == 0.0f) val = 0.0f;    // -0.0 would read as INT_MIN below
   if (val >= 0.0f) atomicMin(reinterpret_cast<int*>(addr), __float_as_int(val));
   else atomicMax(reinterpret_cast<unsigned*>(addr), __float_as_uint(val));
+#endif
 }
 
 __global__ void k_elev_fill(float* elevation, float* variance, float* intensity, float* lowest, float* traver, int* R, int* G, int* B,

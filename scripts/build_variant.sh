@@ -6,9 +6,11 @@ name=$1; shift
 out=build/variants/$name
 mkdir -p $out
 FL="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -std=c++17 -Xcompiler -fPIC"
+TU=${VARIANT_TU:-gicp}   # the translation unit the -D flags are meant for (the others are reused from build/obj)
 for f in runtime gicp keyframe elevation elev_post bev radon; do
-  if [ $f = gicp ] || [ ! -f build/obj/$f.o ]; then
-    nvcc $FL "$@" -c mr_slam_b200/csrc/$f.cu -o $out/$f.o &
+  if [ $f = $TU ] || [ ! -f build/obj/$f.o ]; then
+    FLF="$FL"; [ $f = elev_post ] && FLF="${FL/-fmad=false/}"
+    nvcc $FLF "$@" -c mr_slam_b200/csrc/$f.cu -o $out/$f.o &
   else
     cp build/obj/$f.o $out/$f.o
   fi
