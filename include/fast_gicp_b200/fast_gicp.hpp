@@ -5,10 +5,10 @@
 //      (FG/include/fast_gicp/gicp/fast_gicp.hpp:19-100, lsq_registration.hpp:15-85).  PointT is any POD whose first three
 //      floats are x,y,z (pcl::PointXYZ: 4 floats, pcl::PointXYZI / PointNormal: 8 floats).  Used by tests/cpp and by ports
 //      that do not link PCL.
-//  (2) when PCL is available (MRSLAM_WITH_PCL), fast_gicp::FastGICP<PointSource,PointTarget> deriving from
-//      pcl::Registration<PointSource,PointTarget,float> -- same class name, namespace and virtual surface as the reference,
-//      so Mapping/src/global_manager/src/global_manager.cpp:2435-2443 and FG/src/python/main.cpp compile unchanged against
-//      this header + libmrslam_b200.so instead of libfast_gicp.so.  It is logic-free: every method forwards to layer (1).
+//  (2) fast_gicp::LsqRegistration / fast_gicp::FastGICP<PointSource,PointTarget> deriving from
+//      pcl::Registration<PointSource,PointTarget,float> -- same class names, namespace and virtual surface as the reference --
+//      are in pcl_dropin.hpp (libfast_gicp.so), so Mapping/src/global_manager/src/global_manager.cpp:2435-2443 and
+//      FG/src/python/main.cpp compile unchanged against <fast_gicp/gicp/fast_gicp.hpp> of this repository.
 //
 // Eigen matrices are column-major, the C-ABI is row-major: the adapters transpose.
 #pragma once
@@ -133,94 +133,6 @@ private:
 
 }  // namespace fast_gicp_b200
 
-#if defined(MRSLAM_WITH_PCL)
-// ---------------------------------------------------------------------------------------------------------------------
-// Drop-in class for the ROS nodes: same name / namespace / base class as FG/include/fast_gicp/gicp/fast_gicp.hpp.
-// Compiled only where PCL 1.10 + Eigen exist (not in this image); deliberately free of logic.
-// ---------------------------------------------------------------------------------------------------------------------
-#include <pcl/point_cloud.h>
-#include <pcl/point_types.h>
-#include <pcl/registration/registration.h>
-
-namespace fast_gicp {
-using RegularizationMethod = fast_gicp_b200::RegularizationMethod;
-
-template <typename PointSource, typename PointTarget>
-class FastGICP : public pcl::Registration<PointSource, PointTarget, float> {
-public:
-  using Base = pcl::Registration<PointSource, PointTarget, float>;
-  using Matrix4 = typename Base::Matrix4;
-  using PointCloudSource = typename Base::PointCloudSource;
-  using PointCloudSourceConstPtr = typename PointCloudSource::ConstPtr;
-  using PointCloudTargetConstPtr = typename Base::PointCloudTarget::ConstPtr;
-  using Ptr = pcl::shared_ptr<FastGICP<PointSource, PointTarget>>;
-  EIGEN_MAKE_ALIGNED_OPERATOR_NEW
-
-  FastGICP() : h_(mrslam_gicp_create()) {
-    this->reg_name_ = "FastGICP";
-    this->max_iterations_ = 64;
-    this->transformation_epsilon_ = 5e-4;
-  }
-  ~FastGICP() override { mrslam_gicp_destroy(h_); }
-
-  void setNumThreads(int n) { mrslam_gicp_set_num_threads(h_, n); }
-  void setCorrespondenceRandomness(int k) { mrslam_gicp_set_correspondence_randomness(h_, k); }
-  void setRegularizationMethod(RegularizationMethod m) { mrslam_gicp_set_regularization_method(h_, static_cast<int>(m)); }
-  void setRotationEpsilon(double e) { mrslam_gicp_set_rotation_epsilon(h_, e); }
-  void setInitialLambdaFactor(double f) { mrslam_gicp_set_initial_lambda_factor(h_, f); }
-  void setDebugPrint(bool on) { mrslam_gicp_set_debug_print(h_, on); }
-  const Eigen::Matrix<double, 6, 6>& getFinalHessian() const {
-    double H[36];
-    mrslam_gicp_get_final_hessian(h_, H);
-    final_hessian_ = Eigen::Map<Eigen::Matrix<double, 6, 6, Eigen::RowMajor>>(H);
-    return final_hessian_;
-  }
-  virtual void swapSourceAndTarget() {
-    this->input_.swap(this->target_);
-    mrslam_gicp_swap_source_and_target(h_);
-  }
-  virtual void clearSource() {
-    this->input_.reset();
-    mrslam_gicp_clear_source(h_);
-  }
-  virtual void clearTarget() {
-    this->target_.reset();
-    mrslam_gicp_clear_target(h_);
-  }
-  void setInputSource(const PointCloudSourceConstPtr& cloud) override {
-    if (this->input_ == cloud) return;
-    Base::setInputSource(cloud);
-    mrslam_gicp_set_input_source(h_, reinterpret_cast<const float*>(cloud->points.data()), static_cast<int>(cloud->size()),
-                                 static_cast<int>(sizeof(PointSource) / sizeof(float)));
-  }
-  void setInputTarget(const PointCloudTargetConstPtr& cloud) override {
-    if (this->target_ == cloud) return;
-    Base::setInputTarget(cloud);
-    mrslam_gicp_set_input_target(h_, reinterpret_cast<const float*>(cloud->points.data()), static_cast<int>(cloud->size()),
-                                 static_cast<int>(sizeof(PointTarget) / sizeof(float)));
-  }
-
-protected:
-  // pcl::Registration::align() is non-virtual and calls this (PCL registration.hpp); members it reads afterwards are kept.
-  void computeTransformation(PointCloudSource& output, const Matrix4& guess) override {
-    mrslam_gicp_set_maximum_iterations(h_, this->max_iterations_);
-    mrslam_gicp_set_transformation_epsilon(h_, this->transformation_epsilon_);
-    mrslam_gicp_set_max_correspondence_distance(h_, this->corr_dist_threshold_);
-    Eigen::Matrix<float, 4, 4, Eigen::RowMajor> g = guess;
-    int s = mrslam_gicp_align(h_, g.data());
-    if (s != MRSLAM_OK && s != MRSLAM_ERR_NOTCONV) std::fprintf(stderr, "FastGICP: %s\n", mrslam_last_error());
-    Eigen::Matrix<float, 4, 4, Eigen::RowMajor> T;
-    mrslam_gicp_get_final_transformation(h_, T.data());
-    this->final_transformation_ = T;
-    this->converged_ = mrslam_gicp_has_converged(h_) != 0;
-    this->nr_iterations_ = mrslam_gicp_get_num_iterations(h_);
-    output = *this->input_;
-    mrslam_gicp_get_aligned(h_, reinterpret_cast<float*>(output.points.data()), static_cast<int>(sizeof(PointSource) / sizeof(float)));
-  }
-
-private:
-  mrslam_gicp_t* h_;
-  mutable Eigen::Matrix<double, 6, 6> final_hessian_;
-};
-}  // namespace fast_gicp
-#endif  // MRSLAM_WITH_PCL
+// The pcl::Registration-derived drop-in classes (fast_gicp::LsqRegistration / fast_gicp::FastGICP, the ones the ROS nodes
+// instantiate) live in pcl_dropin.hpp + pcl_dropin_impl.hpp and are built into libfast_gicp.so; include <fast_gicp/gicp/fast_gicp.hpp>
+// from this repository's include/ directory to get them.

@@ -639,8 +639,11 @@ constexpr int KCAND = 64;
 #define MR_KNN_SHARED 1
 #endif
 
+#ifndef MR_KNN_MINBLK
+#define MR_KNN_MINBLK 8
+#endif
 template <bool STATS>
-__global__ void __launch_bounds__(128, 8) k_knn_search(const KnnParams* __restrict__ plist, int only_flagged) {
+__global__ void __launch_bounds__(128, MR_KNN_MINBLK) k_knn_search(const KnnParams* __restrict__ plist, int only_flagged) {
   __shared__ int s_list[4][KCAND];
   const KnnParams P = plist[blockIdx.y];
   // second pass behind k_knn_search_v2: only the tiles it flagged (one flag per tile; warp-uniform exit further down)
@@ -1171,7 +1174,10 @@ __device__ __forceinline__ void regularize_cov(int reg, const double C[9], doubl
 }
 
 // covariance of the k neighbours (double), one thread per SORTED point; grid = (ceil(npad/128), n_clouds)
-__global__ void __launch_bounds__(128) k_cov(const KnnParams* __restrict__ plist) {
+#ifndef MR_COV_MINBLK
+#define MR_COV_MINBLK 1
+#endif
+__global__ void __launch_bounds__(128, MR_COV_MINBLK) k_cov(const KnnParams* __restrict__ plist) {
   const KnnParams P = plist[blockIdx.y];
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= P.ntiles * TILE) return;
@@ -1410,8 +1416,11 @@ __device__ __forceinline__ void warp_query_nn1(const PairParams& P, float qx, fl
 //           farther than every coherent best; a lane is final unless the list overflowed below its best.
 //  phase B  all other lanes (isolated points, overflow leftovers, and every lane in the unseeded first pass) run the
 //           warp-cooperative single-query search, so one far outlier cannot inflate the walk of the other 31 queries.
+#ifndef MR_NN1_MINBLK
+#define MR_NN1_MINBLK 1
+#endif
 template <int MODE>
-__global__ void __launch_bounds__(128) k_nn1_search(const PairParams* __restrict__ plist, const int* __restrict__ active,
+__global__ void __launch_bounds__(128, MR_NN1_MINBLK) k_nn1_search(const PairParams* __restrict__ plist, const int* __restrict__ active,
                                                     const double* __restrict__ Tbuf, double max_range,
                                                     unsigned long long* stat_pairs) {
   const int pid = active[blockIdx.y];
