@@ -1295,6 +1295,37 @@ enum { MODE_LINEARIZE = 0, MODE_FITNESS = 1 };
 #define MR_NN1_WPQ 0
 #endif
 constexpr int NN1_STAGE = 16;  // candidate tiles staged in shared memory per warp (8 KB); later ones are read from L2
+// Packed FP32 pairs (sm_100: FADD2 / FMUL2 / FFMA2 work on two floats in a 64-bit register pair; every element is the same IEEE
+// round-to-nearest operation as its scalar form, so a distance computed this way equals dist2() bit for bit).
+#ifndef MR_NN1_X2
+#define MR_NN1_X2 1
+#endif
+__device__ __forceinline__ u64 f2_pack(float lo, float hi) {
+  u64 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ u64 f2_sub(u64 a, u64 b) {
+  u64 r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ u64 f2_mul(u64 a, u64 b) {
+  u64 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ u64 f2_fma(u64 a, u64 b, u64 c) {
+  u64 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+// dist2() of one query against two points at once: fma(dz,dz, fma(dy,dy, dx*dx)) per element
+__device__ __forceinline__ u64 f2_dist2(u64 qx2, u64 qy2, u64 qz2, u64 px2, u64 py2, u64 pz2) {
+  const u64 dx = f2_sub(qx2, px2), dy = f2_sub(qy2, py2), dz = f2_sub(qz2, pz2);
+  return f2_fma(dz, dz, f2_fma(dy, dy, f2_mul(dx, dx)));
+}
 
 // Warp-cooperative exact NN-1 of ONE query (all lanes hold the same query); the 32 lanes evaluate the 32 points of a
 // candidate tile in parallel.  (key0,pos0) is a known candidate (seed) or (KEY_NONE,-1).  Returns the best (key,pos).
@@ -1424,7 +1455,12 @@ __global__ void __launch_bounds__(128) k_nn1_search(const PairParams* __restrict
   const int pid = active[blockIdx.y];
   const PairParams P = plist[pid];
   __shared__ double s_red[4][2];
+#if MR_NN1_X2
+  __shared__ __align__(16) float s_tx[4][TILE], s_ty[4][TILE], s_tz[4][TILE];  // the staged target tile, one coordinate per array
+  __shared__ __align__(16) int s_tw[4][TILE];                                  // ... and its original indices
+#else
   __shared__ float4 s_tile[4][TILE];
+#endif
   __shared__ u64 s_cand[4][CAND];
 #if MR_NN1_WPQ
   __shared__ __align__(16) float4 s_pts[4][NN1_STAGE][TILE];  // the first NN1_STAGE candidate tiles of the warp, staged once
@@ -1458,6 +1494,45 @@ __global__ void __launch_bounds__(128) k_nn1_search(const PairParams* __restrict
     int bp = -1;
 
     // lane-per-query scan of one target tile (staged in shared memory)
+#if MR_NN1_X2
+    // Four points per step on the packed-FP32 pipe: 12 two-wide operations give the four squared distances, their minimum decides
+    // whether any of them can matter (m <= best distance, as `ckey < bkey` needs), and only then are indices loaded and keys
+    // compared.  The winner is the smallest (distance, index) key among the four, i.e. exactly what four sequential updates leave.
+    const u64 qx2 = f2_pack(qx, qx), qy2 = f2_pack(qy, qy), qz2 = f2_pack(qz, qz);
+    auto scan_tile = [&](int t) {
+      const float4 c = P.tgt_sort[(size_t)t * TILE + lane];
+      __syncwarp();
+      s_tx[wib][lane] = c.x;
+      s_ty[wib][lane] = c.y;
+      s_tz[wib][lane] = c.z;
+      s_tw[wib][lane] = __float_as_int(c.w);
+      __syncwarp();
+      float bd = key_dist(bkey);
+#pragma unroll 4
+      for (int g = 0; g < TILE / 4; g++) {
+        const ulonglong2 X = reinterpret_cast<const ulonglong2*>(s_tx[wib])[g], Y = reinterpret_cast<const ulonglong2*>(s_ty[wib])[g],
+                         Z = reinterpret_cast<const ulonglong2*>(s_tz[wib])[g];
+        float d0, d1, d2, d3;
+        f2_unpack(f2_dist2(qx2, qy2, qz2, X.x, Y.x, Z.x), d0, d1);
+        f2_unpack(f2_dist2(qx2, qy2, qz2, X.y, Y.y, Z.y), d2, d3);
+        const float m = fminf(fminf(d0, d1), fminf(d2, d3));
+        if (m <= bd) {
+          const int4 W = reinterpret_cast<const int4*>(s_tw[wib])[g];
+          // unsigned order of the index bit patterns, as make_key() packs them
+          const unsigned i0 = d0 == m ? (unsigned)W.x : 0xffffffffu, i1 = d1 == m ? (unsigned)W.y : 0xffffffffu,
+                         i2 = d2 == m ? (unsigned)W.z : 0xffffffffu, i3 = d3 == m ? (unsigned)W.w : 0xffffffffu;
+          const unsigned im = min(min(i0, i1), min(i2, i3));
+          const u64 ckey = ((u64)__float_as_uint(m) << 32) | im;
+          if (ckey < bkey) {
+            bkey = ckey;
+            bd = m;
+            bp = t * TILE + g * 4 + (i0 == im ? 0 : i1 == im ? 1 : i2 == im ? 2 : 3);
+          }
+        }
+      }
+      tiles_done++;
+    };
+#else
     auto scan_tile = [&](int t) {
       const float4 c = P.tgt_sort[(size_t)t * TILE + lane];
       __syncwarp();
@@ -1479,6 +1554,7 @@ __global__ void __launch_bounds__(128) k_nn1_search(const PairParams* __restrict
       }
       tiles_done++;
     };
+#endif
 
     // ---- phase A: seeds ----
     int sp = -1;

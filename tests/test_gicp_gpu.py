@@ -80,6 +80,37 @@ def test_linearize_stage_parity(gpu, vlp_pair):
     assert abs(e_g - e_o) <= 1e-11 * abs(e_o)
 
 
+def test_correspondence_ties_pick_lowest_index(gpu):
+    """NN-1 under exact distance ties: every target point exists three times (shuffled original indices) on a coarse lattice and
+    the queries sit on the half lattice, so each query has several nearest neighbours at bit-equal distances -- the answer is the
+    lowest original index (oracle: gicp_oracle.cpp nn1; reference fast_gicp_impl.hpp:183-214).  Unseeded pass: evaluate_cost();
+    seeded pass: the second linearisation inside align(), compared with the oracle's exact search at the same x1."""
+    rng = np.random.default_rng(5)
+    base = np.round(rng.uniform(-6, 6, size=(5000, 3)) * 4) / 4
+    tgt = np.concatenate([base, base, base]).astype(np.float32)
+    tgt = tgt[rng.permutation(len(tgt))]
+    src = (np.round(rng.uniform(-6, 6, size=(4000, 3)) * 8) / 8).astype(np.float32)
+    g = make(pygicp.FastGICP, src, tgt)
+    o = make(oracle.FastGICP, src, tgt)
+    for T in (np.eye(4), synth.pose_matrix(0.125, 0.0, -0.125, 0.0)):   # lattice-preserving shifts keep the ties exact
+        Tg = np.asarray(T, np.float32)
+        g.evaluate_cost(Tg)
+        corr_o, sqd_o = o.linearize(Tg.astype(np.float64), len(src))[3:5]
+        corr_g, sqd_g, _ = g.last_correspondences(len(src))
+        assert np.array_equal(sqd_g, sqd_o)
+        assert np.array_equal(corr_g, corr_o)
+    guess = synth.pose_matrix(0.03, -0.02, 0.01, 0.01)
+    g2 = make(pygicp.FastGICP, src, tgt, iters=2)
+    g2.align(guess)
+    o1 = make(oracle.FastGICP, src, tgt, iters=1)
+    o1.align(guess)
+    x1 = o1.result()["Td"]
+    corr_o, sqd_o = o.linearize(x1, len(src))[3:5]
+    corr_g, sqd_g, _ = g2.last_correspondences(len(src))
+    assert np.array_equal(sqd_g, sqd_o)
+    assert np.array_equal(corr_g, corr_o)      # the three copies of a target point tie exactly: lowest index wins
+
+
 @pytest.mark.parametrize("pid,k", [(0, 15), (1, 20), (2, 15)])
 def test_align_matches_oracle(gpu, pid, k):
     src, tgt, T_gt, T_guess = synth.make_pair(pid, "vlp16")[:4]
