@@ -267,14 +267,19 @@ __device__ __forceinline__ float box_box_dist2(const float a[6], const float* __
   return gx * gx + gy * gy + gz * gz;
 }
 
+// ascending sort of one 32-bit key per lane; every compare-exchange keeps the smaller key in the lower lane (first step of a
+// merge: partner = mirror image inside the block, then partner = lane ^ stride), so a step's direction is one bit of the lane id
 __device__ __forceinline__ unsigned warp_sort_u32(unsigned key, int lane) {
 #pragma unroll
   for (int size = 2; size <= 32; size <<= 1) {
+    {
+      const unsigned other = __shfl_xor_sync(FULL, key, size - 1);
+      key = (lane & (size >> 1)) == 0 ? min(key, other) : max(key, other);
+    }
 #pragma unroll
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+    for (int stride = size >> 2; stride > 0; stride >>= 1) {
       const unsigned other = __shfl_xor_sync(FULL, key, stride);
-      const bool take_min = ((lane & size) == 0) == ((lane & stride) == 0);
-      key = take_min ? min(key, other) : max(key, other);
+      key = (lane & stride) == 0 ? min(key, other) : max(key, other);
     }
   }
   return key;
@@ -527,6 +532,27 @@ __device__ __forceinline__ u64 warp_sort_keys(u64 key, int lane) {
   return key;
 }
 
+// The same sort as a network whose compare-exchanges all point the same way (lower lane keeps the smaller key): the first
+// step of every merge pairs lane i with its mirror image inside the block (xor with size-1), the others with i ^ stride, so the
+// direction of a step depends on ONE bit of the lane number instead of two.
+__device__ __forceinline__ u64 warp_sort_keys_mirror(u64 key, int lane) {
+#pragma unroll
+  for (int size = 2; size <= 32; size <<= 1) {
+    {
+      const u64 other = __shfl_xor_sync(FULL, key, size - 1);
+      const bool low = (lane & (size >> 1)) == 0;
+      key = ((key < other) == low) ? key : other;
+    }
+#pragma unroll
+    for (int stride = size >> 2; stride > 0; stride >>= 1) {
+      const u64 other = __shfl_xor_sync(FULL, key, stride);
+      const bool low = (lane & stride) == 0;
+      key = ((key < other) == low) ? key : other;
+    }
+  }
+  return key;
+}
+
 // Warp-cooperative exact kNN of ONE query (all lanes hold the same query): the k-best list lives one key per lane.
 // Returns this lane's entry of the sorted list (lane j = j-th neighbour).
 __device__ __forceinline__ u64 warp_query_knn(const KnnParams& P, float qx, float qy, float qz, int qt, int k, int lane,
@@ -543,7 +569,11 @@ __device__ __forceinline__ u64 warp_query_knn(const KnnParams& P, float qx, floa
   u64 wkey;
   {  // own tile: all 32 candidates enter the (empty) list -> one bitonic sort instead of 32 insertions
     const float4 c = P.psort[(size_t)qt * TILE + lane];
+#if MR_KNN_MIRRORSORT
+    my_key = warp_sort_keys_mirror(make_key(dist2(qx, qy, qz, c.x, c.y, c.z), __float_as_int(c.w)), lane);
+#else
     my_key = warp_sort_keys(make_key(dist2(qx, qy, qz, c.x, c.y, c.z), __float_as_int(c.w)), lane);
+#endif
     wkey = __shfl_sync(FULL, my_key, k - 1);
     tiles_done++;
   }
@@ -642,6 +672,9 @@ constexpr int KCAND = 64;
 #ifndef MR_KNN_MINBLK
 #define MR_KNN_MINBLK 8
 #endif
+#ifndef MR_KNN_MIRRORSORT
+#define MR_KNN_MIRRORSORT 1  // 6 instead of 7 instructions per compare-exchange step (SASS), 15 steps per query
+#endif
 template <bool STATS>
 __global__ void __launch_bounds__(128, MR_KNN_MINBLK) k_knn_search(const KnnParams* __restrict__ plist, int only_flagged) {
   __shared__ int s_list[4][KCAND];
@@ -715,7 +748,11 @@ __global__ void __launch_bounds__(128, MR_KNN_MINBLK) k_knn_search(const KnnPara
       const float qx = __shfl_sync(FULL, qmine.x, qi), qy = __shfl_sync(FULL, qmine.y, qi), qz = __shfl_sync(FULL, qmine.z, qi);
       const int qidx = __shfl_sync(FULL, __float_as_int(qmine.w), qi);
       // own tile: all 32 candidates enter the (empty) list -> one bitonic sort instead of 32 insertions
+#if MR_KNN_MIRRORSORT
+      u64 my_key = warp_sort_keys_mirror(make_key(dist2(qx, qy, qz, qmine.x, qmine.y, qmine.z), __float_as_int(qmine.w)), lane);
+#else
       u64 my_key = warp_sort_keys(make_key(dist2(qx, qy, qz, qmine.x, qmine.y, qmine.z), __float_as_int(qmine.w)), lane);
+#endif
       u64 wkey = __shfl_sync(FULL, my_key, k - 1);
       if (STATS) tiles_done++;
       // per-query distance to the candidate boxes; the low 6 bits of the (non-negative) float carry the slot, which rounds
@@ -1300,6 +1337,9 @@ constexpr int NN1_STAGE = 16;  // candidate tiles staged in shared memory per wa
 #ifndef MR_NN1_X2
 #define MR_NN1_X2 1
 #endif
+#ifndef MR_NN1_NEEDTEST
+#define MR_NN1_NEEDTEST 1
+#endif
 __device__ __forceinline__ u64 f2_pack(float lo, float hi) {
   u64 r;
   asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
@@ -1499,8 +1539,7 @@ __global__ void __launch_bounds__(128) k_nn1_search(const PairParams* __restrict
     // whether any of them can matter (m <= best distance, as `ckey < bkey` needs), and only then are indices loaded and keys
     // compared.  The winner is the smallest (distance, index) key among the four, i.e. exactly what four sequential updates leave.
     const u64 qx2 = f2_pack(qx, qx), qy2 = f2_pack(qy, qy), qz2 = f2_pack(qz, qz);
-    auto scan_tile = [&](int t) {
-      const float4 c = P.tgt_sort[(size_t)t * TILE + lane];
+    auto scan_tile = [&](const float4 c, int t) {
       __syncwarp();
       s_tx[wib][lane] = c.x;
       s_ty[wib][lane] = c.y;
@@ -1533,8 +1572,7 @@ __global__ void __launch_bounds__(128) k_nn1_search(const PairParams* __restrict
       tiles_done++;
     };
 #else
-    auto scan_tile = [&](int t) {
-      const float4 c = P.tgt_sort[(size_t)t * TILE + lane];
+    auto scan_tile = [&](const float4 c, int t) {
       __syncwarp();
       s_tile[wib][lane] = c;
       __syncwarp();
@@ -1700,21 +1738,46 @@ __global__ void __launch_bounds__(128) k_nn1_search(const PairParams* __restrict
           }
         }
 #else
-        u64 e0 = lane < n ? s_cand[wib][lane] : KEY_NONE;
-        u64 e1 = lane + 32 < n ? s_cand[wib][lane + 32] : KEY_NONE;
-        // nearest-first walk: stop as soon as the nearest remaining tile is farther than every coherent best
-        while (true) {
-          const u64 m = e0 < e1 ? e0 : e1;
-          const unsigned hi = (unsigned)(m >> 32);
-          const unsigned mhi = __reduce_min_sync(FULL, hi);
-          if (mhi >= 0x7f800000u) break;  // list exhausted
-          const unsigned mlo = __reduce_min_sync(FULL, hi == mhi ? (unsigned)(m & 0xffffffffull) : 0xffffffffu);
-          const u64 pick = ((u64)mhi << 32) | mlo;
-          if (e0 == pick) e0 = KEY_NONE;
-          else if (e1 == pick) e1 = KEY_NONE;
-          const float R = __uint_as_float(__reduce_max_sync(FULL, coherent ? __float_as_uint(key_dist(bkey)) : 0u));
-          if (__uint_as_float(mhi) * CULL_SAFETY > fminf(R, cap)) break;
-          scan_tile((int)mlo);
+        // Nearest-first walk over the candidate tiles: stop as soon as the nearest remaining tile is farther than every coherent best.
+        // One 32-bit key per candidate, (box distance bits & ~63) | slot -- the distance rounded DOWN by < 2^-17 relative, which only
+        // makes the stop test more conservative -- so one warp min-reduction picks the next tile.  The tile after the current one is
+        // picked, and its row fetched, BEFORE the current one is scanned (the order does not depend on the scan), so the global load
+        // overlaps ~180 instructions of scanning instead of stalling the warp at the head of every tile.
+        constexpr unsigned NONE32 = 0xffffffffu;
+        unsigned k0 = lane < n ? (((unsigned)(s_cand[wib][lane] >> 32) & ~63u) | (unsigned)lane) : NONE32;
+        unsigned k1 = lane + 32 < n ? (((unsigned)(s_cand[wib][lane + 32] >> 32) & ~63u) | (unsigned)(lane + 32)) : NONE32;
+        auto pick = [&](unsigned& key, int& t) -> bool {  // removes the nearest remaining candidate from the list
+          key = __reduce_min_sync(FULL, min(k0, k1));
+          if (key == NONE32) return false;
+          const int slot = (int)(key & 63u);
+          if (slot == lane) k0 = NONE32;
+          if (slot == lane + 32) k1 = NONE32;
+          t = (int)(unsigned)(s_cand[wib][slot] & 0xffffffffull);
+          return true;
+        };
+        unsigned nkey;
+        int nt = 0;
+        bool have = pick(nkey, nt);
+        float4 cn = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (have) cn = P.tgt_sort[(size_t)nt * TILE + lane];
+        while (have) {
+          const unsigned ckey = nkey;
+          const int t = nt;
+          const float4 c = cn;
+          const float R = fminf(__uint_as_float(__reduce_max_sync(FULL, coherent ? __float_as_uint(key_dist(bkey)) : 0u)), cap);
+          if (__uint_as_float(ckey & ~63u) * CULL_SAFETY > R) break;
+          have = pick(nkey, nt);
+          if (have) cn = P.tgt_sort[(size_t)nt * TILE + lane];
+#if MR_NN1_NEEDTEST
+          {
+            // The list was built from the box of ALL coherent queries; a tile near one corner of that box is often out of reach of
+            // every single query.  Skip it unless some coherent lane's own point-to-box distance is within its current best.
+            const float pbd = pt_box_dist2(qx, qy, qz, P.tgt_tb, ntp, t);
+            const bool need = coherent && pbd * CULL_SAFETY <= fminf(key_dist(bkey), cap);
+            if (!__any_sync(FULL, need)) continue;
+          }
+#endif
+          scan_tile(c, t);
         }
 #endif
         // with an overflowing candidate list some tiles at distance >= dropped_min were never looked at:
@@ -1781,6 +1844,9 @@ __global__ void __launch_bounds__(128) k_nn1_search(const PairParams* __restrict
   }
 }
 
+#ifndef MR_LIN_SMEMRED
+#define MR_LIN_SMEMRED 1
+#endif
 // Mahalanobis + linearisation terms, one thread per SORTED source point.  grid = (ceil(src_ntiles/4), n_active)
 __global__ void __launch_bounds__(128) k_linearize(const PairParams* __restrict__ plist, const int* __restrict__ active,
                                                    const double* __restrict__ Tbuf) {
@@ -1858,13 +1924,36 @@ __global__ void __launch_bounds__(128) k_linearize(const PairParams* __restrict_
       }
     }
   }
-  // deterministic reduction: lanes -> warp (butterfly) -> block (fixed order) -> one partial row per block
+  // deterministic reduction: lanes -> warp -> block (fixed order) -> one partial row per block
+#if MR_LIN_SMEMRED
+  // through shared memory: 28 stores per thread, then thread (w, c) adds the 32 values of column c of warp w in a fixed order
+  // (four interleaved partial sums) -- ~90 instructions per warp instead of the ~450 of 28 64-bit shuffle butterflies
+  __shared__ double s_acc[4][NRED][33];
+#pragma unroll
+  for (int i = 0; i < NRED; i++) s_acc[wib][i][lane] = acc[i];
+  __syncthreads();
+  if (threadIdx.x < 4 * NRED) {
+    const int w = threadIdx.x / NRED, c = threadIdx.x - w * NRED;
+    const double* col = s_acc[w][c];
+    double u0 = col[0], u1 = col[8], u2 = col[16], u3 = col[24];
+#pragma unroll
+    for (int l = 1; l < 8; l++) {
+      u0 += col[l];
+      u1 += col[8 + l];
+      u2 += col[16 + l];
+      u3 += col[24 + l];
+    }
+    s_red[w][c] = (u0 + u1) + (u2 + u3);
+  }
+  __syncthreads();
+#else
 #pragma unroll
   for (int i = 0; i < NRED; i++) {
     double v = warp_sum(acc[i]);
     if (lane == 0) s_red[wib][i] = v;
   }
   __syncthreads();
+#endif
   if (threadIdx.x < NRED) {
     double v = ((s_red[0][threadIdx.x] + s_red[1][threadIdx.x]) + s_red[2][threadIdx.x]) + s_red[3][threadIdx.x];
     P.partials[(size_t)blockIdx.x * NRED + threadIdx.x] = v;
