@@ -151,6 +151,8 @@ int mrslam_gicp_debug_last_correspondences(mrslam_gicp_t*, int* corr, float* sq_
 int mrslam_gicp_compute_error(mrslam_gicp_t*, const double* T16, double* cost); /* FastGICP::compute_error */
 /* instrumentation: distance evaluations (0: kNN, 1: NN-1) and k-min insertion rounds (2) since stats_enable(1) */
 int mrslam_gicp_stats_enable(int on);
+/* development aid: with MRSLAM_BUILD_DIAG=1 in the environment, print (stderr) and reset the per-stage device times of the cloud build */
+void mrslam_build_diag_dump(const char* label);
 unsigned long long mrslam_gicp_stats_get(int which);
 unsigned long long mrslam_gicp_stats_pairs(void);
 /* kNN building block (calculate_covariances' search): indices (original order) and squared distances, n x k */

@@ -146,6 +146,22 @@ struct StageFence {
 #ifdef __CUDACC__
 constexpr unsigned FULL = 0xffffffffu;
 
+// Small parameter blocks (descriptor tables, pair lists, transforms) reach the device through a kernel that reads the pinned --
+// hence device-visible -- host copy, NOT through the copy engine: an H2D cudaMemcpyAsync on the library stream queues in the
+// DMA engine behind every bulk upload handed to it before (the clouds of this or of the next batch), which stalled the stream
+// for the length of those uploads (~2.5 ms per 32-pair step, gpurun_out/r2ac).  The source must stay untouched until the
+// launch has run, exactly as with cudaMemcpyAsync from pinned memory.
+static __global__ void k_fetch_words(unsigned* __restrict__ dst, const unsigned* __restrict__ src_pinned, size_t nwords) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nwords; i += (size_t)gridDim.x * blockDim.x) dst[i] = src_pinned[i];
+}
+static inline cudaError_t upload_params(void* dst, const void* src_pinned, size_t bytes, cudaStream_t st) {
+  const size_t nw = bytes / 4;  // every parameter type is a multiple of four bytes
+  if (nw == 0) return cudaSuccess;
+  const unsigned blocks = (unsigned)std::min<size_t>((nw + 255) / 256, 32);
+  k_fetch_words<<<blocks, 256, 0, st>>>(reinterpret_cast<unsigned*>(dst), reinterpret_cast<const unsigned*>(src_pinned), nw);
+  return cudaGetLastError();
+}
+
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL, v, o));

@@ -948,9 +948,9 @@ static int elev_group_onepass(Elev* m, const mrslam_elev_frame_t* frames, int nf
     off += (size_t)F.n;
   }
   for (int f = nframes; f < ELEV_GROUP; f++) bo.off[f] = 0;
-  MR_CUDA(cudaMemcpyAsync(m->d_frames.p, m->h_frames.p, sizeof(BatchFrame) * nframes, cudaMemcpyHostToDevice, st));
-  if (nclear) MR_CUDA(cudaMemcpyAsync(m->d_ctab.p, m->h_ctab.p, sizeof(ClearTab) * nclear, cudaMemcpyHostToDevice, st));
-  if (any_move) MR_CUDA(cudaMemcpyAsync(m->d_clr.p, m->h_clr.p, sizeof(unsigned long long) * 2 * (size_t)L, cudaMemcpyHostToDevice, st));
+  MR_CUDA(upload_params(m->d_frames.p, m->h_frames.p, sizeof(BatchFrame) * nframes, st));
+  if (nclear) MR_CUDA(upload_params(m->d_ctab.p, m->h_ctab.p, sizeof(ClearTab) * nclear, st));
+  if (any_move) MR_CUDA(upload_params(m->d_clr.p, m->h_clr.p, sizeof(unsigned long long) * 2 * (size_t)L, st));
   MR_CHECK(m->batch_fence.mark(st));
   if (nclear) {
     k_elev_clear_tab<<<dim3((max_cnt + 255) / 256, nclear), 256, 0, st>>>(m->elevation.p, m->variance.p, m->intensity.p, m->R.p, m->G.p,

@@ -21,6 +21,18 @@ namespace mrslam {
 // ---------------------------------------------------------------------------------------------
 // device-resident cloud
 // ---------------------------------------------------------------------------------------------
+// ordering between host uploads (copy stream) and their unpack kernels (library stream), shared by all clouds
+struct UploadSync {
+  cudaEvent_t alloc_ev = nullptr;  // a staging buffer allocated on the library stream exists
+  cudaEvent_t pack_ev = nullptr;   // recorded behind every unpack launch: staging buffers unpacked so far may be overwritten
+  bool pack_recorded = false;
+  unsigned long long seq = 0;
+};
+static UploadSync& upload_sync() {
+  static UploadSync u;
+  return u;
+}
+
 struct Cloud {
   int n = 0, npad = 0, ntiles = 0, ntiles_pad = 0, nsuper = 0, nsuper_pad = 0;
   DevBuf<float4> porig, psort;
@@ -32,10 +44,13 @@ struct Cloud {
   bool cov_valid = false;
   bool built = false;   // spatial structures (psort / tb / sb) are produced lazily, batched with the other clouds of a call
   DevBuf<float> raw;    // staging of host input
-  // uploads run on the runtime's copy stream so that they overlap kernels already queued on the library stream (the target
-  // clouds of a batch go up while the source clouds' kNN runs): ev_raw_free = the staging buffer is allocated and no longer read
-  // (library-stream order), ev_up = the upload has landed (copy-stream order)
-  cudaEvent_t ev_raw_free = nullptr, ev_up = nullptr;
+  // Uploads run on the runtime's copy stream and are only ENQUEUED at setInput time: the library stream neither waits for them
+  // nor unpacks them before the cloud is first used (build_clouds() waits for the newest upload of its batch once and unpacks
+  // all of them with one launch).  A caller can therefore hand over the clouds of the next batch while the current one is still
+  // being aligned; their uploads run under its kernels.  ev_up = this cloud's upload has landed (copy-stream order).
+  cudaEvent_t ev_up = nullptr;
+  int pending_stride = 0;  // > 0: raw holds an upload that has not been unpacked into porig yet
+  unsigned long long upload_seq = 0;  // order of the uploads on the copy stream
   int refs = 1;
 
   // stage 1 (at setInput time): points into porig (device).  The Morton sort etc. is deferred to build_clouds().
@@ -50,11 +65,13 @@ struct Cloud {
     if (nsuper_pad == 0) nsuper_pad = 32;
     cov_valid = false;
     built = false;
+    pending_stride = 0;
     return porig.reserve(std::max(n, 1));
   }
 
   int set_from_device_raw(const float* d_raw, int n_, int stride) {
     cudaStream_t st = rt().stream;
+    pending_stride = 0;
     n = n_;
     npad = ((n + TILE - 1) / TILE) * TILE;
     ntiles = npad / TILE;
@@ -82,32 +99,40 @@ struct Cloud {
     }
     size_t nf = (size_t)n_ * stride;
     const float* before = raw.p;
+    // an upload that was never consumed may still be in flight into the staging buffer that reserve() is about to free
+    if (pending_stride > 0 && ev_up && raw.cap < std::max<size_t>(nf, 1)) MR_CUDA(cudaStreamWaitEvent(rt().stream, ev_up, 0));
     MR_CHECK(raw.reserve(std::max<size_t>(nf, 1)));
+    MR_CHECK(set_sizes(n_));
     if (n_ > 0) {
       cudaStream_t up = rt().copy_stream, st = rt().stream;
-      if (!ev_up) {
-        MR_CUDA(cudaEventCreateWithFlags(&ev_up, cudaEventDisableTiming));
-        MR_CUDA(cudaEventCreateWithFlags(&ev_raw_free, cudaEventDisableTiming));
-        before = nullptr;
+      UploadSync& U = upload_sync();
+      if (!ev_up) MR_CUDA(cudaEventCreateWithFlags(&ev_up, cudaEventDisableTiming));
+      if (!U.alloc_ev) {
+        MR_CUDA(cudaEventCreateWithFlags(&U.alloc_ev, cudaEventDisableTiming));
+        MR_CUDA(cudaEventCreateWithFlags(&U.pack_ev, cudaEventDisableTiming));
       }
-      // a (re)allocated staging buffer exists in library-stream order only; otherwise ev_raw_free was recorded behind the
-      // last kernel that read the buffer (a previous life of this pooled cloud), long complete by now
-      if (raw.p != before) MR_CUDA(cudaEventRecord(ev_raw_free, st));
-      MR_CUDA(cudaStreamWaitEvent(up, ev_raw_free, 0));
+      // the staging buffer must exist (a fresh allocation lives in library-stream order) and must no longer be read: its last
+      // reader was the unpack kernel of an earlier batch, and every such kernel precedes the newest pack_ev record
+      if (raw.p != before) {
+        MR_CUDA(cudaEventRecord(U.alloc_ev, st));
+        MR_CUDA(cudaStreamWaitEvent(up, U.alloc_ev, 0));
+      } else if (U.pack_recorded) {
+        MR_CUDA(cudaStreamWaitEvent(up, U.pack_ev, 0));
+      }
       size_t bytes = ((size_t)(n_ - 1) * stride + 3) * sizeof(float);
       MR_CUDA(cudaMemcpyAsync(raw.p, xyz, bytes, cudaMemcpyHostToDevice, up));
       MR_CUDA(cudaEventRecord(ev_up, up));
-      MR_CUDA(cudaStreamWaitEvent(st, ev_up, 0));
+      upload_seq = ++U.seq;
+      pending_stride = stride;
     }
-    int rc = set_from_device_raw(raw.p, n_, stride);
-    if (rc == MRSLAM_OK && n_ > 0) MR_CUDA(cudaEventRecord(ev_raw_free, rt().stream));  // packed: the staging buffer is free again
-    return rc;
+    return MRSLAM_OK;
   }
 
   void release() {
+    if (pending_stride > 0 && ev_up) cudaStreamWaitEvent(rt().stream, ev_up, 0);  // frees are library-stream ordered
+    pending_stride = 0;
     if (ev_up) cudaEventDestroy(ev_up);
-    if (ev_raw_free) cudaEventDestroy(ev_raw_free);
-    ev_up = ev_raw_free = nullptr;
+    ev_up = nullptr;
     porig.release(); psort.release(); tb.release(); sb.release(); qp.release(); skeys.release(); cov.release(); knn_ids.release(); knn_fb.release(); raw.release();
   }
 };
@@ -150,6 +175,41 @@ static BuildScratch& build_scratch() {
 
 // stage 2: Morton order, tiles and boxes of every not-yet-built cloud in `clouds`, ONE pass over the whole batch:
 // per-cloud bounding cube -> (cloud id, 48-bit Morton) keys -> one radix sort -> gather + tile boxes -> super-tile boxes.
+// development aid (MRSLAM_BUILD_DIAG=1): device time of the stages of build_clouds, summed over the process, printed at exit
+struct BuildDiag {
+  bool on = getenv("MRSLAM_BUILD_DIAG") != nullptr;
+  cudaEvent_t ev[6] = {};
+  double ms[5] = {};
+  double host_ms = 0.0;
+  long calls = 0;
+  void mark(int i, cudaStream_t st) {
+    if (!on) return;
+    if (!ev[i]) cudaEventCreate(&ev[i]);
+    cudaEventRecord(ev[i], st);
+  }
+  void collect() {
+    if (!on) return;
+    cudaEventSynchronize(ev[5]);
+    for (int i = 0; i < 5; i++) {
+      float t = 0.f;
+      cudaEventElapsedTime(&t, ev[i], ev[i + 1]);
+      ms[i] += t;
+    }
+    calls++;
+  }
+  void dump(const char* label) {
+    if (on && calls)
+      fprintf(stderr, "build diag [%s]: %ld calls; ms per call: host-setup-to-first-kernel %.3f | wait+unpack %.3f | bbox+keys %.3f | sort %.3f | gather+boxes %.3f\n",
+              label ? label : "", calls, ms[0] / calls, ms[1] / calls, ms[2] / calls, ms[3] / calls, ms[4] / calls);
+    for (double& m : ms) m = 0.0;
+    calls = 0;
+  }
+};
+static BuildDiag& build_diag() {
+  static BuildDiag d;
+  return d;
+}
+
 static int build_clouds(const std::vector<Cloud*>& clouds) {
   std::vector<Cloud*> todo;
   for (Cloud* c : clouds)
@@ -158,6 +218,8 @@ static int build_clouds(const std::vector<Cloud*>& clouds) {
   cudaStream_t st = rt().stream;
   BuildScratch& S = build_scratch();
   ProfScope ps(PROF_CLOUD_BUILD);
+  BuildDiag& D = build_diag();
+  D.mark(0, st);
   const int nc = (int)todo.size();
   if (nc >= (1 << 15)) {
     set_error("too many clouds in one batch (%d)", nc);
@@ -168,6 +230,7 @@ static int build_clouds(const std::vector<Cloud*>& clouds) {
   MR_CHECK(S.d_desc.reserve(nc));
   long long total = 0;
   int max_n = 0, max_tiles_pad = 0, max_super_pad = 0;
+  Cloud* newest_upload = nullptr;  // uploads complete in copy-stream order: waiting for the newest one covers the batch
   for (int i = 0; i < nc; i++) {
     Cloud* c = todo[i];
     MR_CHECK(c->psort.reserve(std::max(c->npad, 1)));
@@ -180,26 +243,45 @@ static int build_clouds(const std::vector<Cloud*>& clouds) {
     d.porig = c->porig.p; d.psort = c->psort.p; d.tb = c->tb.p; d.sb = c->sb.p; d.qp = c->qp.p;
     d.n = c->n; d.ntiles = c->ntiles; d.ntiles_pad = c->ntiles_pad; d.nsuper_pad = c->nsuper_pad;
     d.offset = total;
+    d.raw = nullptr;
+    d.raw_stride = 0;
+    if (c->pending_stride > 0 && c->n > 0) {
+      d.raw = c->raw.p;
+      d.raw_stride = c->pending_stride;
+      if (!newest_upload || c->upload_seq > newest_upload->upload_seq) newest_upload = c;
+    }
+    c->pending_stride = 0;
     S.h_desc.p[i] = d;
     total += c->n;
     max_n = std::max(max_n, c->n);
     max_tiles_pad = std::max(max_tiles_pad, c->ntiles_pad);
     max_super_pad = std::max(max_super_pad, c->nsuper_pad);
   }
-  MR_CUDA(cudaMemcpyAsync(S.d_desc.p, S.h_desc.p, sizeof(BuildDesc) * nc, cudaMemcpyHostToDevice, st));
+  MR_CUDA(upload_params(S.d_desc.p, S.h_desc.p, sizeof(BuildDesc) * nc, st));
   MR_CHECK(S.fence.mark(st));
+  D.mark(1, st);
+  if (newest_upload) {
+    UploadSync& U = upload_sync();
+    MR_CUDA(cudaStreamWaitEvent(st, newest_upload->ev_up, 0));
+    k_pack_pending<<<dim3(std::max(1, std::min((max_n + 255) / 256, 128)), nc), 256, 0, st>>>(S.d_desc.p);
+    count_launch(1);
+    MR_CUDA(cudaEventRecord(U.pack_ev, st));
+    U.pack_recorded = true;
+  }
   size_t tot = (size_t)std::max<long long>(total, 1);
   MR_CHECK(S.keys.reserve(tot)); MR_CHECK(S.keys_alt.reserve(tot));
   MR_CHECK(S.vals.reserve(tot)); MR_CHECK(S.vals_alt.reserve(tot));
   MR_CHECK(S.bbox.reserve((size_t)6 * nc));
   const int* order = S.vals.p;
   const unsigned long long* keys_sorted = S.keys.p;
+  D.mark(2, st);
   if (total > 0) {
     k_bbox_init<<<(nc * 6 + 127) / 128, 128, 0, st>>>(S.bbox.p, nc);
     int gx = std::max(1, std::min((max_n + 255) / 256, 32));
     k_bbox<<<dim3(gx, nc), 256, 0, st>>>(S.d_desc.p, S.bbox.p);
     k_morton<<<dim3((max_n + 255) / 256, nc), 256, 0, st>>>(S.d_desc.p, S.bbox.p, S.keys.p, S.vals.p);
     count_launch(3);
+    D.mark(3, st);
     int bits = 48;
     while ((1 << (bits - 48)) < nc) bits++;
     cub::DoubleBuffer<unsigned long long> dk(S.keys.p, S.keys_alt.p);
@@ -211,10 +293,13 @@ static int build_clouds(const std::vector<Cloud*>& clouds) {
     order = dv.Current();
     keys_sorted = dk.Current();
   }
+  D.mark(4, st);
   k_gather_tiles<<<dim3((max_tiles_pad * 32 + 127) / 128, nc), 128, 0, st>>>(S.d_desc.p, order, keys_sorted);
   k_super_boxes<<<dim3((max_super_pad * 32 + 127) / 128, nc), 128, 0, st>>>(S.d_desc.p);
   count_launch(2);
   MR_CUDA(cudaGetLastError());
+  D.mark(5, st);
+  D.collect();
   for (Cloud* c : todo) c->built = true;
   return MRSLAM_OK;
 }
@@ -524,7 +609,7 @@ static int compute_covariances(Gicp** hs, int n, int which = 3) {
     p.stat_pairs = S.stats ? S.d_stat.p : nullptr;
     S.h_knn.p[pos++] = p;
   }
-  MR_CUDA(cudaMemcpyAsync(S.d_knn.p, S.h_knn.p, sizeof(KnnParams) * todo.size(), cudaMemcpyHostToDevice, rt().stream));
+  MR_CUDA(upload_params(S.d_knn.p, S.h_knn.p, sizeof(KnnParams) * todo.size(), rt().stream));
   MR_CHECK(S.knn_fence.mark(rt().stream));
   size_t i0 = 0;
   while (i0 < order.size()) {
@@ -583,9 +668,9 @@ static int run_linearize(Gicp** hs, const std::vector<int>& ids) {
   }
   // whole descriptor table + active list (small): one async copy each
   int nmax = *std::max_element(ids.begin(), ids.end()) + 1;
-  MR_CUDA(cudaMemcpyAsync(S.d_pairs.p, S.h_pairs.p, sizeof(PairParams) * nmax, cudaMemcpyHostToDevice, st));
-  MR_CUDA(cudaMemcpyAsync(S.d_active.p, S.h_active.p, sizeof(int) * na, cudaMemcpyHostToDevice, st));
-  MR_CUDA(cudaMemcpyAsync(S.d_T.p, S.h_T.p, sizeof(double) * 12 * nmax, cudaMemcpyHostToDevice, st));
+  MR_CUDA(upload_params(S.d_pairs.p, S.h_pairs.p, sizeof(PairParams) * nmax, st));
+  MR_CUDA(upload_params(S.d_active.p, S.h_active.p, sizeof(int) * na, st));
+  MR_CUDA(upload_params(S.d_T.p, S.h_T.p, sizeof(double) * 12 * nmax, st));
   if (maxt > 0) {
     dim3 grid((maxt + 3) / 4, na);
     {
@@ -624,10 +709,10 @@ static int run_error(Gicp** hs, const std::vector<int>& ids) {
     S.h_out.p[(size_t)ids[a] * NRED + 27] = 0.0;
     hs[ids[a]]->n_error++;
   }
-  MR_CUDA(cudaMemcpyAsync(S.d_active.p, S.h_active.p, sizeof(int) * na, cudaMemcpyHostToDevice, st));
+  MR_CUDA(upload_params(S.d_active.p, S.h_active.p, sizeof(int) * na, st));
   {
     int nmax = *std::max_element(ids.begin(), ids.end()) + 1;
-    MR_CUDA(cudaMemcpyAsync(S.d_T.p, S.h_T.p, sizeof(double) * 12 * nmax, cudaMemcpyHostToDevice, st));
+    MR_CUDA(upload_params(S.d_T.p, S.h_T.p, sizeof(double) * 12 * nmax, st));
   }
   if (maxt > 0) {
     dim3 grid((maxt + 3) / 4, na);
@@ -821,9 +906,9 @@ static int fitness_batch(Gicp** hs, int n, double max_range, double* out) {
     S.h_out.p[(size_t)i * NRED] = 0;
     S.h_out.p[(size_t)i * NRED + 1] = 0;
   }
-  MR_CUDA(cudaMemcpyAsync(S.d_pairs.p, S.h_pairs.p, sizeof(PairParams) * n, cudaMemcpyHostToDevice, st));
-  MR_CUDA(cudaMemcpyAsync(S.d_active.p, S.h_active.p, sizeof(int) * n, cudaMemcpyHostToDevice, st));
-  MR_CUDA(cudaMemcpyAsync(S.d_T.p, S.h_T.p, sizeof(double) * 12 * n, cudaMemcpyHostToDevice, st));
+  MR_CUDA(upload_params(S.d_pairs.p, S.h_pairs.p, sizeof(PairParams) * n, st));
+  MR_CUDA(upload_params(S.d_active.p, S.h_active.p, sizeof(int) * n, st));
+  MR_CUDA(upload_params(S.d_T.p, S.h_T.p, sizeof(double) * 12 * n, st));
   if (maxt > 0) {
     dim3 grid((maxt + 3) / 4, n);
     k_nn1_search<MODE_FITNESS><<<grid, 128, 0, st>>>(S.d_pairs.p, S.d_active.p, S.d_T.p, max_range, S.stats ? S.d_stat.p : nullptr);
@@ -921,7 +1006,7 @@ int mrslam_cloud_create_device_batch(const float* const* d_xyz, const int* n, in
   }
   if (max_n > 0) {
     ProfScope ps(PROF_CLOUD_BUILD);
-    MR_CUDA(cudaMemcpyAsync(d_desc.p, h_desc.p, sizeof(PackDesc) * count, cudaMemcpyHostToDevice, rt().stream));
+    MR_CUDA(upload_params(d_desc.p, h_desc.p, sizeof(PackDesc) * count, rt().stream));
     MR_CHECK(fence.mark(rt().stream));
     int gx = std::max(1, std::min((max_n + 255) / 256, 128));
     k_pack_points_batch<<<dim3(gx, count), 256, 0, rt().stream>>>(d_desc.p);
@@ -965,7 +1050,7 @@ int mrslam_cloud_knn(mrslam_cloud_t* h, int k, int* idx_out, float* sqd_out) {
   p.ntiles = c->ntiles; p.ntiles_pad = c->ntiles_pad; p.nsuper = c->nsuper; p.nsuper_pad = c->nsuper_pad; p.k = k; p.reg = 0;
   p.cov = nullptr; p.knn_idx = di.p; p.knn_sqd = dd.p; p.stat_pairs = nullptr;
   S.h_knn.p[0] = p;
-  MR_CUDA(cudaMemcpyAsync(S.d_knn.p, S.h_knn.p, sizeof(KnnParams), cudaMemcpyHostToDevice, rt().stream));
+  MR_CUDA(upload_params(S.d_knn.p, S.h_knn.p, sizeof(KnnParams), rt().stream));
   MR_CHECK(dispatch_knn(k, S.d_knn.p, 1, c->ntiles, false));
   if (c->n > 0) {
     MR_CUDA(cudaMemcpyAsync(idx_out, di.p, sizeof(int) * (size_t)c->n * k, cudaMemcpyDeviceToHost, rt().stream));
@@ -1014,7 +1099,7 @@ int mrslam_ringpp_build_neighbors(const float* xyz, int n, int stride_floats, in
     p.ntiles = c->ntiles; p.ntiles_pad = c->ntiles_pad; p.nsuper = c->nsuper; p.nsuper_pad = c->nsuper_pad; p.k = k; p.reg = 0;
     p.cov = nullptr; p.knn_idx = di.p; p.knn_sqd = nullptr; p.stat_pairs = nullptr;
     S.h_knn.p[0] = p;
-    MR_CUDA(cudaMemcpyAsync(S.d_knn.p, S.h_knn.p, sizeof(KnnParams), cudaMemcpyHostToDevice, rt().stream));
+    MR_CUDA(upload_params(S.d_knn.p, S.h_knn.p, sizeof(KnnParams), rt().stream));
     MR_CHECK(S.knn_fence.mark(rt().stream));
     MR_CHECK(dispatch_knn(k, S.d_knn.p, 1, c->ntiles, false));
     float* cov = dout.p;
@@ -1369,7 +1454,7 @@ int mrslam_gicp_compute_error(mrslam_gicp_t* h, const double* T16, double* cost)
   T16_to_iso(T16, x);
   BatchScratch& S = scratch();
   S.h_pairs.p[0] = make_pair_params(g);
-  MR_CUDA(cudaMemcpyAsync(S.d_pairs.p, S.h_pairs.p, sizeof(PairParams), cudaMemcpyHostToDevice, rt().stream));
+  MR_CUDA(upload_params(S.d_pairs.p, S.h_pairs.p, sizeof(PairParams), rt().stream));
   iso_to_T12(x, S.h_T.p);
   std::vector<int> ids(1, 0);
   MR_CHECK(run_error(arr, ids));
@@ -1407,6 +1492,7 @@ int mrslam_gicp_debug_last_correspondences(mrslam_gicp_t* h, int* corr, float* s
 }
 
 // instrumentation used by bench.py's roofline block: number of distance evaluations since the last reset
+void mrslam_build_diag_dump(const char* label) { build_diag().dump(label); }
 int mrslam_gicp_stats_enable(int on) {
   MR_CHECK(ensure_init());
   LOCK();

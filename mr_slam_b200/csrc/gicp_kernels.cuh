@@ -72,7 +72,20 @@ struct BuildDesc {
   float* qp;  // [4] quantisation frame of the Morton keys: min x,y,z and scale (kept for Morton look-ups)
   int n, ntiles, ntiles_pad, nsuper_pad;
   long long offset;  // position of this cloud's keys in the concatenated sort arrays
+  const float* raw;  // != nullptr: a host upload (xyz with raw_stride floats per point) still to be unpacked into porig
+  int raw_stride;
 };
+
+// unpack the pending host uploads of a batch (blockIdx.y = cloud): one launch, in front of the build kernels
+__global__ void k_pack_pending(const BuildDesc* __restrict__ descs) {
+  const BuildDesc d = descs[blockIdx.y];
+  if (!d.raw) return;
+  float4* porig = const_cast<float4*>(d.porig);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < d.n; i += gridDim.x * blockDim.x) {
+    const float* p = d.raw + (size_t)i * d.raw_stride;
+    porig[i] = make_float4(p[0], p[1], p[2], 1.0f);
+  }
+}
 
 __global__ void k_bbox_init(unsigned* bb, int nclouds) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -130,10 +143,14 @@ __device__ __forceinline__ unsigned long long spread16(unsigned v) {  // 16 bits
 #ifndef MR_HILBERT
 #define MR_HILBERT 1
 #endif
-// The batched radix sort skips the lowest KEY_DROP_BITS bits of the curve key (2 per axis: cells of extent/2^14, ~1 cm for
-// a 200 m scan) so that (cloud id | key) fits six 8-bit passes instead of seven; ties keep input order (stable sort).  Any
-// order is correct for the exact searches -- the curve only makes tiles compact.
-constexpr int KEY_DROP_BITS = 6;
+// The batched radix sort skips the lowest KEY_DROP_BITS bits of the curve key (4 per axis: cells of extent/2^12, ~5 cm for
+// a 200 m scan) so that (cloud id | key) fits FIVE 8-bit passes; ties keep input order (stable sort).  Any order is correct for
+// the exact searches -- the curve only makes tiles compact; measured with 6 (six passes) against 12 dropped bits: cloud build
+// 0.413 -> 0.384 ms per 16 clouds, kNN / NN-1 times unchanged (gpurun_out/r2y).
+#ifndef MR_KEY_DROP_BITS
+#define MR_KEY_DROP_BITS 12
+#endif
+constexpr int KEY_DROP_BITS = MR_KEY_DROP_BITS;
 constexpr unsigned long long KEY48_SORTED_MASK = 0xffffffffffffull & ~((1ull << KEY_DROP_BITS) - 1ull);
 // 48-bit space-filling-curve key of a point in the cloud's bounding cube (16 bits per axis): Hilbert order (Skilling's
 // axes-to-transpose transform + bit interleave) keeps 32 consecutive points in tighter boxes than Morton order does.
@@ -644,6 +661,54 @@ __device__ __forceinline__ u64 warp_query_knn(const KnnParams& P, float qx, floa
   return my_key;
 }
 
+// ---- two queries per warp (k <= 16): each 16-lane half keeps the k-best list of its own query -------------------------------
+// ascending (DESC = false) or descending sort of one key per lane inside each 16-lane half (xor masks < 16 never cross halves)
+template <bool DESC>
+__device__ __forceinline__ u64 half_sort_keys(u64 key, int l16) {
+#pragma unroll
+  for (int size = 2; size <= 16; size <<= 1) {
+    {
+      const u64 other = __shfl_xor_sync(FULL, key, size - 1);
+      const bool low = ((l16 & (size >> 1)) == 0) != DESC;
+      key = ((key < other) == low) ? key : other;
+    }
+#pragma unroll
+    for (int stride = size >> 2; stride > 0; stride >>= 1) {
+      const u64 other = __shfl_xor_sync(FULL, key, stride);
+      const bool low = ((l16 & stride) == 0) != DESC;
+      key = ((key < other) == low) ? key : other;
+    }
+  }
+  return key;
+}
+// bitonic sequence of 16 keys per half -> ascending
+__device__ __forceinline__ u64 half_merge_keys(u64 key, int l16) {
+#pragma unroll
+  for (int stride = 8; stride > 0; stride >>= 1) {
+    const u64 other = __shfl_xor_sync(FULL, key, stride);
+    const bool low = (l16 & stride) == 0;
+    key = ((key < other) == low) ? key : other;
+  }
+  return key;
+}
+// position of the highest set bit (-1 if none): one FLO
+__device__ __forceinline__ int top_bit(unsigned v) {
+  int r;
+  asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(v));
+  return r;
+}
+// 1 << s with PTX semantics (s >= 32, e.g. (unsigned)-1, gives 0)
+__device__ __forceinline__ unsigned bit_clamp(int s) {
+  unsigned r;
+  asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(1u), "r"(s));
+  return r;
+}
+__device__ __forceinline__ unsigned half_min_u32(unsigned v) {
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(FULL, v, o));
+  return v;
+}
+
 __device__ __forceinline__ void knn_write_warp_list(const KnnParams& P, u64 my_key, size_t spos, int qidx, int k, int lane) {
   if (lane < k) {
     const int my_i = key_idx(my_key);
@@ -672,12 +737,26 @@ constexpr int KCAND = 64;
 #ifndef MR_KNN_MINBLK
 #define MR_KNN_MINBLK 8
 #endif
+#ifndef MR_KNN_PAIR
+#define MR_KNN_PAIR 1
+#endif
+#ifndef MR_KNN_UNIFORM_ROUNDS
+#define MR_KNN_UNIFORM_ROUNDS 1
+#endif
+#ifndef MR_KNN_INS_UNROLL
+#define MR_KNN_INS_UNROLL 2
+#endif
+#define MR_PRAGMA_(x) _Pragma(#x)
+#define MR_UNROLL(n) MR_PRAGMA_(unroll n)
 #ifndef MR_KNN_MIRRORSORT
 #define MR_KNN_MIRRORSORT 1  // 6 instead of 7 instructions per compare-exchange step (SASS), 15 steps per query
 #endif
 template <bool STATS>
 __global__ void __launch_bounds__(128, MR_KNN_MINBLK) k_knn_search(const KnnParams* __restrict__ plist, int only_flagged) {
   __shared__ int s_list[4][KCAND];
+#if MR_KNN_PAIR
+  __shared__ float4 s_own[4][TILE];
+#endif
   const KnnParams P = plist[blockIdx.y];
   // second pass behind k_knn_search_v2: only the tiles it flagged (one flag per tile; warp-uniform exit further down)
   if (only_flagged && blockIdx.x * (blockDim.x >> 5) >= P.ntiles) return;
@@ -732,6 +811,102 @@ __global__ void __launch_bounds__(128, MR_KNN_MINBLK) k_knn_search(const KnnPara
     }
     __syncwarp();
   }
+#if MR_KNN_PAIR
+  if (shared_ok && k <= 16 && ncand <= 32) {
+    // TWO queries at a time, one per 16-lane half (k <= 16 list entries fit a half).  Every warp-wide instruction of the walk --
+    // the sorting network, the box tests, the candidate visit, each insertion round -- now serves two queries; a half that has
+    // finished its walk (or has no qualifier left in an insertion round) idles while the other one completes.  A candidate tile
+    // is visited as two points per lane; qualifiers are inserted in (lane, then second element) order, which does not matter for
+    // the final list (exact sorted insertion of distinct keys).
+    const int ntp = P.ntiles_pad;
+    const int l16 = lane & 15, h16 = lane & 16;
+    s_own[wib][lane] = qmine;
+    const int t0 = (l16 < ncand) ? s_list[wib][l16] : -1;
+    const int t1 = (l16 + 16 < ncand) ? s_list[wib][l16 + 16] : -1;
+    float b0[6], b1[6];
+#pragma unroll
+    for (int c = 0; c < 6; c++) {
+      b0[c] = (t0 >= 0) ? P.tb[(size_t)c * ntp + t0] : 0.0f;
+      b1[c] = (t1 >= 0) ? P.tb[(size_t)c * ntp + t1] : 0.0f;
+    }
+    __syncwarp();
+    constexpr unsigned NONE = 0xffffffffu;
+#pragma unroll 1
+    for (int qp = 0; qp < TILE / 2; qp++) {
+      const int qi = 2 * qp + (lane >> 4);
+      const float4 q = s_own[wib][qi];
+      const float qx = q.x, qy = q.y, qz = q.z;
+      u64 my_key;
+      {  // own tile: 16 smallest of its 32 keys, ascending (half-cleaner of an ascending and a descending run, then a merge)
+        const float4 pa = s_own[wib][l16], pb = s_own[wib][l16 + 16];
+        const u64 ka = half_sort_keys<false>(make_key(dist2(qx, qy, qz, pa.x, pa.y, pa.z), __float_as_int(pa.w)), l16);
+        const u64 kb = half_sort_keys<true>(make_key(dist2(qx, qy, qz, pb.x, pb.y, pb.z), __float_as_int(pb.w)), l16);
+        my_key = half_merge_keys(ka < kb ? ka : kb, l16);
+      }
+      u64 wkey = __shfl_sync(FULL, my_key, h16 + k - 1);
+      if (STATS) tiles_done++;
+      unsigned c0 = NONE, c1 = NONE;
+      if (t0 >= 0) {
+        const float gx = fmaxf(0.0f, fmaxf(b0[0] - qx, qx - b0[3])), gy = fmaxf(0.0f, fmaxf(b0[1] - qy, qy - b0[4])),
+                    gz = fmaxf(0.0f, fmaxf(b0[2] - qz, qz - b0[5]));
+        c0 = (__float_as_uint(gx * gx + gy * gy + gz * gz) & ~63u) | (unsigned)l16;
+      }
+      if (t1 >= 0) {
+        const float gx = fmaxf(0.0f, fmaxf(b1[0] - qx, qx - b1[3])), gy = fmaxf(0.0f, fmaxf(b1[1] - qy, qy - b1[4])),
+                    gz = fmaxf(0.0f, fmaxf(b1[2] - qz, qz - b1[5]));
+        c1 = (__float_as_uint(gx * gx + gy * gy + gz * gz) & ~63u) | (unsigned)(16 + l16);
+      }
+      bool active = true;  // uniform inside a half
+      while (true) {
+        const unsigned m = half_min_u32(min(c0, c1));
+        active = active && m != NONE && !(__uint_as_float(m & ~63u) * CULL_SAFETY > key_dist(wkey));
+        if (!__any_sync(FULL, active)) break;
+        u64 x0 = KEY_NONE, x1 = KEY_NONE;
+        if (active) {
+          const int slot = (int)(m & 63u);
+          const int t = s_list[wib][slot];
+          if (slot == l16) c0 = NONE;
+          if (slot == l16 + 16) c1 = NONE;
+          const float4 p0 = P.psort[(size_t)t * TILE + l16], p1 = P.psort[(size_t)t * TILE + 16 + l16];
+          x0 = make_key(dist2(qx, qy, qz, p0.x, p0.y, p0.z), __float_as_int(p0.w));
+          x1 = make_key(dist2(qx, qy, qz, p1.x, p1.y, p1.z), __float_as_int(p1.w));
+          if (STATS) tiles_done++;
+        }
+        const unsigned q0 = __ballot_sync(FULL, x0 < wkey), q1 = __ballot_sync(FULL, x1 < wkey);
+        unsigned mm = ((q0 >> h16) & 0xffffu) | (((q1 >> h16) & 0xffffu) << 16);  // the qualifiers of MY half's tile
+        // insertion rounds: as many as the busier half has qualifiers (a warp-uniform count from a warp reduction, so the loop
+        // needs no convergence checks and unrolls)
+        const int rounds = (int)__reduce_max_sync(FULL, (unsigned)__popc(mm));
+        MR_UNROLL(MR_KNN_INS_UNROLL)
+        for (int it = 0; it < rounds; it++) {
+          const bool on = mm != 0u;  // an idle half inserts nothing
+          const int j = top_bit(mm);  // highest qualifier first (-1 when idle)
+          mm &= ~bit_clamp(j);
+          const u64 ck = __shfl_sync(FULL, (j & 16) ? x1 : x0, h16 | (j & 15));
+          const u64 up = __shfl_up_sync(FULL, my_key, 1, 16);
+          if (on && ck < my_key) my_key = (l16 > 0 && ck < up) ? up : ck;
+          if (STATS && on) inserts++;
+        }
+        wkey = __shfl_sync(FULL, my_key, h16 + k - 1);
+      }
+      if (l16 < k) {
+        const size_t spos = (size_t)qt * TILE + qi;
+        const int qidx = __float_as_int(q.w);
+        const int my_i = key_idx(my_key);
+        P.ids[spos * k + l16] = my_i;
+        if (P.knn_idx) {
+          const bool real = my_i != PAD_IDX;
+          P.knn_idx[(size_t)qidx * k + l16] = real ? my_i : -1;
+          if (P.knn_sqd) P.knn_sqd[(size_t)qidx * k + l16] = real ? key_dist(my_key) : INFINITY;
+        }
+      }
+    }
+    if (STATS) {  // fold the upper half's counters into lane 0
+      tiles_done += __shfl_sync(FULL, tiles_done, 16);
+      inserts += __shfl_sync(FULL, inserts, 16);
+    }
+  } else
+#endif
   if (shared_ok) {
     const int ntp = P.ntiles_pad;
     const int t0 = (lane < ncand) ? s_list[wib][lane] : -1;
@@ -779,9 +954,18 @@ __global__ void __launch_bounds__(128, MR_KNN_MINBLK) k_knn_search(const KnnPara
         const u64 ckey = make_key(dist2(qx, qy, qz, c.x, c.y, c.z), __float_as_int(c.w));
         unsigned mm = __ballot_sync(FULL, ckey < wkey);
         if (mm) {
+#if MR_KNN_UNIFORM_ROUNDS
+          // the round count comes out of a warp reduction, i.e. in a uniform register: no convergence check per round, unrollable
+          const int rounds = (int)__reduce_max_sync(FULL, (unsigned)__popc(mm));
+          MR_UNROLL(MR_KNN_INS_UNROLL)
+          for (int it = 0; it < rounds; it++) {
+            const int j = top_bit(mm);
+            mm ^= 1u << j;
+#else
           while (mm) {
             const int j = __ffs(mm) - 1;
             mm &= mm - 1;
+#endif
             const u64 ck = __shfl_sync(FULL, ckey, j);
             const u64 up = __shfl_up_sync(FULL, my_key, 1);
             if (ck < my_key) my_key = (lane > 0 && ck < up) ? up : ck;
@@ -1340,6 +1524,15 @@ constexpr int NN1_STAGE = 16;  // candidate tiles staged in shared memory per wa
 #ifndef MR_NN1_NEEDTEST
 #define MR_NN1_NEEDTEST 1
 #endif
+#ifndef MR_NN1_KEY32
+#define MR_NN1_KEY32 1
+#endif
+#ifndef MR_NN1_PREFETCH
+#define MR_NN1_PREFETCH 0
+#endif
+#ifndef MR_NN1_SCAN_UNROLL
+#define MR_NN1_SCAN_UNROLL 4
+#endif
 __device__ __forceinline__ u64 f2_pack(float lo, float hi) {
   u64 r;
   asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
@@ -1547,7 +1740,7 @@ __global__ void __launch_bounds__(128) k_nn1_search(const PairParams* __restrict
       s_tw[wib][lane] = __float_as_int(c.w);
       __syncwarp();
       float bd = key_dist(bkey);
-#pragma unroll 4
+      MR_UNROLL(MR_NN1_SCAN_UNROLL)
       for (int g = 0; g < TILE / 4; g++) {
         const ulonglong2 X = reinterpret_cast<const ulonglong2*>(s_tx[wib])[g], Y = reinterpret_cast<const ulonglong2*>(s_ty[wib])[g],
                          Z = reinterpret_cast<const ulonglong2*>(s_tz[wib])[g];
@@ -1743,18 +1936,48 @@ __global__ void __launch_bounds__(128) k_nn1_search(const PairParams* __restrict
         // makes the stop test more conservative -- so one warp min-reduction picks the next tile.  The tile after the current one is
         // picked, and its row fetched, BEFORE the current one is scanned (the order does not depend on the scan), so the global load
         // overlaps ~180 instructions of scanning instead of stalling the warp at the head of every tile.
+#if MR_NN1_KEY32
         constexpr unsigned NONE32 = 0xffffffffu;
         unsigned k0 = lane < n ? (((unsigned)(s_cand[wib][lane] >> 32) & ~63u) | (unsigned)lane) : NONE32;
         unsigned k1 = lane + 32 < n ? (((unsigned)(s_cand[wib][lane + 32] >> 32) & ~63u) | (unsigned)(lane + 32)) : NONE32;
-        auto pick = [&](unsigned& key, int& t) -> bool {  // removes the nearest remaining candidate from the list
-          key = __reduce_min_sync(FULL, min(k0, k1));
+        auto pick = [&](unsigned& dbits, int& t) -> bool {  // removes the nearest remaining candidate from the list
+          const unsigned key = __reduce_min_sync(FULL, min(k0, k1));
           if (key == NONE32) return false;
           const int slot = (int)(key & 63u);
           if (slot == lane) k0 = NONE32;
           if (slot == lane + 32) k1 = NONE32;
           t = (int)(unsigned)(s_cand[wib][slot] & 0xffffffffull);
+          dbits = key & ~63u;
           return true;
         };
+#else
+        u64 e0 = lane < n ? s_cand[wib][lane] : KEY_NONE;
+        u64 e1 = lane + 32 < n ? s_cand[wib][lane + 32] : KEY_NONE;
+        auto pick = [&](unsigned& dbits, int& t) -> bool {
+          const u64 m = e0 < e1 ? e0 : e1;
+          const unsigned hi = (unsigned)(m >> 32);
+          const unsigned mhi = __reduce_min_sync(FULL, hi);
+          if (mhi >= 0x7f800000u) return false;  // list exhausted
+          const unsigned mlo = __reduce_min_sync(FULL, hi == mhi ? (unsigned)(m & 0xffffffffull) : 0xffffffffu);
+          const u64 pk = ((u64)mhi << 32) | mlo;
+          if (e0 == pk) e0 = KEY_NONE;
+          else if (e1 == pk) e1 = KEY_NONE;
+          dbits = mhi;
+          t = (int)mlo;
+          return true;
+        };
+#endif
+        auto needed = [&](int t) -> bool {
+#if MR_NN1_NEEDTEST
+          // The list was built from the box of ALL coherent queries; a tile near one corner of that box is often out of reach of
+          // every single query.  Scan it only if some coherent lane's own point-to-box distance is within its current best.
+          const float pbd = pt_box_dist2(qx, qy, qz, P.tgt_tb, ntp, t);
+          return __any_sync(FULL, coherent && pbd * CULL_SAFETY <= fminf(key_dist(bkey), cap));
+#else
+          return true;
+#endif
+        };
+#if MR_NN1_PREFETCH
         unsigned nkey;
         int nt = 0;
         bool have = pick(nkey, nt);
@@ -1765,20 +1988,21 @@ __global__ void __launch_bounds__(128) k_nn1_search(const PairParams* __restrict
           const int t = nt;
           const float4 c = cn;
           const float R = fminf(__uint_as_float(__reduce_max_sync(FULL, coherent ? __float_as_uint(key_dist(bkey)) : 0u)), cap);
-          if (__uint_as_float(ckey & ~63u) * CULL_SAFETY > R) break;
+          if (__uint_as_float(ckey) * CULL_SAFETY > R) break;
           have = pick(nkey, nt);
           if (have) cn = P.tgt_sort[(size_t)nt * TILE + lane];
-#if MR_NN1_NEEDTEST
-          {
-            // The list was built from the box of ALL coherent queries; a tile near one corner of that box is often out of reach of
-            // every single query.  Skip it unless some coherent lane's own point-to-box distance is within its current best.
-            const float pbd = pt_box_dist2(qx, qy, qz, P.tgt_tb, ntp, t);
-            const bool need = coherent && pbd * CULL_SAFETY <= fminf(key_dist(bkey), cap);
-            if (!__any_sync(FULL, need)) continue;
-          }
-#endif
-          scan_tile(c, t);
+          if (needed(t)) scan_tile(c, t);
         }
+#else
+        while (true) {
+          unsigned dbits;
+          int t;
+          if (!pick(dbits, t)) break;
+          const float R = fminf(__uint_as_float(__reduce_max_sync(FULL, coherent ? __float_as_uint(key_dist(bkey)) : 0u)), cap);
+          if (__uint_as_float(dbits) * CULL_SAFETY > R) break;
+          if (needed(t)) scan_tile(P.tgt_sort[(size_t)t * TILE + lane], t);
+        }
+#endif
 #endif
         // with an overflowing candidate list some tiles at distance >= dropped_min were never looked at:
         // coherent lanes whose best is not provably closer go to phase B
