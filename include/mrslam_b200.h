@@ -108,6 +108,10 @@ int mrslam_gicp_set_initial_lambda_factor(mrslam_gicp_t*, double f);  /* LsqRegi
 int mrslam_gicp_set_lsq_optimizer(mrslam_gicp_t*, int type);
 int mrslam_gicp_set_debug_print(mrslam_gicp_t*, int on);              /* LsqRegistration::setDebugPrint */
 
+/* Host input: the upload is only ENQUEUED (copy stream) by these calls and is waited for / unpacked when the cloud is first used
+ * (prepare / align).  From pageable memory -- what the reference's pcl clouds are -- the source buffer may be reused as soon as the
+ * call returns; a PAGE-LOCKED source buffer is read asynchronously and must stay unchanged until that first use has completed.
+ * Handing over the clouds of the next batch while the current one is being aligned is allowed and overlaps their uploads with it. */
 int mrslam_gicp_set_input_source(mrslam_gicp_t*, const float* xyz, int n, int stride_floats); /* setInputSource (host) */
 int mrslam_gicp_set_input_target(mrslam_gicp_t*, const float* xyz, int n, int stride_floats); /* setInputTarget (host) */
 /* share a device-resident cloud (and its cached covariances) between registrations; not owned by the handle */
