@@ -844,7 +844,7 @@ def run_cfg2(args):
                                    % KNN_WARP_INST_PER_QUERY),
             "cov": grp(["cov"], "cov", "hbm", 36.0 * q_knn, "GB/s", hbm_peak, note="36 B/pt/cloud (SURVEY 8d); FP64 eigen-solve dominated, see profiles/"),
             "nn1_search": grp(["nn1_search"], "nn1_search", "issue", NN1_WARP_INST_PER_QUERY * q_nn1, "Gwarp-inst/s", issue_peak,
-                              hbm_bytes=24.0 * q_nn1, note="%.0f warp-instructions per query" % NN1_WARP_INST_PER_QUERY),
+                              hbm_bytes=24.0 * q_nn1, note="%.0f warp-instructions per query; about a third of them are packed FADD2/FMUL2/FFMA2, which issue once but occupy the FP32 pipe for two cycles, so the issue fraction understates the pipe load of the tile scan" % NN1_WARP_INST_PER_QUERY),
             "linearize": grp(["linearize"], "linearize", "hbm", 100.0 * q_nn1, "GB/s", hbm_peak, note="100 B/pt/pass (SURVEY 8d)"),
             "error": grp(["error"], "error", "hbm", 52.0 * N_POINTS * p_err, "GB/s", hbm_peak, note="52 B/pt/eval"),
             "cloud_build": grp(["cloud_build"], "cloud_build", "hbm", (12.0 + 40.0 + 6 * 24.0) * q_knn, "GB/s", hbm_peak,
